@@ -1,0 +1,520 @@
+// api.cu -- the C ABI of libb200gs.so (include/b200gs.h): lifecycle, dataset upload, SVC search/refit.
+// Host-side planning only; every floating-point operation of the hot path runs in the CUDA kernels
+// of gram.cu / smo.cu / score.cu.  There is no CPU fallback.
+#include "common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <numeric>
+
+static std::string g_create_error;
+
+void gs_set_error(gs_handle *h, const std::string &msg)
+{
+    if (h) h->err = msg; else g_create_error = msg;
+}
+
+namespace {
+
+// dst[r][:] = src[perm[r]][:]; optionally also a float32 copy of a float64 source
+template <typename T>
+__global__ void gather_rows_kernel(const T *__restrict__ src, const int *__restrict__ perm, int64_t n, int64_t d,
+                                   T *__restrict__ dst, float *__restrict__ dst32)
+{
+    const int64_t total = n * d;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = idx / d, c = idx - r * d;
+        const T v = src[(int64_t)perm[r] * d + c];
+        dst[idx] = v;
+        if (dst32) dst32[idx] = (float)v;
+    }
+}
+
+struct EvTimer {       // accumulates elapsed ms between consecutive marks on one stream
+    cudaStream_t st;
+    std::vector<cudaEvent_t> evs;
+    std::vector<int> tag;
+    explicit EvTimer(cudaStream_t s) : st(s) {}
+    void mark(int t)
+    {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        evs.push_back(e); tag.push_back(t);
+    }
+    // after a stream sync: add the time between mark k-1 and mark k to acc[tag[k]]
+    void collect(float *acc, int ntags)
+    {
+        for (size_t k = 1; k < evs.size(); k++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, evs[k - 1], evs[k]);
+            if (tag[k] >= 0 && tag[k] < ntags) acc[tag[k]] += ms;
+        }
+        for (auto e : evs) cudaEventDestroy(e);
+        evs.clear(); tag.clear();
+    }
+};
+
+inline uint64_t dbits(double x) { uint64_t u; memcpy(&u, &x, 8); return u; }
+
+}  // namespace
+
+extern "C" {
+
+int gs_version(void) { return 100; }
+
+const char *gs_last_error(const gs_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int gs_create(int device, gs_handle **out)
+{
+    if (!out) return GS_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libb200gs has no CPU fallback)";
+        return GS_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) { g_create_error = "device index out of range"; return GS_ERR_ARG; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return GS_ERR_CUDA; }
+    if (prop.major != 10) {
+        g_create_error = "libb200gs is built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor);
+        return GS_ERR_UNSUPPORTED;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return GS_ERR_CUDA; }
+    gs_handle *h = new gs_handle();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e); delete h; return GS_ERR_CUDA;
+    }
+    memset(&h->prof, 0, sizeof h->prof);
+    *out = h;
+    return GS_OK;
+}
+
+void gs_destroy(gs_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    h->dX.release(); h->dY.release(); h->dFold.release(); h->dYt.release();
+    h->dS.release(); h->dXsq.release(); h->dK.release(); h->dX64.release();
+    for (auto &w : h->dWork) w.release();
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int gs_set_data(gs_handle *h, const void *X, int32_t x_dtype, int64_t n, int64_t d, const int32_t *y_class,
+                const float *y_target, const int8_t *fold_id, int32_t n_splits)
+{
+    if (!h) return GS_ERR_ARG;
+    if (!X || n <= 0 || d <= 0 || !fold_id || n_splits < 1 || (!y_class && !y_target) ||
+        (x_dtype != GS_F32 && x_dtype != GS_F64)) {
+        gs_set_error(h, "gs_set_data: bad arguments"); return GS_ERR_ARG;
+    }
+    if (n > 65535) { gs_set_error(h, "gs_set_data: n > 65535 rows is outside the small-dense-data scope of this engine"); return GS_ERR_UNSUPPORTED; }
+    GS_CUDA(cudaSetDevice(h->device));
+    h->n = n; h->d = d; h->n_splits = n_splits; h->x_dtype = x_dtype;
+    h->classification = y_class != nullptr;
+    h->perm.resize(n);
+    std::iota(h->perm.begin(), h->perm.end(), 0);
+    h->n_classes = 0;
+    if (y_class) {
+        for (int64_t i = 0; i < n; i++) {
+            if (y_class[i] < 0) { gs_set_error(h, "gs_set_data: negative class id"); return GS_ERR_ARG; }
+            h->n_classes = std::max(h->n_classes, y_class[i] + 1);
+        }
+        // internal order: by class, then original index -- makes every one-vs-one sub-problem a
+        // (nearly) contiguous column range of the kernel matrix, so SMO row gathers coalesce
+        std::stable_sort(h->perm.begin(), h->perm.end(), [&](int a, int b) { return y_class[a] < y_class[b]; });
+    }
+    h->yc.assign(n, 0); h->fold.resize(n);
+    h->class_start.assign(h->n_classes + 1, 0);
+    for (int64_t i = 0; i < n; i++) {
+        const int o = h->perm[i];
+        if (y_class) { h->yc[i] = y_class[o]; h->class_start[y_class[o] + 1]++; }
+        h->fold[i] = fold_id[o];
+        if (fold_id[o] >= n_splits) { gs_set_error(h, "gs_set_data: fold id >= n_splits"); return GS_ERR_ARG; }
+    }
+    for (int c = 0; c < h->n_classes; c++) h->class_start[c + 1] += h->class_start[c];
+
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, h->stream);
+    const size_t esz = x_dtype == GS_F64 ? 8 : 4;
+    GS_CUDA(h->dX.reserve((size_t)n * d * 4));
+    if (x_dtype == GS_F64) GS_CUDA(h->dX64.reserve((size_t)n * d * 8));
+    GS_CUDA(h->dWork[0].reserve((size_t)n * d * esz));
+    GS_CUDA(h->dWork[1].reserve((size_t)n * 4));
+    GS_CUDA(h->dY.reserve((size_t)n * 4));
+    GS_CUDA(h->dFold.reserve((size_t)n));
+    GS_CUDA(h->dYt.reserve((size_t)n * 4));
+    GS_CUDA(cudaMemcpyAsync(h->dWork[0].p, X, (size_t)n * d * esz, cudaMemcpyHostToDevice, h->stream));
+    GS_CUDA(cudaMemcpyAsync(h->dWork[1].p, h->perm.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    if (x_dtype == GS_F64)
+        gather_rows_kernel<double><<<h->sm_count * 8, 256, 0, h->stream>>>(h->dWork[0].as<double>(), h->dWork[1].as<int>(), n, d,
+                                                                           h->dX64.as<double>(), h->dX.as<float>());
+    else
+        gather_rows_kernel<float><<<h->sm_count * 8, 256, 0, h->stream>>>(h->dWork[0].as<float>(), h->dWork[1].as<int>(), n, d,
+                                                                          h->dX.as<float>(), nullptr);
+    GS_CUDA(cudaGetLastError());
+    GS_CUDA(cudaMemcpyAsync(h->dY.p, h->yc.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    GS_CUDA(cudaMemcpyAsync(h->dFold.p, h->fold.data(), (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    if (y_target) {
+        std::vector<float> yt(n);
+        for (int64_t i = 0; i < n; i++) yt[i] = y_target[h->perm[i]];
+        GS_CUDA(cudaMemcpyAsync(h->dYt.p, yt.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+        GS_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    cudaEventRecord(e1, h->stream);
+    GS_CUDA(cudaStreamSynchronize(h->stream));
+    cudaEventElapsedTime(&h->prof.ms_h2d, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    h->prof.h2d_bytes = (int64_t)n * d * (int64_t)esz + n * 9;
+    return GS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SVC: shared implementation of gs_svc (folds) and gs_svc_refit (all rows train).
+// ------------------------------------------------------------------------------------------------
+static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double *Cv, const double *gamma,
+                   double tol, int max_iter, uint32_t flags, bool refit,
+                   double *test_scores, double *train_scores, int32_t *n_iter, int32_t *n_sv,
+                   float *fit_ms, float *score_ms, double *pair_coef, double *rho_out, int32_t *pair_iter)
+{
+    if (!h) return GS_ERR_ARG;
+    if (h->n == 0) { gs_set_error(h, "gs_svc: no dataset (call gs_set_data first)"); return GS_ERR_NO_DATA; }
+    if (!h->classification) { gs_set_error(h, "gs_svc: dataset has no class labels"); return GS_ERR_ARG; }
+    if (h->n_classes < 2 || h->n_classes > 32) { gs_set_error(h, "gs_svc: need 2..32 classes"); return GS_ERR_UNSUPPORTED; }
+    if (flags & GS_GRAM_TENSOR) { gs_set_error(h, "gs_svc: GS_GRAM_TENSOR is not available in this build"); return GS_ERR_UNSUPPORTED; }
+    if (n_cand <= 0 || !kernel || !Cv || !gamma) { gs_set_error(h, "gs_svc: bad arguments"); return GS_ERR_ARG; }
+    GS_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int n = (int)h->n, d = (int)h->d, nc = h->n_classes;
+    const int n_splits = refit ? 1 : h->n_splits;
+    const int n_pairs = nc * (nc - 1) / 2;
+    const int n_tasks = n_cand * n_splits;
+    const int64_t ldk = ((int64_t)n + 31) & ~31LL;
+    for (int c = 0; c < n_cand; c++) {
+        if (kernel[c] != GS_KERNEL_LINEAR && kernel[c] != GS_KERNEL_RBF) { gs_set_error(h, "gs_svc: unsupported kernel id"); return GS_ERR_UNSUPPORTED; }
+        if (!(Cv[c] > 0)) { gs_set_error(h, "gs_svc: C must be > 0"); return GS_ERR_ARG; }
+    }
+
+    gs_profile &pf = h->prof;
+    const float keep_h2d = pf.ms_h2d; const int64_t keep_h2d_bytes = pf.h2d_bytes;
+    memset(&pf, 0, sizeof pf);
+    pf.ms_h2d = keep_h2d; pf.h2d_bytes = keep_h2d_bytes;
+    float acc[5] = {0, 0, 0, 0, 0};   // 0 gram, 1 kernel matrix, 2 solve, 3 score, 4 other
+    EvTimer tm(st);
+    cudaEvent_t ev_begin, ev_end;
+    cudaEventCreate(&ev_begin); cudaEventCreate(&ev_end);
+    cudaEventRecord(ev_begin, st);
+    tm.mark(-1);
+
+    // ---- 1. float64 Gram (shared by every candidate, fold and pair) ----
+    GS_CUDA(h->dS.reserve((size_t)n * n * 8));
+    GS_CUDA(h->dXsq.reserve((size_t)n * 8));
+    GS_CUDA(launch_gram_f64(h->x_dtype == GS_F64 ? h->dX64.p : h->dX.p, h->x_dtype, n, d, h->dS.as<double>(), h->dXsq.as<double>(), st));
+    pf.launches++;
+    pf.gram_flops = 2.0 * n * (double)n * d;
+    pf.gram_bytes = (double)n * d * 4 + (double)n * n * 8;
+    tm.mark(0);
+
+    // ---- 2. sub-problem row lists per (fold, pair): class a rows then class b rows, train rows only ----
+    std::vector<int> rows_all;
+    std::vector<int> sp_off((size_t)n_splits * n_pairs + 1, 0), sp_npos((size_t)n_splits * n_pairs, 0);
+    int lmax = 0;
+    for (int k = 0; k < n_splits; k++) {
+        int p = 0;
+        for (int a = 0; a < nc; a++)
+            for (int b = a + 1; b < nc; b++, p++) {
+                const size_t s = (size_t)k * n_pairs + p;
+                sp_off[s] = (int)rows_all.size();
+                for (int r = h->class_start[a]; r < h->class_start[a + 1]; r++)
+                    if (refit || h->fold[r] != k) rows_all.push_back(r);
+                sp_npos[s] = (int)rows_all.size() - sp_off[s];
+                for (int r = h->class_start[b]; r < h->class_start[b + 1]; r++)
+                    if (refit || h->fold[r] != k) rows_all.push_back(r);
+                const int l = (int)rows_all.size() - sp_off[s];
+                if (sp_npos[s] == 0 || sp_npos[s] == l) {
+                    gs_set_error(h, "gs_svc: a training fold lacks one of the classes"); return GS_ERR_ARG;
+                }
+                lmax = std::max(lmax, l);
+            }
+    }
+    sp_off.back() = (int)rows_all.size();
+    if (lmax > smo_max_rows()) {
+        gs_set_error(h, "gs_svc: sub-problem with " + std::to_string(lmax) + " rows exceeds the resident-state SMO kernel limit of " +
+                            std::to_string(smo_max_rows()));
+        return GS_ERR_UNSUPPORTED;
+    }
+
+    // ---- 3. group tasks by kernel matrix (kernel, gamma) ----
+    std::map<std::pair<int, uint64_t>, int> gmap;
+    std::vector<std::pair<int, double>> groups;         // (kernel, gamma)
+    std::vector<int> task_group(n_tasks);
+    for (int c = 0; c < n_cand; c++)
+        for (int k = 0; k < n_splits; k++) {
+            const double g = kernel[c] == GS_KERNEL_RBF ? gamma[(size_t)c * n_splits + k] : 0.0;
+            if (kernel[c] == GS_KERNEL_RBF && !(g > 0) ) { gs_set_error(h, "gs_svc: gamma must be > 0"); return GS_ERR_ARG; }
+            auto key = std::make_pair((int)kernel[c], dbits(g));
+            auto it = gmap.find(key);
+            if (it == gmap.end()) { it = gmap.emplace(key, (int)groups.size()).first; groups.emplace_back(kernel[c], g); }
+            task_group[(size_t)c * n_splits + k] = it->second;
+        }
+    const int n_groups = (int)groups.size();
+    std::vector<std::vector<int>> group_tasks(n_groups);
+    for (int t = 0; t < n_tasks; t++) group_tasks[task_group[t]].push_back(t);
+
+    // ---- 4. memory plan: kernel matrices are processed in batches that fit in free HBM ----
+    size_t free_b = 0, total_b = 0;
+    GS_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    free_b += h->dK.cap;
+    const size_t kbytes = (size_t)n * ldk * 4;
+    size_t budget = (size_t)(free_b * 0.6);
+    int gpb = (int)std::max<size_t>(1, std::min<size_t>(n_groups, budget / std::max<size_t>(kbytes, 1)));
+    GS_CUDA(h->dK.reserve(kbytes * gpb));
+
+    GS_CUDA(h->dWork[0].reserve(rows_all.size() * 4));
+    GS_CUDA(cudaMemcpyAsync(h->dWork[0].p, rows_all.data(), rows_all.size() * 4, cudaMemcpyHostToDevice, st));
+    pf.h2d_bytes += rows_all.size() * 4;
+    const int *d_rows = h->dWork[0].as<int>();
+
+    std::vector<int> cnt_host;            // per task: 4 counters
+    std::vector<int> task_iter(n_tasks, 0), task_sv(n_tasks, 0);
+    std::vector<double> task_fit_ms(n_tasks, 0.0);
+    std::vector<int> all_counts((size_t)n_tasks * 4, 0);
+    int64_t total_iter = 0;
+    double solve_bytes = 0;
+
+    for (int g0 = 0; g0 < n_groups; g0 += gpb) {
+        const int g1 = std::min(n_groups, g0 + gpb);
+        // -- kernel matrices of this batch --
+        for (int g = g0; g < g1; g++) {
+            GS_CUDA(launch_kernel_matrix(h->dS.as<double>(), h->dXsq.as<double>(), n, groups[g].first, groups[g].second,
+                                         h->dK.as<float>() + (size_t)(g - g0) * n * ldk, ldk, st));
+            pf.launches++;
+        }
+        tm.mark(1);
+        // -- problems: ordered by (group, task, pair); column index == problem index --
+        std::vector<SmoProblem> probs;
+        std::vector<int> prob_task, group_first(g1 - g0 + 1, 0);
+        std::vector<VoteTask> vtasks;
+        std::vector<int> vtask_id;
+        size_t wl = 0, ws = 0;            // workspace doubles / ints
+        for (int g = g0; g < g1; g++) {
+            group_first[g - g0] = (int)probs.size();
+            for (int t : group_tasks[g]) {
+                const int c = t / n_splits, k = t % n_splits;
+                vtasks.push_back(VoteTask{(int)probs.size(), refit ? -100 : k});
+                vtask_id.push_back(t);
+                for (int p = 0; p < n_pairs; p++) {
+                    const size_t s = (size_t)k * n_pairs + p;
+                    SmoProblem P;
+                    memset(&P, 0, sizeof P);
+                    P.K = h->dK.as<float>() + (size_t)(g - g0) * n * ldk;
+                    P.qd = groups[g].first == GS_KERNEL_LINEAR ? h->dXsq.as<double>() : nullptr;
+                    P.rows = d_rows + sp_off[s];
+                    P.l = sp_off[s + 1] - sp_off[s];
+                    P.n_pos = sp_npos[s];
+                    P.ldk = ldk; P.C = Cv[c]; P.eps = tol; P.max_iter = max_iter;
+                    P.shrinking = (flags & GS_NO_SHRINKING) ? 0 : 1;
+                    P.alpha = (double *)wl; wl += P.l;          // offsets now, pointers below
+                    P.Gbar = (double *)wl; wl += P.l;
+                    P.scratch = (int *)ws; ws += 2 * (size_t)P.l + 64;
+                    probs.push_back(P);
+                    prob_task.push_back(t);
+                }
+            }
+        }
+        group_first[g1 - g0] = (int)probs.size();
+        const int np = (int)probs.size();
+        // workspaces
+        GS_CUDA(h->dWork[1].reserve(wl * 8));
+        GS_CUDA(h->dWork[2].reserve(ws * 4));
+        GS_CUDA(h->dWork[3].reserve((size_t)np * n * 8));                 // coef columns
+        GS_CUDA(h->dWork[4].reserve((size_t)np * n * 8));                 // decision columns
+        GS_CUDA(h->dWork[5].reserve((size_t)np * (8 + 16 + 16) + 64));    // rho, info[4], ns[2]
+        GS_CUDA(h->dWork[6].reserve((size_t)np * sizeof(SmoProblem) + (size_t)np * 4 + vtasks.size() * (sizeof(VoteTask) + 16) + 256));
+        double *d_rho = h->dWork[5].as<double>();
+        int *d_info = (int *)(d_rho + np);
+        unsigned long long *d_ns = (unsigned long long *)(d_info + 4 * (size_t)np);
+        for (int q = 0; q < np; q++) {
+            SmoProblem &P = probs[q];
+            P.alpha = h->dWork[1].as<double>() + (size_t)P.alpha;
+            P.Gbar = h->dWork[1].as<double>() + (size_t)P.Gbar;
+            P.scratch = h->dWork[2].as<int>() + (size_t)P.scratch;
+            P.coef = h->dWork[3].as<double>() + (size_t)q * n;
+            P.out_rho = d_rho + q; P.out_info = d_info + 4 * (size_t)q; P.out_ns = d_ns + 2 * (size_t)q;
+        }
+        // longest-first launch order: iterations grow with C and with 1/gamma
+        std::vector<int> order(np);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            const int ta = prob_task[a], tb = prob_task[b];
+            const double ca = Cv[ta / n_splits] * probs[a].l, cb = Cv[tb / n_splits] * probs[b].l;
+            if (ca != cb) return ca > cb;
+            return groups[task_group[ta]].second < groups[task_group[tb]].second;
+        });
+        unsigned char *dmeta = h->dWork[6].as<unsigned char>();
+        SmoProblem *d_probs = (SmoProblem *)dmeta;
+        int *d_order = (int *)(dmeta + (size_t)np * sizeof(SmoProblem));
+        size_t off = (size_t)np * sizeof(SmoProblem) + (size_t)np * 4;
+        off = (off + 15) & ~(size_t)15;
+        VoteTask *d_vt = (VoteTask *)(dmeta + off);
+        off += vtasks.size() * sizeof(VoteTask);
+        off = (off + 15) & ~(size_t)15;
+        int *d_counts = (int *)(dmeta + off);
+        GS_CUDA(cudaMemcpyAsync(d_probs, probs.data(), (size_t)np * sizeof(SmoProblem), cudaMemcpyHostToDevice, st));
+        GS_CUDA(cudaMemcpyAsync(d_order, order.data(), (size_t)np * 4, cudaMemcpyHostToDevice, st));
+        GS_CUDA(cudaMemcpyAsync(d_vt, vtasks.data(), vtasks.size() * sizeof(VoteTask), cudaMemcpyHostToDevice, st));
+        GS_CUDA(cudaMemsetAsync(d_counts, 0, vtasks.size() * 16, st));
+        GS_CUDA(cudaMemsetAsync(h->dWork[3].p, 0, (size_t)np * n * 8, st));
+        pf.h2d_bytes += (size_t)np * sizeof(SmoProblem) + (size_t)np * 4 + vtasks.size() * sizeof(VoteTask);
+        tm.mark(4);
+        // -- solve --
+        std::string why;
+        cudaError_t ce = launch_smo(d_probs, d_order, np, lmax, st, &why);
+        if (ce != cudaSuccess) { gs_set_error(h, why.empty() ? std::string("launch_smo: ") + cudaGetErrorString(ce) : why); return why.empty() ? GS_ERR_CUDA : GS_ERR_UNSUPPORTED; }
+        pf.launches++;
+        tm.mark(2);
+        // -- score (skipped for refit) --
+        if (!refit) {
+            for (int g = g0; g < g1; g++) {
+                const int c0 = group_first[g - g0], c1 = group_first[g - g0 + 1];
+                GS_CUDA(launch_decision(h->dS.as<double>(), h->dXsq.as<double>(), n, groups[g].first, groups[g].second,
+                                        h->dWork[3].as<double>() + (size_t)c0 * n, c1 - c0,
+                                        h->dWork[4].as<double>() + (size_t)c0 * n, st));
+                pf.launches++;
+            }
+            GS_CUDA(launch_vote(h->dWork[4].as<double>(), d_rho, n, nc, h->dY.as<int>(), h->dFold.as<signed char>(),
+                                d_vt, (int)vtasks.size(), d_counts, st));
+            pf.launches++;
+        }
+        tm.mark(3);
+        // -- results of this batch --
+        std::vector<int> info((size_t)np * 4), counts(vtasks.size() * 4);
+        std::vector<unsigned long long> ns((size_t)np * 2);
+        std::vector<double> rho(np);
+        GS_CUDA(cudaMemcpyAsync(info.data(), d_info, info.size() * 4, cudaMemcpyDeviceToHost, st));
+        GS_CUDA(cudaMemcpyAsync(ns.data(), d_ns, ns.size() * 8, cudaMemcpyDeviceToHost, st));
+        GS_CUDA(cudaMemcpyAsync(rho.data(), d_rho, rho.size() * 8, cudaMemcpyDeviceToHost, st));
+        GS_CUDA(cudaMemcpyAsync(counts.data(), d_counts, counts.size() * 4, cudaMemcpyDeviceToHost, st));
+        std::vector<double> coef_host;
+        if (refit && pair_coef) {
+            coef_host.resize((size_t)np * n);
+            GS_CUDA(cudaMemcpyAsync(coef_host.data(), h->dWork[3].p, coef_host.size() * 8, cudaMemcpyDeviceToHost, st));
+        }
+        GS_CUDA(cudaStreamSynchronize(st));
+        pf.d2h_bytes += info.size() * 4 + ns.size() * 8 + rho.size() * 8 + counts.size() * 4 + coef_host.size() * 8;
+        tm.collect(acc, 5);
+        tm.mark(-1);
+        for (int q = 0; q < np; q++) {
+            const int t = prob_task[q];
+            task_iter[t] += info[(size_t)q * 4]; task_sv[t] += info[(size_t)q * 4 + 2];
+            task_fit_ms[t] += (double)(ns[(size_t)q * 2 + 1] - ns[(size_t)q * 2]) * 1e-6;
+            total_iter += info[(size_t)q * 4];
+            // two gathered K rows of the problem's (initially full) active set per iteration
+            solve_bytes += (double)info[(size_t)q * 4] * 2.0 * probs[q].l * 4.0;
+            if (!std::isfinite(rho[q])) { gs_set_error(h, "gs_svc: non-finite intercept"); return GS_ERR_NUMERIC; }
+        }
+        for (size_t v = 0; v < vtasks.size(); v++)
+            for (int e = 0; e < 4; e++) all_counts[(size_t)vtask_id[v] * 4 + e] = counts[v * 4 + e];
+        if (refit) {
+            for (int q = 0; q < np; q++) {
+                if (rho_out) rho_out[q] = rho[q];
+                if (pair_iter) pair_iter[q] = info[(size_t)q * 4];
+                if (pair_coef)
+                    for (int r = 0; r < n; r++) pair_coef[(size_t)q * n + h->perm[r]] = coef_host[(size_t)q * n + r];
+            }
+        }
+    }
+    cudaEventRecord(ev_end, st);
+    GS_CUDA(cudaStreamSynchronize(st));
+    tm.collect(acc, 5);
+    cudaEventElapsedTime(&pf.ms_total, ev_begin, ev_end);
+    cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end);
+    pf.ms_gram = acc[0]; pf.ms_kernel_matrix = acc[1]; pf.ms_solve = acc[2]; pf.ms_score = acc[3];
+    pf.smo_iterations = total_iter;
+    pf.solve_bytes = solve_bytes;
+
+    if (!refit) {
+        for (int t = 0; t < n_tasks; t++) {
+            const int *cn = &all_counts[(size_t)t * 4];
+            test_scores[t] = cn[1] > 0 ? (double)cn[0] / (double)cn[1] : NAN;
+            if (train_scores) train_scores[t] = cn[3] > 0 ? (double)cn[2] / (double)cn[3] : NAN;
+            if (n_iter) n_iter[t] = task_iter[t];
+            if (n_sv) n_sv[t] = task_sv[t];
+            if (fit_ms) fit_ms[t] = (float)task_fit_ms[t];
+            if (score_ms) score_ms[t] = pf.ms_score / (float)n_tasks;
+        }
+    }
+    return GS_OK;
+}
+
+int gs_svc(gs_handle *h, int32_t n_cand, const int32_t *kernel, const double *C, const double *gamma, double tol,
+           int32_t max_iter, uint32_t flags, double *test_scores, double *train_scores, int32_t *n_iter,
+           int32_t *n_sv, float *fit_ms, float *score_ms)
+{
+    if (h && !test_scores) { gs_set_error(h, "gs_svc: test_scores is NULL"); return GS_ERR_ARG; }
+    return svc_run(h, n_cand, kernel, C, gamma, tol, max_iter, flags, false, test_scores,
+                   (flags & GS_RETURN_TRAIN) ? train_scores : nullptr, n_iter, n_sv, fit_ms, score_ms, nullptr, nullptr, nullptr);
+}
+
+int gs_svc_refit(gs_handle *h, int32_t kernel, double C, double gamma, double tol, int32_t max_iter, uint32_t flags,
+                 double *pair_coef, double *rho, int32_t *n_iter)
+{
+    const int32_t k = kernel;
+    return svc_run(h, 1, &k, &C, &gamma, tol, max_iter, flags, true, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                   pair_coef, rho, n_iter);
+}
+
+int gs_debug_gram(gs_handle *h, double *S_out, double *xsq_out)
+{
+    if (!h) return GS_ERR_ARG;
+    if (h->n == 0) { gs_set_error(h, "gs_debug_gram: no dataset"); return GS_ERR_NO_DATA; }
+    GS_CUDA(cudaSetDevice(h->device));
+    const int n = (int)h->n, d = (int)h->d;
+    GS_CUDA(h->dS.reserve((size_t)n * n * 8));
+    GS_CUDA(h->dXsq.reserve((size_t)n * 8));
+    GS_CUDA(launch_gram_f64(h->x_dtype == GS_F64 ? h->dX64.p : h->dX.p, h->x_dtype, n, d, h->dS.as<double>(), h->dXsq.as<double>(), h->stream));
+    std::vector<double> S((size_t)n * n), xs(n);
+    GS_CUDA(cudaMemcpyAsync(S.data(), h->dS.p, S.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    GS_CUDA(cudaMemcpyAsync(xs.data(), h->dXsq.p, xs.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    GS_CUDA(cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < n; r++) {
+        if (xsq_out) xsq_out[h->perm[r]] = xs[r];
+        if (S_out)
+            for (int c = 0; c < n; c++) S_out[(size_t)h->perm[r] * n + h->perm[c]] = S[(size_t)r * n + c];
+    }
+    return GS_OK;
+}
+
+int gs_debug_kernel_matrix(gs_handle *h, int32_t kernel, double gamma, float *K_out)
+{
+    if (!h || !K_out) return GS_ERR_ARG;
+    int st = gs_debug_gram(h, nullptr, nullptr);
+    if (st) return st;
+    const int n = (int)h->n;
+    const int64_t ldk = ((int64_t)n + 31) & ~31LL;
+    GS_CUDA(h->dK.reserve((size_t)n * ldk * 4));
+    GS_CUDA(launch_kernel_matrix(h->dS.as<double>(), h->dXsq.as<double>(), n, kernel, gamma, h->dK.as<float>(), ldk, h->stream));
+    std::vector<float> K((size_t)n * ldk);
+    GS_CUDA(cudaMemcpyAsync(K.data(), h->dK.p, K.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+    GS_CUDA(cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < n; r++)
+        for (int c = 0; c < n; c++) K_out[(size_t)h->perm[r] * n + h->perm[c]] = K[(size_t)r * ldk + c];
+    return GS_OK;
+}
+
+int gs_get_profile(const gs_handle *h, gs_profile *out)
+{
+    if (!h || !out) return GS_ERR_ARG;
+    *out = h->prof;
+    return GS_OK;
+}
+
+}  // extern "C"

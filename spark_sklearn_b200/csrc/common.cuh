@@ -1,0 +1,101 @@
+// common.cuh -- shared declarations of the libb200gs.so translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/b200gs.h"
+
+#define GS_CUDA(call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            gs_set_error(h, std::string(#call) + ": " + cudaGetErrorString(e_) + " @" +       \
+                                __FILE__ + ":" + std::to_string(__LINE__));                   \
+            return GS_ERR_CUDA;                                                               \
+        }                                                                                     \
+    } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+struct gs_handle {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // dataset (rows stored in INTERNAL order: sorted by class, then by original index)
+    int64_t n = 0, d = 0;
+    int n_splits = 0, n_classes = 0;
+    bool classification = false;
+    std::vector<int32_t> perm;        // internal row -> original row
+    std::vector<int32_t> yc;          // [n] class ids, internal order
+    std::vector<int8_t> fold;         // [n] fold ids, internal order
+    std::vector<int32_t> class_start; // [n_classes+1] internal row ranges per class
+    DevBuf dX, dY, dFold, dYt;        // float X[n][d], int32 y[n], int8 fold[n], float yt[n]
+    DevBuf dX64;                      // double X[n][d] when the caller's matrix is float64
+    int x_dtype = GS_F32;
+    DevBuf dS, dXsq;                  // float64 Gram [n][n], squared norms [n]
+    DevBuf dK;                        // float32 kernel matrices (batch)
+    DevBuf dWork[8];                  // per-search scratch
+    gs_profile prof;
+    cudaEvent_t ev[8];
+};
+
+void gs_set_error(gs_handle *h, const std::string &msg);
+
+// ---- gram.cu ----
+// S = X X^T in float64 from float32 X (exact products, float64 accumulation); xsq = diag(S).
+cudaError_t launch_gram_f64(const void *X, int x_dtype, int n, int d, double *S, double *xsq, cudaStream_t st);
+// K[r][c] = (float) k(x_r, x_c) from S: rbf exp(-gamma*(xsq_r + xsq_c - 2 S_rc)) or linear S_rc.
+cudaError_t launch_kernel_matrix(const double *S, const double *xsq, int n, int kernel, double gamma,
+                                 float *K, int64_t ldk, cudaStream_t st);
+
+// ---- smo.cu ----
+struct SmoProblem {
+    const float *K;       // float32 kernel matrix of this (kernel, gamma): [n][ldk]
+    const double *qd;     // float64 diagonal by dataset row (linear kernel) or nullptr (rbf: QD == 1)
+    const int *rows;      // [l] dataset rows in sub-problem order: n_pos rows of the +1 class first
+    double *alpha;        // [l] workspace: alpha by position
+    double *Gbar;         // [l] workspace
+    int *scratch;         // [2*l + 64] workspace
+    double *coef;         // [n] out: alpha*y scattered by dataset row (pre-zeroed)
+    double *out_rho;      // out
+    int *out_info;        // out: [0] n_iter [1] timed_out [2] n_sv [3] n_bounded_sv
+    unsigned long long *out_ns;   // out: [0] start [1] end (globaltimer)
+    int64_t ldk;
+    double C, eps;
+    int l, n_pos, max_iter, shrinking;
+};
+// Solve problems order[0..n_prob) (one CTA each); lmax = max l (selects the template instance).
+cudaError_t launch_smo(const SmoProblem *d_probs, const int *d_order, int n_prob, int lmax, cudaStream_t st,
+                       std::string *why);
+int smo_max_rows();   // largest sub-problem the resident-state kernel supports
+
+// ---- score.cu ----
+// dec[c][r] = sum_j k64(r, j) * coef[c][j]  (float64 kernel values recomputed from S, not the
+// float32-rounded K: svm.cpp:2821 svm_predict_values uses k_function in double).
+cudaError_t launch_decision(const double *S, const double *xsq, int n, int kernel, double gamma,
+                            const double *coef, int ncols, double *dec, cudaStream_t st);
+struct VoteTask {          // one (candidate, fold) task
+    int first_col;         // first decision column of this task inside its group (n_pairs consecutive)
+    int fold;              // test fold id
+};
+// counts[task][0..3] = {test correct, test total, train correct, train total}
+cudaError_t launch_vote(const double *dec, const double *rho, int n, int n_classes, const int *y,
+                        const signed char *fold, const VoteTask *tasks, int n_tasks, int *counts,
+                        cudaStream_t st);

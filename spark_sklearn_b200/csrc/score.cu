@@ -1,0 +1,143 @@
+// score.cu -- SVC decision values for every (row, sub-model) and one-vs-one voting / accuracy.
+//
+// libsvm predicts with float64 kernel values (svm.cpp:2821-2904 svm_predict_values calls
+// Kernel::k_function in double; the float32 rounding applies only to the training Q matrix), so the
+// decision values are NOT formed from the float32 K matrix.  They are a float64 product
+//      dec[c][r] = sum_j k64(r, j) * coef[c][j],   k64 = exp(-gamma*d2(r,j)) or S_rj
+// evaluated for ALL rows r at once (test rows give the test score, the other rows the train score)
+// and for all sub-models c that share one (kernel, gamma): one pass over the float64 Gram per gamma,
+// with the exp fused into the operand load.  coef is zero outside a sub-model's training rows.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TR = 64, TC = 32, TJ = 32;
+
+__global__ void __launch_bounds__(256)
+decision_kernel(const double *__restrict__ S, const double *__restrict__ xsq, int n, int kernel, double gamma,
+                const double *__restrict__ coef, int ncols, double *__restrict__ dec)
+{
+    __shared__ __align__(16) double E[TJ][TR + 2];
+    __shared__ __align__(16) double Cf[TJ][TC + 2];
+    const int tid = threadIdx.x;
+    const int r0 = blockIdx.x * TR, c0 = blockIdx.y * TC;
+    const int ty = tid >> 3, tx = tid & 7;          // rows ty*2..+1, cols tx*4..+3
+    const int lj = tid & 31, lr = tid >> 5;         // loader mapping
+    double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    const double ng = -gamma;
+
+    for (int j0 = 0; j0 < n; j0 += TJ) {
+        const int j = j0 + lj;
+        const double xj = j < n ? xsq[j] : 0.0;
+#pragma unroll
+        for (int s = 0; s < TR / 8; s++) {
+            const int r = r0 + lr + 8 * s;
+            double v = 0.0;
+            if (r < n && j < n) {
+                const double sv = S[(size_t)r * n + j];
+                if (kernel == GS_KERNEL_RBF) {
+                    const double d2 = __dsub_rn(__dadd_rn(xsq[r], xj), __dmul_rn(2.0, sv));
+                    v = exp(__dmul_rn(ng, d2));
+                } else {
+                    v = sv;
+                }
+            }
+            E[lj][lr + 8 * s] = v;
+        }
+#pragma unroll
+        for (int s = 0; s < TC / 8; s++) {
+            const int c = c0 + lr + 8 * s;
+            Cf[lj][lr + 8 * s] = (c < ncols && j < n) ? coef[(size_t)c * n + j] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < TJ; k++) {
+            const double2 e = *reinterpret_cast<const double2 *>(&E[k][ty * 2]);
+            const double2 ca = *reinterpret_cast<const double2 *>(&Cf[k][tx * 4]);
+            const double2 cb = *reinterpret_cast<const double2 *>(&Cf[k][tx * 4 + 2]);
+            acc[0][0] = fma(e.x, ca.x, acc[0][0]); acc[0][1] = fma(e.x, ca.y, acc[0][1]);
+            acc[0][2] = fma(e.x, cb.x, acc[0][2]); acc[0][3] = fma(e.x, cb.y, acc[0][3]);
+            acc[1][0] = fma(e.y, ca.x, acc[1][0]); acc[1][1] = fma(e.y, ca.y, acc[1][1]);
+            acc[1][2] = fma(e.y, cb.x, acc[1][2]); acc[1][3] = fma(e.y, cb.y, acc[1][3]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 2; a++) {
+        const int r = r0 + ty * 2 + a;
+        if (r >= n) continue;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int c = c0 + tx * 4 + b;
+            if (c < ncols) dec[(size_t)c * n + r] = acc[a][b];
+        }
+    }
+}
+
+// One-vs-one vote (svm.cpp:2862-2892): dec - rho > 0 votes for the lower class of the pair, else the
+// higher; first maximum wins.  Accuracy counts split by fold membership.
+__global__ void __launch_bounds__(256)
+vote_kernel(const double *__restrict__ dec, const double *__restrict__ rho, int n, int n_classes,
+            const int *__restrict__ y, const signed char *__restrict__ fold,
+            const VoteTask *__restrict__ tasks, int *__restrict__ counts)
+{
+    const VoteTask T = tasks[blockIdx.y];
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int c_te = 0, n_te = 0, c_tr = 0, n_tr = 0;
+    if (r < n) {
+        int pred;
+        if (n_classes == 2) {
+            const double dv = dec[(size_t)T.first_col * n + r] - rho[T.first_col];
+            pred = dv > 0 ? 0 : 1;
+        } else {
+            int votes[32];
+            for (int c = 0; c < n_classes; c++) votes[c] = 0;
+            int p = T.first_col;
+            for (int a = 0; a < n_classes; a++)
+                for (int b = a + 1; b < n_classes; b++, p++) {
+                    const double dv = dec[(size_t)p * n + r] - rho[p];
+                    if (dv > 0) ++votes[a]; else ++votes[b];
+                }
+            pred = 0;
+            for (int c = 1; c < n_classes; c++) if (votes[c] > votes[pred]) pred = c;
+        }
+        const bool ok = pred == y[r];
+        if (fold[r] == T.fold) { n_te = 1; c_te = ok; } else { n_tr = 1; c_tr = ok; }
+    }
+    // block reduce the four counters
+    __shared__ int sh[4][8];
+#pragma unroll
+    for (int m = 16; m; m >>= 1) {
+        c_te += __shfl_xor_sync(0xffffffffu, c_te, m); n_te += __shfl_xor_sync(0xffffffffu, n_te, m);
+        c_tr += __shfl_xor_sync(0xffffffffu, c_tr, m); n_tr += __shfl_xor_sync(0xffffffffu, n_tr, m);
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { sh[0][w] = c_te; sh[1][w] = n_te; sh[2][w] = c_tr; sh[3][w] = n_tr; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        int s = 0;
+        for (int i = 0; i < 8; i++) s += sh[threadIdx.x][i];
+        if (s) atomicAdd(&counts[blockIdx.y * 4 + threadIdx.x], s);
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_decision(const double *S, const double *xsq, int n, int kernel, double gamma,
+                            const double *coef, int ncols, double *dec, cudaStream_t st)
+{
+    if (ncols <= 0) return cudaSuccess;
+    dim3 grid((n + TR - 1) / TR, (ncols + TC - 1) / TC);
+    decision_kernel<<<grid, 256, 0, st>>>(S, xsq, n, kernel, gamma, coef, ncols, dec);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_vote(const double *dec, const double *rho, int n, int n_classes, const int *y,
+                        const signed char *fold, const VoteTask *tasks, int n_tasks, int *counts,
+                        cudaStream_t st)
+{
+    if (n_tasks <= 0) return cudaSuccess;
+    dim3 grid((n + 255) / 256, n_tasks);
+    vote_kernel<<<grid, 256, 0, st>>>(dec, rho, n, n_classes, y, fold, tasks, counts);
+    return cudaGetLastError();
+}

@@ -1,0 +1,191 @@
+"""ctypes binding of libb200gs.so (include/b200gs.h) -- the only way the package computes.
+
+There is deliberately no CPU fallback: if the CUDA library is missing or no sm_100 GPU is visible,
+``Engine()`` raises.  The oracle under ``oracle/`` is test infrastructure and is never imported here.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200gs.so")
+
+GS_RETURN_TRAIN, GS_GRAM_TENSOR, GS_NO_SHRINKING = 1, 2, 4
+KERNEL_ID = {"linear": 0, "rbf": 1}
+
+_lib = None
+
+
+class GsProfile(ctypes.Structure):
+    _fields_ = [("ms_total", ctypes.c_float), ("ms_h2d", ctypes.c_float), ("ms_gram", ctypes.c_float),
+                ("ms_kernel_matrix", ctypes.c_float), ("ms_solve", ctypes.c_float), ("ms_score", ctypes.c_float),
+                ("launches", ctypes.c_int64), ("smo_iterations", ctypes.c_int64),
+                ("solve_bytes", ctypes.c_double), ("gram_flops", ctypes.c_double), ("gram_bytes", ctypes.c_double),
+                ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64)]
+
+
+class EngineError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("libb200gs status %d: %s" % (status, msg))
+        self.status = status
+
+
+def load_library():
+    """dlopen libb200gs.so and declare the prototypes of include/b200gs.h.  Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "spark_sklearn_b200: %s is missing -- build it with `python -m spark_sklearn_b200.build` "
+            "(nvcc, sm_100a).  There is no CPU fallback." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    vp, i32, i64, u32, dbl = c.c_void_p, c.c_int32, c.c_int64, c.c_uint32, c.c_double
+    L.gs_version.restype = c.c_int
+    L.gs_create.argtypes = [c.c_int, c.POINTER(vp)]
+    L.gs_destroy.argtypes = [vp]
+    L.gs_destroy.restype = None
+    L.gs_last_error.argtypes = [vp]
+    L.gs_last_error.restype = c.c_char_p
+    L.gs_set_data.argtypes = [vp, vp, i32, i64, i64, vp, vp, vp, i32]
+    L.gs_svc.argtypes = [vp, i32, vp, vp, vp, dbl, i32, u32, vp, vp, vp, vp, vp, vp]
+    L.gs_svc_refit.argtypes = [vp, i32, dbl, dbl, dbl, i32, u32, vp, vp, vp]
+    L.gs_ridge.argtypes = [vp, i32, vp, i32, u32, vp, vp, vp, vp]
+    L.gs_ridge_refit.argtypes = [vp, dbl, i32, vp]
+    L.gs_logreg.argtypes = [vp, i32, vp, dbl, i32, i32, u32, vp, vp, vp, vp, vp]
+    L.gs_logreg_refit.argtypes = [vp, dbl, dbl, i32, i32, vp, vp]
+    L.gs_get_profile.argtypes = [vp, c.POINTER(GsProfile)]
+    L.gs_debug_gram.argtypes = [vp, vp, vp]
+    L.gs_debug_kernel_matrix.argtypes = [vp, i32, dbl, vp]
+    for f in ("gs_create", "gs_set_data", "gs_svc", "gs_svc_refit", "gs_ridge", "gs_ridge_refit", "gs_logreg",
+              "gs_logreg_refit", "gs_get_profile", "gs_debug_gram", "gs_debug_kernel_matrix"):
+        getattr(L, f).restype = c.c_int
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Engine:
+    """One handle = one GPU (reference analogue: the SparkContext `sc`, util.py:51-58)."""
+
+    def __init__(self, device=None):
+        self._L = load_library()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        h = ctypes.c_void_p()
+        st = self._L.gs_create(int(device), ctypes.byref(h))
+        if st != 0:
+            raise EngineError(st, (self._L.gs_last_error(None) or b"").decode())
+        self._h = h
+        self.device = int(device)
+        self.n = self.d = self.n_splits = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.gs_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, st):
+        if st != 0:
+            raise EngineError(st, (self._L.gs_last_error(self._h) or b"").decode())
+
+    # -- the "broadcast" (reference base_search.py:63-65) --
+    def set_data(self, X, fold_id, n_splits, y_class=None, y_target=None):
+        X = np.ascontiguousarray(X, np.float32 if np.asarray(X).dtype == np.float32 else np.float64)
+        fold_id = np.ascontiguousarray(fold_id, np.int8)
+        yc = None if y_class is None else np.ascontiguousarray(y_class, np.int32)
+        yt = None if y_target is None else np.ascontiguousarray(y_target, np.float32)
+        self.n, self.d = X.shape
+        self.n_splits = int(n_splits)
+        self._check(self._L.gs_set_data(self._h, _ptr(X), 0 if X.dtype == np.float32 else 1, X.shape[0], X.shape[1], _ptr(yc), _ptr(yt),
+                                        _ptr(fold_id), int(n_splits)))
+
+    # -- map(fun).collect() for SVC (reference base_search.py:74-95) --
+    def svc(self, kernel, C, gamma, tol=1e-3, max_iter=-1, shrinking=True, return_train=True, flags=0):
+        kernel = np.ascontiguousarray([KERNEL_ID[k] if isinstance(k, str) else int(k) for k in kernel], np.int32)
+        C = np.ascontiguousarray(C, np.float64)
+        n_cand = len(C)
+        gamma = np.ascontiguousarray(np.broadcast_to(np.asarray(gamma, np.float64).reshape(n_cand, -1),
+                                                     (n_cand, self.n_splits)))
+        shape = (n_cand, self.n_splits)
+        out = dict(test=np.zeros(shape), train=np.zeros(shape), n_iter=np.zeros(shape, np.int32),
+                   n_sv=np.zeros(shape, np.int32), fit_ms=np.zeros(shape, np.float32),
+                   score_ms=np.zeros(shape, np.float32))
+        fl = int(flags) | (GS_RETURN_TRAIN if return_train else 0) | (0 if shrinking else GS_NO_SHRINKING)
+        self._check(self._L.gs_svc(self._h, n_cand, _ptr(kernel), _ptr(C), _ptr(gamma), float(tol), int(max_iter), fl,
+                                   _ptr(out["test"]), _ptr(out["train"]), _ptr(out["n_iter"]), _ptr(out["n_sv"]),
+                                   _ptr(out["fit_ms"]), _ptr(out["score_ms"])))
+        if not return_train:
+            out["train"] = None
+        return out
+
+    def svc_refit(self, kernel, C, gamma, n_classes, tol=1e-3, max_iter=-1, shrinking=True):
+        n_pairs = n_classes * (n_classes - 1) // 2
+        coef = np.zeros((n_pairs, self.n))
+        rho = np.zeros(n_pairs)
+        it = np.zeros(n_pairs, np.int32)
+        k = KERNEL_ID[kernel] if isinstance(kernel, str) else int(kernel)
+        self._check(self._L.gs_svc_refit(self._h, k, float(C), float(gamma), float(tol), int(max_iter),
+                                         0 if shrinking else GS_NO_SHRINKING, _ptr(coef), _ptr(rho), _ptr(it)))
+        return coef, rho, it
+
+    def ridge(self, alpha, fit_intercept=True, return_train=True):
+        alpha = np.ascontiguousarray(alpha, np.float64)
+        shape = (len(alpha), self.n_splits)
+        out = dict(test=np.zeros(shape), train=np.zeros(shape), fit_ms=np.zeros(shape, np.float32),
+                   score_ms=np.zeros(shape, np.float32))
+        self._check(self._L.gs_ridge(self._h, len(alpha), _ptr(alpha), int(bool(fit_intercept)),
+                                     GS_RETURN_TRAIN if return_train else 0, _ptr(out["test"]), _ptr(out["train"]),
+                                     _ptr(out["fit_ms"]), _ptr(out["score_ms"])))
+        if not return_train:
+            out["train"] = None
+        return out
+
+    def ridge_refit(self, alpha, fit_intercept=True):
+        coef = np.zeros(self.d + 1)
+        self._check(self._L.gs_ridge_refit(self._h, float(alpha), int(bool(fit_intercept)), _ptr(coef)))
+        return coef[:-1].copy(), float(coef[-1])
+
+    def logreg(self, C, tol=1e-4, max_iter=100, fit_intercept=True, return_train=True):
+        C = np.ascontiguousarray(C, np.float64)
+        shape = (len(C), self.n_splits)
+        out = dict(test=np.zeros(shape), train=np.zeros(shape), n_iter=np.zeros(shape, np.int32),
+                   fit_ms=np.zeros(shape, np.float32), score_ms=np.zeros(shape, np.float32))
+        self._check(self._L.gs_logreg(self._h, len(C), _ptr(C), float(tol), int(max_iter), int(bool(fit_intercept)),
+                                      GS_RETURN_TRAIN if return_train else 0, _ptr(out["test"]), _ptr(out["train"]),
+                                      _ptr(out["n_iter"]), _ptr(out["fit_ms"]), _ptr(out["score_ms"])))
+        if not return_train:
+            out["train"] = None
+        return out
+
+    def logreg_refit(self, C, tol=1e-4, max_iter=100, fit_intercept=True):
+        coef = np.zeros(self.d + 1)
+        it = np.zeros(1, np.int32)
+        self._check(self._L.gs_logreg_refit(self._h, float(C), float(tol), int(max_iter), int(bool(fit_intercept)),
+                                            _ptr(coef), _ptr(it)))
+        return coef[:-1].copy(), float(coef[-1]), int(it[0])
+
+    # -- test hooks --
+    def debug_gram(self):
+        S = np.zeros((self.n, self.n))
+        xsq = np.zeros(self.n)
+        self._check(self._L.gs_debug_gram(self._h, _ptr(S), _ptr(xsq)))
+        return S, xsq
+
+    def debug_kernel_matrix(self, kernel, gamma):
+        K = np.zeros((self.n, self.n), np.float32)
+        k = KERNEL_ID[kernel] if isinstance(kernel, str) else int(kernel)
+        self._check(self._L.gs_debug_kernel_matrix(self._h, k, float(gamma), _ptr(K)))
+        return K
+
+    def profile(self):
+        p = GsProfile()
+        self._check(self._L.gs_get_profile(self._h, ctypes.byref(p)))
+        return {k: getattr(p, k) for k, _ in GsProfile._fields_}

@@ -1,0 +1,358 @@
+"""Estimator adapters: turn (estimator, candidate dicts, folds) into the scalar tables the C ABI takes,
+and turn refit buffers back into genuine fitted scikit-learn estimators for ``best_estimator_``
+(reference base_search.py:165-174 delegates ``predict`` & co. to it).
+
+Only estimators with a CUDA path are accepted (SVC rbf/linear, Ridge, LogisticRegression -- the
+families the reference ships examples for); anything else raises: no CPU fallback.
+"""
+import numbers
+import warnings
+
+import numpy as np
+from sklearn.base import clone
+
+from .engine import Engine, EngineError
+
+_ENGINES = {}
+
+
+def get_engine(device=None):
+    """One cached handle per device: GPU allocations stay warm across searches."""
+    import os
+    dev = int(os.environ.get("LOCAL_RANK", "0")) if device is None else int(device)
+    if dev not in _ENGINES:
+        _ENGINES[dev] = Engine(dev)
+    return _ENGINES[dev]
+
+
+def fold_ids_from_splits(splits, n):
+    """fold_id[row] = index of the split whose TEST set holds the row.  The engine keeps one int8 per
+    row instead of per-task index arrays (reference base_search.py:81-82), which requires what every
+    (Stratified)KFold/GroupKFold/LeaveOneOut-style splitter gives: disjoint test sets whose complement
+    is the training set."""
+    if len(splits) > 127:
+        raise NotImplementedError("more than 127 CV splits")
+    fold_id = np.full(n, -1, np.int8)
+    for k, (tr, te) in enumerate(splits):
+        te = np.asarray(te)
+        if np.any(fold_id[te] != -1):
+            raise NotImplementedError("CV splitter with overlapping test sets is not supported by the CUDA path")
+        fold_id[te] = k
+        if len(tr) + len(te) != n or len(np.intersect1d(tr, te)):
+            raise NotImplementedError("CV splitter whose train set is not the complement of its test set "
+                                      "is not supported by the CUDA path")
+    return fold_id
+
+
+def adapter_for(estimator):
+    from sklearn.linear_model import LogisticRegression, Ridge
+    from sklearn.svm import SVC
+    t = type(estimator)
+    if t is SVC:
+        return SVCAdapter
+    if t is Ridge:
+        return RidgeAdapter
+    if t is LogisticRegression:
+        return LogRegAdapter
+    raise NotImplementedError(
+        "spark_sklearn_b200 has CUDA paths for SVC, Ridge and LogisticRegression only; got %s "
+        "(no CPU fallback)" % t.__name__)
+
+
+def _as_matrix(X):
+    X = np.asarray(X)
+    if X.ndim != 2:
+        raise ValueError("X must be 2-dimensional")
+    if X.dtype == np.float32:
+        return np.ascontiguousarray(X)
+    return np.ascontiguousarray(X, np.float64)        # scikit-learn upcasts everything else to float64
+
+
+def _pad_scores(arr_list, my):
+    return None if not my else np.concatenate(arr_list, 0)
+
+
+class _Plan:
+    def __init__(self, estimator, cands, X, y, fold_id, n_splits):
+        self.estimator, self.cands = estimator, cands
+        self.X, self.y, self.fold_id, self.n_splits = _as_matrix(X), y, fold_id, n_splits
+        self.engine = get_engine()
+        self._prof = {}
+
+    def profile(self):
+        return dict(self._prof)
+
+    def close(self):
+        pass
+
+    def _base_params(self, cand):
+        p = self.estimator.get_params(deep=False)
+        unknown = set(cand) - set(p)
+        if unknown:
+            raise ValueError("Invalid parameter(s) %s for estimator %s" % (sorted(unknown), self.estimator))
+        p.update(cand)
+        return p
+
+    def _finish(self, res, return_train, error_score, n_my):
+        test, train = res["test"], res.get("train")
+        bad = ~np.isfinite(test)
+        if bad.any():
+            if error_score == 'raise':
+                raise FloatingPointError("non-finite score from the CUDA path")
+            warnings.warn("non-finite scores replaced by error_score=%r" % (error_score,))
+            test[bad] = error_score
+            if train is not None:
+                train[~np.isfinite(train)] = error_score
+        return dict(test=test, train=train if return_train else None,
+                    fit_time=res["fit_ms"] * 1e-3, score_time=res["score_ms"] * 1e-3)
+
+
+# ------------------------------------------------------------------ SVC -----------------------
+class SVCAdapter:
+    @staticmethod
+    def plan(estimator, cands, X, y, fold_id, n_splits):
+        return SVCPlan(estimator, cands, X, y, fold_id, n_splits)
+
+
+class SVCPlan(_Plan):
+    """sklearn.svm.SVC (C-SVC).  Scalars per candidate: kernel, C, gamma (resolved per fold)."""
+
+    def __init__(self, estimator, cands, X, y, fold_id, n_splits):
+        super().__init__(estimator, cands, X, y, fold_id, n_splits)
+        if y is None:
+            raise ValueError("SVC needs y")
+        self.classes, self.y_class = np.unique(np.asarray(y), return_inverse=True)
+        if len(self.classes) < 2:
+            raise ValueError("The number of classes has to be greater than one; got %d class" % len(self.classes))
+        self.engine.set_data(self.X, fold_id, n_splits, y_class=self.y_class.astype(np.int32))
+        self._var_cache = {}
+
+    def _check(self, p):
+        if p["kernel"] not in ("rbf", "linear"):
+            raise NotImplementedError("SVC kernel=%r has no CUDA path (rbf and linear do)" % (p["kernel"],))
+        if p.get("class_weight") is not None:
+            raise NotImplementedError("SVC class_weight is not supported by the CUDA path")
+        if p.get("probability") not in (False, "deprecated", None):
+            raise NotImplementedError("SVC probability=True is not supported by the CUDA path")
+        if p.get("break_ties"):
+            raise NotImplementedError("SVC break_ties=True is not supported by the CUDA path")
+        if not (isinstance(p["C"], numbers.Real) and p["C"] > 0):
+            raise ValueError("C must be a positive number; got %r" % (p["C"],))
+
+    def _gamma(self, g, k):
+        """sklearn svm/_base.py:278-286; 'scale' uses the variance of the TRAINING fold (float64)."""
+        if isinstance(g, str):
+            if g == "auto":
+                return 1.0 / self.X.shape[1]
+            if g == "scale":
+                if k not in self._var_cache:
+                    rows = self.fold_id != k if k >= 0 else np.ones(len(self.fold_id), bool)
+                    self._var_cache[k] = np.asarray(self.X[rows], np.float64).var()
+                v = self._var_cache[k]
+                return 1.0 / (self.X.shape[1] * v) if v != 0 else 1.0
+            raise ValueError("gamma=%r" % (g,))
+        if not (isinstance(g, numbers.Real) and g >= 0):
+            raise ValueError("gamma must be >= 0 or 'scale'/'auto'; got %r" % (g,))
+        return float(g)
+
+    def evaluate(self, my, return_train=True, error_score='raise'):
+        ns = self.n_splits
+        shape = (len(my), ns)
+        res = dict(test=np.zeros(shape), train=np.zeros(shape), fit_ms=np.zeros(shape), score_ms=np.zeros(shape),
+                   n_iter=np.zeros(shape, np.int64))
+        groups = {}
+        params = []
+        for j, ci in enumerate(my):
+            p = self._base_params(self.cands[ci])
+            self._check(p)
+            params.append(p)
+            groups.setdefault((float(p["tol"]), int(p["max_iter"]), bool(p["shrinking"])), []).append(j)
+        prof = {}
+        for (tol, max_iter, shrinking), idx in groups.items():
+            kern = [params[j]["kernel"] for j in idx]
+            C = [float(params[j]["C"]) for j in idx]
+            gam = np.array([[self._gamma(params[j]["gamma"], k) if params[j]["kernel"] == "rbf" else 0.0
+                             for k in range(ns)] for j in idx])
+            r = self.engine.svc(kern, C, gam, tol=tol, max_iter=max_iter, shrinking=shrinking,
+                                return_train=return_train)
+            for key in ("test", "fit_ms", "score_ms", "n_iter"):
+                res[key][idx] = r[key]
+            if return_train:
+                res["train"][idx] = r["train"]
+            for k, v in self.engine.profile().items():
+                prof[k] = prof.get(k, 0) + v
+        self._prof = prof
+        self.n_iter_ = res["n_iter"]
+        return self._finish(res, return_train, error_score, len(my))
+
+    def refit(self, best_params):
+        p = self._base_params(best_params)
+        self._check(p)
+        gamma = self._gamma(p["gamma"], -1)          # all rows train (svm/_base.py:278-286)
+        coef, rho, n_iter = self.engine.svc_refit(p["kernel"], p["C"], gamma if p["kernel"] == "rbf" else 0.0,
+                                                  len(self.classes), tol=p["tol"], max_iter=p["max_iter"],
+                                                  shrinking=p["shrinking"])
+        est = clone(self.estimator).set_params(**best_params)
+        return materialize_svc(est, self.X, self.y_class, self.classes, coef, rho, n_iter, gamma)
+
+
+def materialize_svc(est, X, y_class, classes, pair_coef, rho, n_iter, gamma):
+    """Fill a (cloned, parametrised) sklearn.svm.SVC with the fitted state libsvm would have produced
+    (sklearn svm.cpp:2529-2640 model assembly; svm/_base.py:300-327 attribute post-processing)."""
+    n_class = len(classes)
+    X64 = np.ascontiguousarray(X, np.float64)
+    order = np.argsort(y_class, kind="stable")                    # svm_group_classes: by class, stable
+    nonzero = np.any(pair_coef != 0, axis=0)
+    sv = order[nonzero[order]]                                    # SV rows in libsvm's grouped order
+    sv_class = y_class[sv]
+    n_support = np.array([(sv_class == c).sum() for c in range(n_class)], np.int32)
+    dual = np.zeros((n_class - 1, len(sv)))
+    p = 0
+    for i in range(n_class):
+        for j in range(i + 1, n_class):
+            mi, mj = sv_class == i, sv_class == j
+            dual[j - 1, mi] = pair_coef[p, sv[mi]]                # svm.cpp:2611-2632
+            dual[i, mj] = pair_coef[p, sv[mj]]
+            p += 1
+    est.classes_ = classes
+    est.class_weight_ = np.ones(n_class)
+    est._sparse = False
+    est._gamma = float(gamma)
+    est.support_ = sv.astype(np.int32)
+    est.support_vectors_ = X64[sv]
+    est._n_support = n_support
+    est._dual_coef_ = dual
+    est._intercept_ = -np.asarray(rho, np.float64)                # libsvm wrapper stores -rho
+    est.dual_coef_ = dual.copy()
+    est.intercept_ = est._intercept_.copy()
+    if n_class == 2:                                              # svm/_base.py:305-308
+        est.intercept_ *= -1
+        est.dual_coef_ = -est.dual_coef_
+    est._probA = np.empty(0)
+    est._probB = np.empty(0)
+    est._effective_probability = False
+    est.fit_status_ = 0
+    est._num_iter = np.asarray(n_iter, np.int32)
+    est.n_iter_ = est._num_iter
+    est.shape_fit_ = X.shape
+    est.n_features_in_ = X.shape[1]
+    return est
+
+
+# ------------------------------------------------------------------ Ridge ---------------------
+class RidgeAdapter:
+    @staticmethod
+    def plan(estimator, cands, X, y, fold_id, n_splits):
+        return RidgePlan(estimator, cands, X, y, fold_id, n_splits)
+
+
+class RidgePlan(_Plan):
+    def __init__(self, estimator, cands, X, y, fold_id, n_splits):
+        super().__init__(estimator, cands, X, y, fold_id, n_splits)
+        y = np.asarray(y)
+        if y.ndim != 1:
+            raise NotImplementedError("multi-output Ridge is not supported by the CUDA path")
+        self.engine.set_data(self.X.astype(np.float32, copy=False), fold_id, n_splits, y_target=y.astype(np.float32))
+
+    def _check(self, p):
+        if p.get("solver", "auto") not in ("auto", "cholesky"):
+            raise NotImplementedError("Ridge solver=%r has no CUDA path (auto/cholesky do)" % (p["solver"],))
+        if p.get("positive"):
+            raise NotImplementedError("Ridge positive=True is not supported by the CUDA path")
+        if not (isinstance(p["alpha"], numbers.Real) and p["alpha"] >= 0):
+            raise ValueError("alpha must be a non-negative number; got %r" % (p["alpha"],))
+
+    def evaluate(self, my, return_train=True, error_score='raise'):
+        shape = (len(my), self.n_splits)
+        res = dict(test=np.zeros(shape), train=np.zeros(shape), fit_ms=np.zeros(shape), score_ms=np.zeros(shape))
+        groups = {}
+        for j, ci in enumerate(my):
+            p = self._base_params(self.cands[ci])
+            self._check(p)
+            groups.setdefault(bool(p["fit_intercept"]), []).append((j, float(p["alpha"])))
+        prof = {}
+        for fi, items in groups.items():
+            idx = [j for j, _ in items]
+            r = self.engine.ridge([a for _, a in items], fit_intercept=fi, return_train=return_train)
+            for key in ("test", "fit_ms", "score_ms"):
+                res[key][idx] = r[key]
+            if return_train:
+                res["train"][idx] = r["train"]
+            for k, v in self.engine.profile().items():
+                prof[k] = prof.get(k, 0) + v
+        self._prof = prof
+        return self._finish(res, return_train, error_score, len(my))
+
+    def refit(self, best_params):
+        p = self._base_params(best_params)
+        self._check(p)
+        w, b = self.engine.ridge_refit(p["alpha"], p["fit_intercept"])
+        est = clone(self.estimator).set_params(**best_params)
+        dt = np.float32 if self.X.dtype == np.float32 else np.float64
+        est.coef_ = w.astype(dt)
+        est.intercept_ = dt(b) if p["fit_intercept"] else 0.0
+        est.n_iter_ = None
+        est.solver_ = "cholesky"
+        est.n_features_in_ = self.X.shape[1]
+        return est
+
+
+# ------------------------------------------------------------------ LogisticRegression --------
+class LogRegAdapter:
+    @staticmethod
+    def plan(estimator, cands, X, y, fold_id, n_splits):
+        return LogRegPlan(estimator, cands, X, y, fold_id, n_splits)
+
+
+class LogRegPlan(_Plan):
+    def __init__(self, estimator, cands, X, y, fold_id, n_splits):
+        super().__init__(estimator, cands, X, y, fold_id, n_splits)
+        self.classes, self.y_class = np.unique(np.asarray(y), return_inverse=True)
+        if len(self.classes) != 2:
+            raise NotImplementedError("LogisticRegression CUDA path is binary only (got %d classes)" % len(self.classes))
+        self.engine.set_data(self.X.astype(np.float32, copy=False), fold_id, n_splits,
+                             y_class=self.y_class.astype(np.int32))
+
+    def _check(self, p):
+        if p.get("solver", "lbfgs") != "lbfgs":
+            raise NotImplementedError("LogisticRegression solver=%r has no CUDA path (lbfgs does)" % (p["solver"],))
+        if p.get("penalty", "l2") not in ("l2", "deprecated", None) and p.get("l1_ratio") not in (None, 0, 0.0):
+            raise NotImplementedError("only the L2 penalty has a CUDA path")
+        if p.get("class_weight") is not None:
+            raise NotImplementedError("LogisticRegression class_weight is not supported by the CUDA path")
+        if not (isinstance(p["C"], numbers.Real) and p["C"] > 0):
+            raise ValueError("C must be a positive number; got %r" % (p["C"],))
+
+    def evaluate(self, my, return_train=True, error_score='raise'):
+        shape = (len(my), self.n_splits)
+        res = dict(test=np.zeros(shape), train=np.zeros(shape), fit_ms=np.zeros(shape), score_ms=np.zeros(shape))
+        groups = {}
+        for j, ci in enumerate(my):
+            p = self._base_params(self.cands[ci])
+            self._check(p)
+            groups.setdefault((float(p["tol"]), int(p["max_iter"]), bool(p["fit_intercept"])), []).append((j, float(p["C"])))
+        prof = {}
+        for (tol, mi, fi), items in groups.items():
+            idx = [j for j, _ in items]
+            r = self.engine.logreg([c for _, c in items], tol=tol, max_iter=mi, fit_intercept=fi,
+                                   return_train=return_train)
+            for key in ("test", "fit_ms", "score_ms"):
+                res[key][idx] = r[key]
+            if return_train:
+                res["train"][idx] = r["train"]
+            for k, v in self.engine.profile().items():
+                prof[k] = prof.get(k, 0) + v
+        self._prof = prof
+        return self._finish(res, return_train, error_score, len(my))
+
+    def refit(self, best_params):
+        p = self._base_params(best_params)
+        self._check(p)
+        w, b, it = self.engine.logreg_refit(p["C"], p["tol"], p["max_iter"], p["fit_intercept"])
+        est = clone(self.estimator).set_params(**best_params)
+        est.classes_ = self.classes
+        est.coef_ = w.reshape(1, -1)
+        est.intercept_ = np.array([b if p["fit_intercept"] else 0.0])
+        est.n_iter_ = np.array([it], np.int32)
+        est.n_features_in_ = self.X.shape[1]
+        return est

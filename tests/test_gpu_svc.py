@@ -1,0 +1,156 @@
+"""GPU parity tests for the SVC path, through the C ABI (libb200gs.so) -- run under gpurun.
+
+Checker: the oracle (oracle/svc_oracle.c, pinned against scikit-learn in test_oracle.py) on the same
+seeded inputs, and the committed goldens (scikit-learn 1.9.0 itself).  Bar: integer work (n_iter,
+vote counts -> accuracies) bit-exact; float64 Gram to 1e-13 relative; float32 kernel matrix equal
+to the oracle's on all but a vanishing fraction of entries (float64 exp last-bit differences).
+"""
+import numpy as np
+import pytest
+
+from conftest import golden
+from spark_sklearn_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(engine, key):
+    from oracle import oracle as O
+    w = W.make_workload(key)
+    fold_id, ns = O.folds_from_cv(w["cv"], w["X"], w["y"], True)
+    classes, yc = np.unique(w["y"], return_inverse=True)
+    engine.set_data(w["X"], fold_id, ns, y_class=yc.astype(np.int32))
+    return w, fold_id, ns
+
+
+def test_gram_f64_and_kernel_matrix(engine):
+    w, fold_id, ns = _setup(engine, "c2_small")
+    X64 = w["X"].astype(np.float64)
+    S, xsq = engine.debug_gram()
+    ref = X64 @ X64.T
+    assert np.abs(S - ref).max() <= 1e-13 * np.abs(ref).max()
+    np.testing.assert_array_equal(xsq, np.diag(S))
+    np.testing.assert_array_equal(S, S.T)
+    for gamma in (1 / 512, 1 / 32):
+        K = engine.debug_kernel_matrix("rbf", gamma)
+        d2 = (xsq[:, None] + xsq[None, :]) - 2 * S
+        Kref = np.exp(-gamma * d2).astype(np.float32)
+        frac = np.mean(K != Kref)
+        assert frac < 1e-5, frac                   # last-bit exp differences only
+        assert np.abs(K.astype(np.float64) - Kref).max() <= 1.2e-7
+        np.testing.assert_array_equal(np.diag(K), np.ones(len(K), np.float32))
+    Kl = engine.debug_kernel_matrix("linear", 0.0)
+    np.testing.assert_array_equal(Kl, S.astype(np.float32))
+
+
+def test_gram_ragged_shapes(engine):
+    rng = np.random.RandomState(1)
+    for n, d in ((131, 7), (257, 33), (64, 130)):
+        X = rng.randn(n, d).astype(np.float32)
+        y = (np.arange(n) % 2).astype(np.int32)
+        engine.set_data(X, np.zeros(n, np.int8) + (np.arange(n) % 2).astype(np.int8), 2, y_class=y)
+        S, xsq = engine.debug_gram()
+        ref = X.astype(np.float64) @ X.astype(np.float64).T
+        assert np.abs(S - ref).max() <= 1e-13 * np.abs(ref).max()
+    Xd = rng.randn(90, 5)                           # float64 features (iris-like): products not exact
+    engine.set_data(Xd, (np.arange(90) % 3).astype(np.int8), 3, y_class=(np.arange(90) % 2).astype(np.int32))
+    S, _ = engine.debug_gram()
+    assert np.abs(S - Xd @ Xd.T).max() <= 1e-14 * np.abs(S).max() * 5
+
+
+def _run(engine, w, cands):
+    kern = [c.get("kernel", w["est_params"].get("kernel", "rbf")) for c in cands]
+    C = [float(c.get("C", 1.0)) for c in cands]
+    d = w["X"].shape[1]
+    gam = []
+    for c in cands:
+        g = c.get("gamma", w["est_params"].get("gamma", "scale"))
+        gam.append(1.0 / d if g == "auto" else float(g))
+    return engine.svc(kern, C, np.array(gam)[:, None], tol=1e-3, max_iter=-1, shrinking=True, return_train=True)
+
+
+def test_c1_iris_bitexact(engine):
+    """BASELINE config 1: 3 classes (one-vs-one), linear + rbf, float64 features."""
+    w, fold_id, ns = _setup(engine, "c1")
+    g = golden("c1_iris_svc")
+    r = _run(engine, w, W.candidates(w))
+    np.testing.assert_array_equal(r["test"], g["test_scores"])
+    np.testing.assert_array_equal(r["train"], g["train_scores"])
+    np.testing.assert_array_equal(r["n_iter"], g["diag"][:, :, 0].astype(np.int32))
+    np.testing.assert_allclose(r["test"].mean(1), [0.98, 0.98, 0.9733333333, 0.98], atol=1e-9)
+
+
+@pytest.mark.parametrize("key", ["c2_small", "c2_mid"])
+def test_c2_reduced_bitexact(engine, key):
+    """Same recipe as BASELINE config 2 at sizes the CPU finishes in seconds; c2_mid (l=2400) exercises
+    shrinking, gradient reconstruction and the swap permutation."""
+    w, fold_id, ns = _setup(engine, key)
+    g = golden(key)
+    r = _run(engine, w, W.candidates(w))
+    np.testing.assert_array_equal(r["n_iter"], g["diag"][:, :, 0].astype(np.int32))   # same trajectory
+    np.testing.assert_array_equal(r["n_sv"], g["diag"][:, :, 1].astype(np.int32))
+    np.testing.assert_array_equal(r["test"], g["test_scores"])
+    np.testing.assert_array_equal(r["train"], g["train_scores"])
+
+
+def test_smo_against_oracle_on_gpu_kernel_matrix(engine):
+    """Hand the oracle the very float32 kernel matrix the GPU built: alpha*y and rho must be bit-identical."""
+    from oracle import oracle as O
+    w, fold_id, ns = _setup(engine, "c2_small")
+    X64, y = w["X"].astype(np.float64), w["y"]
+    gamma, C = 1 / 64, 10.0
+    K = engine.debug_kernel_matrix("rbf", gamma)
+    engine.set_data(w["X"], np.full(len(y), -1, np.int8), 1, y_class=y.astype(np.int32))   # refit view: all rows
+    coef, rho, it = engine.svc_refit("rbf", C, gamma, 2)
+    rows = np.concatenate([np.flatnonzero(y == 0), np.flatnonzero(y == 1)]).astype(np.int32)
+    oc, orho, oit, _ = O.svc_solve(X64, rows, int((y == 0).sum()), "rbf", gamma, C, Kpre=K)
+    full = np.zeros(len(y)); full[rows] = oc
+    assert it[0] == oit
+    np.testing.assert_array_equal(coef[0], full)
+    assert rho[0] == orho
+
+
+def test_no_shrinking_and_max_iter(engine):
+    from sklearn.svm import SVC
+    import warnings
+    w, fold_id, ns = _setup(engine, "c2_small")
+    X, y = w["X"], w["y"]
+    for kw in (dict(shrinking=False, max_iter=-1), dict(shrinking=True, max_iter=300)):
+        r = engine.svc(["rbf"], [10.0], [[1 / 64]], tol=1e-3, return_train=True, **kw)
+        for k in range(ns):
+            tr, te = np.flatnonzero(fold_id != k), np.flatnonzero(fold_id == k)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                s = SVC(C=10.0, gamma=1 / 64, **kw).fit(X[tr], y[tr])
+            assert r["n_iter"][0, k] == s.n_iter_[0]
+            assert r["test"][0, k] == s.score(X[te], y[te])
+            assert r["train"][0, k] == s.score(X[tr], y[tr])
+
+
+def test_python_api_iris(engine):
+    """The reference's own example (tests/test_search_2.py:32-45, README): iris, SVC(gamma='auto')."""
+    from sklearn import svm
+    from sklearn.base import clone
+    from sklearn.model_selection import GridSearchCV as SkGrid
+    from spark_sklearn_b200 import GridSearchCV
+    w = W.make_workload("c1")
+    X, y = w["X"], w["y"]
+    parameters = {'kernel': ('linear', 'rbf'), 'C': [1, 10]}
+    clf = GridSearchCV(None, svm.SVC(gamma='auto'), parameters, cv=5).fit(X, y)
+    sk = SkGrid(svm.SVC(gamma='auto'), parameters, cv=5, return_train_score=True).fit(X, y)
+    for key in sk.cv_results_:
+        if key.endswith("_time"):
+            assert key in clf.cv_results_
+            continue
+        a, b = clf.cv_results_[key], sk.cv_results_[key]
+        if key == "params":
+            assert a == b
+        elif key.startswith("param_"):
+            assert list(a) == list(b)
+        else:
+            np.testing.assert_array_equal(np.asarray(a, float), np.asarray(b, float), err_msg=key)
+    assert clf.best_index_ == sk.best_index_ and clf.best_params_ == sk.best_params_
+    np.testing.assert_array_equal(clf.predict(X), sk.predict(X))
+    np.testing.assert_allclose(clf.decision_function(X), sk.decision_function(X), rtol=0, atol=1e-12)
+    assert clf.score(X, y) == sk.score(X, y)
+    assert clf.estimator.get_params() == clone(svm.SVC(gamma='auto')).get_params()   # the reference's assertion

@@ -1,0 +1,104 @@
+"""CPU: pin the oracle (oracle/) against scikit-learn itself and against the committed goldens.
+
+The reference's own tests pin no numeric result on this path; its arithmetic is
+scikit-learn's, so the pin is scikit-learn 1.9.0 run in this image plus tests/golden/*.npz made by
+tests/golden/make_goldens.py.
+"""
+import numpy as np
+import pytest
+from sklearn.model_selection import StratifiedKFold
+from sklearn.svm import SVC
+
+from conftest import golden
+from oracle import oracle as O
+from spark_sklearn_b200 import workloads as W
+
+
+def _compare_with_sklearn(X, y, train, test, exact=True, **prm):
+    X64 = np.ascontiguousarray(X, np.float64)
+    m = O.SVCModel(X64, y, train, **prm)
+    s = SVC(**prm).fit(X[train], y[train])
+    assert list(s.n_iter_) == m.n_iter                      # same iterate sequence, not just same optimum
+    rho = np.array([p[4] for p in m.pairs])
+    if exact:
+        np.testing.assert_array_equal(rho, -s._intercept_)
+    else:       # float64 features: products are not exact, BLAS ddot's summation order shows at 1e-15
+        np.testing.assert_allclose(rho, -s._intercept_, rtol=1e-12)
+    if len(m.classes) == 2:
+        _, _, rows, coef, _ = m.pairs[0]
+        full = np.zeros(len(X)); full[rows] = coef
+        sk = np.zeros(len(X)); sk[np.asarray(train)[s.support_]] = s._dual_coef_[0]
+        np.testing.assert_array_equal(full, sk)             # bit-exact dual coefficients
+    np.testing.assert_array_equal(m.predict(test), s.predict(X[test]))
+    np.testing.assert_array_equal(m.predict(train), s.predict(X[train]))
+
+
+def test_svc_oracle_bitexact_iris():
+    w = W.make_workload("c1")
+    X, y = w["X"], w["y"]
+    tr, te = next(iter(StratifiedKFold(5).split(X, y)))
+    for kernel in ("linear", "rbf"):
+        for C in (1, 10):
+            _compare_with_sklearn(X, y, tr, te, exact=False, kernel=kernel, C=C, gamma="auto")
+
+
+@pytest.mark.parametrize("C,gamma", [(0.1, 1 / 64), (10.0, 1 / 128), (316.0, 1 / 1024), (1.0, "scale")])
+def test_svc_oracle_bitexact_with_shrinking(C, gamma):
+    w = W.make_workload("c2_mid")                          # l = 2400 > 1000: shrinking and unshrinking happen
+    X, y = w["X"], w["y"]
+    tr, te = next(iter(StratifiedKFold(5).split(X, y)))
+    _compare_with_sklearn(X, y, tr, te, kernel="rbf", C=C, gamma=gamma)
+
+
+def test_svc_oracle_vs_golden_c1_and_survey_table():
+    g = golden("c1_iris_svc")
+    # SURVEY.md §8c / BASELINE.md §2 table (generated during the survey with sklearn GridSearchCV)
+    np.testing.assert_allclose(g["mean_test_score"], [0.98, 0.98, 0.9733333333, 0.98], atol=1e-9)
+    np.testing.assert_allclose(g["mean_train_score"], [0.9816666667, 0.9833333333, 0.9783333333, 0.9766666667], atol=1e-9)
+    w = W.make_workload("c1")
+    fold_id, ns = O.folds_from_cv(w["cv"], w["X"], w["y"], True)
+    np.testing.assert_array_equal(fold_id, g["fold_id"])
+    test, train, _ = O.cv_scores_svc(w["X"], w["y"], fold_id, ns, W.candidates(w), w["est_params"])
+    np.testing.assert_array_equal(test, g["test_scores"])
+    np.testing.assert_array_equal(train, g["train_scores"])
+
+
+def test_svc_oracle_vs_golden_c2_small():
+    g = golden("c2_small")
+    w = W.make_workload("c2_small")
+    cands = W.candidates(w)[::3]
+    fold_id, ns = O.folds_from_cv(w["cv"], w["X"], w["y"], True)
+    test, train, iters = O.cv_scores_svc(w["X"], w["y"], fold_id, ns, cands, w["est_params"])
+    np.testing.assert_array_equal(test, g["test_scores"][::3])
+    np.testing.assert_array_equal(train, g["train_scores"][::3])
+    np.testing.assert_array_equal(iters, g["diag"][::3, :, 0].astype(np.int64))
+
+
+def test_golden_tasks_mode_equals_sklearn_search():
+    """make_goldens 'tasks' mode (the reference's task list) == sklearn GridSearchCV run as a whole."""
+    from sklearn.model_selection import GridSearchCV
+    w = W.make_workload("c2_small")
+    g = golden("c2_small")
+    s = GridSearchCV(W.make_estimator(w), w["param_grid"], cv=w["cv"], return_train_score=True).fit(w["X"], w["y"])
+    for k in range(5):
+        np.testing.assert_array_equal(s.cv_results_["split%d_test_score" % k], g["test_scores"][:, k])
+        np.testing.assert_array_equal(s.cv_results_["split%d_train_score" % k], g["train_scores"][:, k])
+
+
+def test_ridge_oracle_vs_golden():
+    g = golden("c5_small")
+    w = W.make_workload("c5_small")
+    fold_id, ns = O.folds_from_cv(w["cv"], w["X"], w["y"], False)
+    test, train = O.cv_scores_ridge(w["X"], w["y"], fold_id, ns, W.candidates(w)[::4])
+    np.testing.assert_allclose(test, g["test_scores"][::4], atol=2e-6)
+    np.testing.assert_allclose(train, g["train_scores"][::4], atol=2e-6)
+
+
+def test_logreg_oracle_vs_golden():
+    g = golden("c3_small")
+    w = W.make_workload("c3_small")
+    fold_id, ns = O.folds_from_cv(w["cv"], w["X"], w["y"], True)
+    test, train = O.cv_scores_logreg(w["X"], w["y"], fold_id, ns, W.candidates(w)[::4])
+    # L-BFGS stops early (gtol); the restated objective follows the same path up to float32 rounding
+    assert np.abs(test - g["test_scores"][::4]).max() <= 2.5e-3
+    assert np.abs(test.mean(1) - g["test_scores"][::4].mean(1)).max() <= 1e-3
