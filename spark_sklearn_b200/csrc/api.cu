@@ -295,10 +295,21 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
     for (int g0 = 0; g0 < n_groups; g0 += gpb) {
         const int g1 = std::min(n_groups, g0 + gpb);
         // -- kernel matrices of this batch --
+        GS_CUDA(h->dWork[7].reserve(64));
+        GS_CUDA(cudaMemsetAsync(h->dWork[7].p, 0, 4, st));
+        bool fast = true;
         for (int g = g0; g < g1; g++) {
             GS_CUDA(launch_kernel_matrix(h->dS.as<double>(), h->dXsq.as<double>(), n, groups[g].first, groups[g].second,
-                                         h->dK.as<float>() + (size_t)(g - g0) * n * ldk, ldk, st));
+                                         h->dK.as<float>() + (size_t)(g - g0) * n * ldk, ldk, h->dWork[7].as<int>(), st));
             pf.launches++;
+            fast = fast && groups[g].first == GS_KERNEL_RBF;
+        }
+        {   // the branch-free SMO instance needs rbf (QD == 1) and only positive normal floats in K
+            int special = 0;
+            GS_CUDA(cudaMemcpyAsync(&special, h->dWork[7].p, 4, cudaMemcpyDeviceToHost, st));
+            GS_CUDA(cudaStreamSynchronize(st));
+            pf.d2h_bytes += 4;
+            fast = fast && special == 0;
         }
         tm.mark(1);
         // -- problems: ordered by (group, task, pair); column index == problem index --
@@ -379,7 +390,7 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
         tm.mark(4);
         // -- solve --
         std::string why;
-        cudaError_t ce = launch_smo(d_probs, d_order, np, lmax, st, &why);
+        cudaError_t ce = launch_smo(d_probs, d_order, np, lmax, fast, st, &why);
         if (ce != cudaSuccess) { gs_set_error(h, why.empty() ? std::string("launch_smo: ") + cudaGetErrorString(ce) : why); return why.empty() ? GS_ERR_CUDA : GS_ERR_UNSUPPORTED; }
         pf.launches++;
         tm.mark(2);
@@ -511,7 +522,7 @@ int gs_debug_kernel_matrix(gs_handle *h, int32_t kernel, double gamma, float *K_
     const int n = (int)h->n;
     const int64_t ldk = ((int64_t)n + 31) & ~31LL;
     GS_CUDA(h->dK.reserve((size_t)n * ldk * 4));
-    GS_CUDA(launch_kernel_matrix(h->dS.as<double>(), h->dXsq.as<double>(), n, kernel, gamma, h->dK.as<float>(), ldk, h->stream));
+    GS_CUDA(launch_kernel_matrix(h->dS.as<double>(), h->dXsq.as<double>(), n, kernel, gamma, h->dK.as<float>(), ldk, nullptr, h->stream));
     std::vector<float> K((size_t)n * ldk);
     GS_CUDA(cudaMemcpyAsync(K.data(), h->dK.p, K.size() * 4, cudaMemcpyDeviceToHost, h->stream));
     GS_CUDA(cudaStreamSynchronize(h->stream));

@@ -62,8 +62,9 @@ void gs_set_error(gs_handle *h, const std::string &msg);
 // S = X X^T in float64 from float32 X (exact products, float64 accumulation); xsq = diag(S).
 cudaError_t launch_gram_f64(const void *X, int x_dtype, int n, int d, double *S, double *xsq, cudaStream_t st);
 // K[r][c] = (float) k(x_r, x_c) from S: rbf exp(-gamma*(xsq_r + xsq_c - 2 S_rc)) or linear S_rc.
+// *special (device int, pre-zeroed, may be null) is set when an entry is not a positive normal float.
 cudaError_t launch_kernel_matrix(const double *S, const double *xsq, int n, int kernel, double gamma,
-                                 float *K, int64_t ldk, cudaStream_t st);
+                                 float *K, int64_t ldk, int *special, cudaStream_t st);
 
 // ---- smo.cu ----
 struct SmoProblem {
@@ -82,8 +83,8 @@ struct SmoProblem {
     int l, n_pos, max_iter, shrinking;
 };
 // Solve problems order[0..n_prob) (one CTA each); lmax = max l (selects the template instance).
-cudaError_t launch_smo(const SmoProblem *d_probs, const int *d_order, int n_prob, int lmax, cudaStream_t st,
-                       std::string *why);
+cudaError_t launch_smo(const SmoProblem *d_probs, const int *d_order, int n_prob, int lmax, bool fast,
+                       cudaStream_t st, std::string *why);
 int smo_max_rows();   // largest sub-problem the resident-state kernel supports
 
 // ---- score.cu ----

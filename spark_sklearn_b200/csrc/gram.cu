@@ -112,8 +112,9 @@ gram_f64_kernel(const T *__restrict__ X, int n, int d, double *__restrict__ S, d
 // of svm.cpp:344-347, each operation individually rounded (no contraction); linear: S_rc.
 __global__ void __launch_bounds__(256)
 kernel_matrix_kernel(const double *__restrict__ S, const double *__restrict__ xsq, int n, int kernel, double gamma,
-                     float *__restrict__ K, int64_t ldk)
+                     float *__restrict__ K, int64_t ldk, int *__restrict__ special)
 {
+    bool odd = false;
     const int r = blockIdx.y;
     const double xr = xsq[r];
     const double ng = -gamma;
@@ -126,8 +127,12 @@ kernel_matrix_kernel(const double *__restrict__ S, const double *__restrict__ xs
         } else {
             v = s;
         }
-        K[(size_t)r * ldk + c] = (float)v;
+        const float kf = (float)v;
+        K[(size_t)r * ldk + c] = kf;
+        const unsigned e = __float_as_uint(kf) >> 23;           // sign + exponent: positive normal <=> 1..254
+        odd |= (e == 0u || e >= 255u);
     }
+    if (special && __any_sync(0xffffffffu, odd) && (threadIdx.x & 31) == 0) atomicOr(special, 1);
 }
 
 }  // namespace
@@ -142,10 +147,10 @@ cudaError_t launch_gram_f64(const void *X, int x_dtype, int n, int d, double *S,
 }
 
 cudaError_t launch_kernel_matrix(const double *S, const double *xsq, int n, int kernel, double gamma,
-                                 float *K, int64_t ldk, cudaStream_t st)
+                                 float *K, int64_t ldk, int *special, cudaStream_t st)
 {
     dim3 grid((n + 1023) / 1024, n);
     if (grid.x < 1) grid.x = 1;
-    kernel_matrix_kernel<<<grid, 256, 0, st>>>(S, xsq, n, kernel, gamma, K, ldk);
+    kernel_matrix_kernel<<<grid, 256, 0, st>>>(S, xsq, n, kernel, gamma, K, ldk, special);
     return cudaGetLastError();
 }

@@ -81,18 +81,6 @@ __device__ __forceinline__ double rcp_approx(double x)
     return r;
 }
 
-// K-row gather flavours: 0 = ld.global.nc (L1-allocating), 1 = ld.global.cg (L2 only), 2 = nc + L1::no_allocate
-template <int LD>
-__device__ __forceinline__ float load_k(const float *p)
-{
-    if constexpr (LD == 1) return __ldcg(p);
-    else if constexpr (LD == 2) {
-        float v;
-        asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-        return v;
-    } else return __ldg(p);
-}
-
 struct KArg { unsigned hi, lo; int idx; };
 
 // warp arg-max over (64-bit key, index): largest key, ties -> largest index.  3 REDUX.
@@ -113,10 +101,12 @@ __device__ __forceinline__ unsigned long long warp_keymax(unsigned long long k)
 }
 
 struct Red {            // static shared scratch; NW <= 32 warps
-    unsigned a_hi[32], a_lo[32]; int a_idx[32];                 // phase A partials
-    unsigned b_hi[32], b_lo[32]; int b_idx[32];                 // phase B partials
-    unsigned m_hi[32], m_lo[32];                                // Gmax2 partials
-    double pl_mg[32], pl_kv[32], pl_alpha[32];                  // phase B payload of each warp's winner
+    unsigned a_hi[32], a_lo[32]; int a_idx[32];                 // phase A partials (arg-max m over I_up)
+    unsigned m_hi[32], m_lo[32];                                // Gmax2 partials (max -m over I_low)
+    unsigned b_hi[32], b_lo[32]; int b_idx[32];                 // phase B partials (approximate arg-max)
+    unsigned t_hi[32], t_lo[32];                                // phase B runner-up partials
+    unsigned x_hi[32], x_lo[32]; int x_idx[32];                 // exact tie-break partials (rare path)
+    double pl_mg[32], pl_kv[32], pl_alpha[32];                  // payload of each warp's winner
     double bc_d[4]; int bc_i[4];                                // scalars broadcast by warp 0
     double dm[32], dm2[32]; int cnt[32];                        // cold-path reductions
 };
@@ -155,54 +145,61 @@ __device__ __forceinline__ int block_rank(bool pred, int *cnt, int &total)
     return base + __popc(b & ((1u << lane) - 1u));
 }
 
-template <int NT, int KPT, bool SMEM_STATE, int LD, bool PROF>
+// FAST: every problem of the launch is rbf (QD == 1) and its K matrix holds only positive normal floats,
+// so the widening is three integer instructions and quad = 2 - 2K needs no diagonal lookups.
+template <int NT, int KPT, bool SMEM_STATE, bool FAST, bool PROF>
 __global__ void __launch_bounds__(NT, 1)
-smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, int lcap)
+smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ Red red;
     constexpr int NW = NT / 32;
+    constexpr int LCAP = NT * KPT;                                          // compile-time layout: no address math
 
-    const SmoProblem P = probs[order[blockIdx.x]];
+    const SmoProblem *__restrict__ Pp = probs + order[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int l = P.l;
+    const int l = Pp->l;
     // ---- resident state ----
-    double *mG = reinterpret_cast<double *>(smem_raw);                      // m_t = -y_t G_t
+    double *const mG = reinterpret_cast<double *>(smem_raw);                // m_t = -y_t G_t
     double *mGbar, *alpha;
-    unsigned char *after;
+    unsigned short *col;                                                    // dataset row of each position
     if constexpr (SMEM_STATE) {
-        mGbar = mG + lcap; alpha = mGbar + lcap;
-        after = reinterpret_cast<unsigned char *>(alpha + lcap);
+        mGbar = mG + LCAP; alpha = mG + 2 * LCAP;
+        col = reinterpret_cast<unsigned short *>(mG + 3 * LCAP);
     } else {
-        mGbar = P.Gbar; alpha = P.alpha;
-        after = reinterpret_cast<unsigned char *>(mG + lcap);
+        mGbar = Pp->Gbar; alpha = Pp->alpha;
+        col = reinterpret_cast<unsigned short *>(mG + LCAP);
     }
-    unsigned short *col = reinterpret_cast<unsigned short *>(after);       // dataset row of each position
-    unsigned char *fl = reinterpret_cast<unsigned char *>(col + lcap);
-    const float *__restrict__ K = P.K;
-    const int64_t ldk = P.ldk;
-    const double C = P.C, eps = P.eps;
-    const bool use_gbar = P.shrinking != 0;
-    const double *__restrict__ qd = P.qd;
+    unsigned char *const fl = reinterpret_cast<unsigned char *>(col + LCAP);
+    const float *__restrict__ const K = Pp->K;
+    const int64_t ldk = Pp->ldk;
+    const double eps = Pp->eps;
+    const bool use_gbar = Pp->shrinking != 0;
+    const double *__restrict__ const qd = FAST ? nullptr : Pp->qd;
+    int *const scratch = Pp->scratch;
 
     unsigned long long t_start = 0;
     if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
 
     // ---- initial point: alpha = 0, G = p = -1  =>  m_t = y_t (svm.cpp:1611-1626, :716-736) ----
-    for (int t = tid; t < l; t += NT) {
-        const bool yp = t < P.n_pos;
-        mG[t] = yp ? 1.0 : -1.0;
-        col[t] = (unsigned short)P.rows[t];
-        fl[t] = (unsigned char)mkflags(yp, ST_LOWER);
-        alpha[t] = 0.0;
-        if (use_gbar) mGbar[t] = 0.0;
+    {
+        const int n_pos = Pp->n_pos;
+        const int *__restrict__ rows = Pp->rows;
+        for (int t = tid; t < l; t += NT) {
+            const bool yp = t < n_pos;
+            mG[t] = yp ? 1.0 : -1.0;
+            col[t] = (unsigned short)rows[t];
+            fl[t] = (unsigned char)mkflags(yp, ST_LOWER);
+            alpha[t] = 0.0;
+            if (use_gbar) mGbar[t] = 0.0;
+        }
     }
     __syncthreads();
 
     int active = l, iter = 0, timed_out = 0;
     int counter = (l < 1000 ? l : 1000) + 1;
     bool unshrink = false;
-    const int max_iter = P.max_iter == -1 ? SAFETY_MAX_ITER : P.max_iter;
+    const int max_iter = Pp->max_iter == -1 ? SAFETY_MAX_ITER : Pp->max_iter;
 
     long long prof[6] = {0, 0, 0, 0, 0, 0};
     long long tprev = PROF ? clock64() : 0;
@@ -213,9 +210,38 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
             tprev = now;
         }
     };
+
     double qi[KPT];      // unsigned K_i row (widened) at the owned active positions t = k*NT + tid
 
-    auto QD = [&](int t) -> double { return qd ? qd[col[t]] : 1.0; };   // svm.cpp:1436-1437
+    auto QD = [&](int t) -> double {                                        // svm.cpp:1436-1437
+        if constexpr (FAST) return 1.0;
+        else return qd ? qd[col[t]] : 1.0;
+    };
+    auto widen = [&](float x) -> double {
+        if constexpr (FAST) {
+            const unsigned u = __float_as_uint(x);
+            return __hiloint2double((int)((u >> 3) + 0x38000000u), (int)(u << 29));
+        } else return f2d(x);
+    };
+
+    // ---------------- local scan: this thread's candidates for the next working-set selection -------
+    // la/la_idx: arg-max m over its I_up positions (ties -> larger position); lm: min m over its I_low
+    // positions (Gmax2 = max -m, svm.cpp:986-1031).  Normally produced for free by the update loop.
+    double la = -CUDART_INF, lm = CUDART_INF;
+    int la_idx = -1;
+    auto local_scan = [&]() {
+        la = -CUDART_INF; lm = CUDART_INF; la_idx = -1;
+#pragma unroll
+        for (int k = 0; k < KPT; k++) {
+            const int t = k * NT + tid;
+            if (t < active) {
+                const int f = fl[t];
+                const double m = mG[t];
+                if ((f & F_UP) && m >= la) { la = m; la_idx = (t << IDX_SHIFT) | f; }
+                if (f & F_LOW) lm = fmin(lm, m);
+            }
+        }
+    };
 
     // ---------------- reconstruct_gradient (svm.cpp:629-668), m-domain ----------------
     // G_k = (Gbar_k + p_k) + sum_{free f, ascending} alpha_f Q_fk   <=>
@@ -228,7 +254,7 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
             const bool isf = t < active && (fl[t] & 3) == ST_FREE;
             int tot;
             const int r = block_rank<NT>(isf, red.cnt, tot);
-            if (isf) P.scratch[nf + r] = t;
+            if (isf) scratch[nf + r] = t;
             nf += tot;
         }
         __syncthreads();
@@ -243,12 +269,12 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
         }
 #pragma unroll 2
         for (int r = 0; r < nf; r++) {
-            const int f = P.scratch[r];
+            const int f = scratch[r];
             const float *__restrict__ Kf = K + (size_t)col[f] * ldk;
             const double af = (fl[f] & F_YPOS) ? -alpha[f] : alpha[f];      // -y_f alpha_f
 #pragma unroll
             for (int k = 0; k < KPT; k++)
-                if (ck[k] >= 0) g[k] = __dadd_rn(g[k], __dmul_rn(af, f2d(load_k<LD>(Kf + ck[k]))));
+                if (ck[k] >= 0) g[k] = __dadd_rn(g[k], __dmul_rn(af, widen(__ldg(Kf + ck[k]))));
         }
 #pragma unroll
         for (int k = 0; k < KPT; k++) {
@@ -262,9 +288,95 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
     int pi = -1, pj = -1;            // packed (position << 5 | flags)
     double gmax = 0, mg_j = 0, k_ij = 0, alpha_i = 0, alpha_j = 0;
     auto select = [&]() -> bool {
-        // ---- phase A: i = argmax m_t over I_up ----
+        // ---- phase A: i = argmax m_t over I_up; Gmax2 = max -m_t over I_low (both from the local scan) ----
+        double gmax2;
         {
-            double best = -CUDART_INF;
+            const unsigned long long key = dkey(la);
+            const KArg w = warp_argmax((unsigned)(key >> 32), (unsigned)key, la_idx);
+            const unsigned long long km = warp_keymax(dkey(-lm));
+            if (lane == 0) {
+                red.a_hi[warp] = w.hi; red.a_lo[warp] = w.lo; red.a_idx[warp] = w.idx;
+                red.m_hi[warp] = (unsigned)(km >> 32); red.m_lo[warp] = (unsigned)km;
+            }
+            tick(0);
+            __syncthreads();                                                      // barrier 1
+            tick(1);
+            const bool v = lane < NW;
+            const KArg a = warp_argmax(v ? red.a_hi[lane] : 0u, v ? red.a_lo[lane] : 0u, v ? red.a_idx[lane] : -1);
+            const unsigned long long km2 =
+                warp_keymax(v ? (((unsigned long long)red.m_hi[lane] << 32) | red.m_lo[lane]) : 0ull);
+            pi = a.idx;
+            gmax = dkey_inv(((unsigned long long)a.hi << 32) | a.lo);
+            gmax2 = dkey_inv(km2);
+        }
+        if (pi < 0 || __dadd_rn(gmax, gmax2) < eps) return true;              // svm.cpp:1040-1041
+        // ---- phase B: j = argmin -(gd^2)/quad over I_low with gd > 0 (svm.cpp:980-1037) ----
+        // Approximate arg-max of gd^2/quad with a 20-bit reciprocal; it IS libsvm's choice unless the
+        // runner-up lies within the error band, in which case the exact quotients decide (rare path).
+        const int i = pi >> IDX_SHIFT;
+        alpha_i = alpha[i];
+        const double QDi = QD(i);
+        const float *__restrict__ Ki = K + (size_t)col[i] * ldk;
+        {
+            float kv[KPT];
+#pragma unroll
+            for (int k = 0; k < KPT; k++) {                                  // issue the whole gather first
+                const int t = k * NT + tid;
+                kv[k] = t < active ? __ldg(Ki + col[t]) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < KPT; k++) qi[k] = widen(kv[k]);
+        }
+        double best1 = -CUDART_INF, best2 = -CUDART_INF, m1 = 0, q1 = 0;
+        int idx1 = -1;
+#pragma unroll
+        for (int k = 0; k < KPT; k++) {
+            const int t = k * NT + tid;
+            if (t < active) {
+                const int f = fl[t];
+                const double m = mG[t];
+                const double gd = __dsub_rn(gmax, m);
+                if ((f & F_LOW) && gd > 0) {
+                    const double quad = FAST ? __dsub_rn(2.0, __dadd_rn(qi[k], qi[k]))
+                                             : __dsub_rn(__dadd_rn(QDi, QD(t)), __dmul_rn(2.0, qi[k]));
+                    const double g2 = __dmul_rn(gd, gd);
+                    const double ap = quad > 0 ? g2 * rcp_approx(quad) : g2 * 1e12;
+                    if (ap > best1) { best2 = best1; best1 = ap; idx1 = (t << IDX_SHIFT) | f; m1 = m; q1 = qi[k]; }
+                    else if (ap > best2) best2 = ap;
+                }
+            }
+        }
+        double top1, top2;
+        {
+            const unsigned long long key = dkey(best1);
+            const KArg w = warp_argmax((unsigned)(key >> 32), (unsigned)key, idx1);
+            const unsigned long long k2 = warp_keymax(dkey(idx1 == w.idx ? best2 : best1));
+            if (idx1 >= 0 && idx1 == w.idx) {                                  // this lane owns the warp's winner
+                red.pl_mg[warp] = m1; red.pl_kv[warp] = q1; red.pl_alpha[warp] = alpha[idx1 >> IDX_SHIFT];
+            }
+            if (lane == 0) {
+                red.b_hi[warp] = w.hi; red.b_lo[warp] = w.lo; red.b_idx[warp] = w.idx;
+                red.t_hi[warp] = (unsigned)(k2 >> 32); red.t_lo[warp] = (unsigned)k2;
+            }
+            tick(2);
+            __syncthreads();                                                      // barrier 2
+            tick(3);
+            const bool v = lane < NW;
+            const unsigned bh = v ? red.b_hi[lane] : 0u, bl = v ? red.b_lo[lane] : 0u;
+            const int bi = v ? red.b_idx[lane] : -1;
+            const KArg b = warp_argmax(bh, bl, bi);
+            const unsigned long long mine = ((unsigned long long)bh << 32) | bl;
+            const unsigned long long ru = v ? (((unsigned long long)red.t_hi[lane] << 32) | red.t_lo[lane]) : 0ull;
+            const unsigned long long k3 = warp_keymax((v && bi == b.idx) ? ru : mine);
+            pj = b.idx;
+            if (pj < 0) return true;                                               // Gmin_idx == -1
+            top1 = dkey_inv(((unsigned long long)b.hi << 32) | b.lo);
+            top2 = dkey_inv(k3);
+        }
+        if (top2 >= top1 * BAND) {
+            // ---- exact tie-break: libsvm's correctly rounded quotients for every element in the band ----
+            const double thrx = top1 * BAND;
+            double bestn = -CUDART_INF;
             int bidx = -1;
 #pragma unroll
             for (int k = 0; k < KPT; k++) {
@@ -272,100 +384,32 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
                 if (t < active) {
                     const int f = fl[t];
                     const double m = mG[t];
-                    if ((f & F_UP) && m >= best) { best = m; bidx = (t << IDX_SHIFT) | (f & 31); }
-                }
-            }
-            const unsigned long long key = dkey(best);
-            const KArg w = warp_argmax((unsigned)(key >> 32), (unsigned)key, bidx);
-            if (lane == 0) { red.a_hi[warp] = w.hi; red.a_lo[warp] = w.lo; red.a_idx[warp] = w.idx; }
-            tick(0);
-            __syncthreads();                                                      // barrier 1
-            tick(1);
-            const bool v = lane < NW;
-            const KArg a = warp_argmax(v ? red.a_hi[lane] : 0u, v ? red.a_lo[lane] : 0u, v ? red.a_idx[lane] : -1);
-            pi = a.idx;
-            gmax = dkey_inv(((unsigned long long)a.hi << 32) | a.lo);
-        }
-        // ---- phase B: j = argmin -(gd^2)/quad over I_low with gd > 0; Gmax2 = max -m_t over I_low ----
-        double bestn = -CUDART_INF;          // best NEGATED objective change (positive), exact value
-        int bidx = -1;
-        double b_mg = 0, b_kv = 0;
-        double mgmin = CUDART_INF;
-        if (pi >= 0) {
-            const int i = pi >> IDX_SHIFT;
-            alpha_i = alpha[i];
-            const double QDi = QD(i);
-            const float *__restrict__ Ki = K + (size_t)col[i] * ldk;
-            float kv[KPT];
-#pragma unroll
-            for (int k = 0; k < KPT; k++) {                                  // issue the whole gather first
-                const int t = k * NT + tid;
-                kv[k] = t < active ? load_k<LD>(Ki + col[t]) : 0.f;
-            }
-            double runmax = -CUDART_INF, thr = -CUDART_INF;   // running max of approx NEGATED od, and its band
-            unsigned mask = 0;
-#pragma unroll
-            for (int k = 0; k < KPT; k++) {
-                const int t = k * NT + tid;
-                if (t < active) {
-                    const double dq = f2d(kv[k]);
-                    qi[k] = dq;
-                    if (fl[t] & F_LOW) {
-                        const double m = mG[t];
-                        mgmin = fmin(mgmin, m);
-                        const double gd = __dsub_rn(gmax, m);
-                        if (gd > 0) {
-                            const double quad = __dsub_rn(__dadd_rn(QDi, QD(t)), __dmul_rn(2.0, dq));
-                            const double g2 = __dmul_rn(gd, gd);
-                            const double ap = quad > 0 ? g2 * rcp_approx(quad) : g2 * 1e12;
-                            if (ap >= thr) {                                  // may still be the exact winner
-                                mask |= 1u << k;
-                                if (ap > runmax) { runmax = ap; thr = ap * BAND; }
-                            }
+                    const double gd = __dsub_rn(gmax, m);
+                    if ((f & F_LOW) && gd > 0) {
+                        const double quad = __dsub_rn(__dadd_rn(QDi, QD(t)), __dmul_rn(2.0, qi[k]));
+                        const double g2 = __dmul_rn(gd, gd);
+                        const double ap = quad > 0 ? g2 * rcp_approx(quad) : g2 * 1e12;
+                        if (ap >= thrx) {
+                            const double nod = quad > 0 ? __ddiv_rn(g2, quad) : __ddiv_rn(g2, TAU);   // == -obj_diff
+                            if (nod >= bestn) { bestn = nod; bidx = (t << IDX_SHIFT) | f; m1 = m; q1 = qi[k]; }
                         }
                     }
                 }
             }
-#pragma unroll
-            for (int k = 0; k < KPT; k++) {                                   // exact libsvm values for the survivors
-                if (mask & (1u << k)) {
-                    const int t = k * NT + tid;
-                    const double m = mG[t];
-                    const double gd = __dsub_rn(gmax, m);
-                    const double quad = __dsub_rn(__dadd_rn(QDi, QD(t)), __dmul_rn(2.0, qi[k]));
-                    const double g2 = __dmul_rn(gd, gd);
-                    const double nod = quad > 0 ? __ddiv_rn(g2, quad) : __ddiv_rn(g2, TAU);   // == -obj_diff
-                    if (nod >= bestn) { bestn = nod; bidx = (t << IDX_SHIFT) | (fl[t] & 31); b_mg = m; b_kv = qi[k]; }
-                }
-            }
-        }
-        {
             const unsigned long long key = dkey(bestn);
             const KArg w = warp_argmax((unsigned)(key >> 32), (unsigned)key, bidx);
-            const unsigned long long km = warp_keymax(dkey(-mgmin));
-            if (bidx >= 0 && bidx == w.idx) {                                  // this lane owns the warp's winner
-                red.pl_mg[warp] = b_mg; red.pl_kv[warp] = b_kv; red.pl_alpha[warp] = alpha[bidx >> IDX_SHIFT];
+            if (bidx >= 0 && bidx == w.idx) {
+                red.pl_mg[warp] = m1; red.pl_kv[warp] = q1; red.pl_alpha[warp] = alpha[bidx >> IDX_SHIFT];
             }
-            if (lane == 0) {
-                red.b_hi[warp] = w.hi; red.b_lo[warp] = w.lo; red.b_idx[warp] = w.idx;
-                red.m_hi[warp] = (unsigned)(km >> 32); red.m_lo[warp] = (unsigned)km;
-            }
-            tick(2);
-            __syncthreads();                                                      // barrier 2
-            tick(3);
+            if (lane == 0) { red.x_hi[warp] = w.hi; red.x_lo[warp] = w.lo; red.x_idx[warp] = w.idx; }
+            __syncthreads();                                                      // rare barrier
             const bool v = lane < NW;
-            const KArg b = warp_argmax(v ? red.b_hi[lane] : 0u, v ? red.b_lo[lane] : 0u, v ? red.b_idx[lane] : -1);
-            const unsigned long long km2 =
-                warp_keymax(v ? (((unsigned long long)red.m_hi[lane] << 32) | red.m_lo[lane]) : 0ull);
+            const KArg b = warp_argmax(v ? red.x_hi[lane] : 0u, v ? red.x_lo[lane] : 0u, v ? red.x_idx[lane] : -1);
             pj = b.idx;
-            if (pi < 0) return true;
-            const double gmax2 = dkey_inv(km2);
-            if (pj >= 0) {
-                const int wj = ((pj >> IDX_SHIFT) % NT) >> 5;
-                mg_j = red.pl_mg[wj]; k_ij = red.pl_kv[wj]; alpha_j = red.pl_alpha[wj];
-            }
-            return (__dadd_rn(gmax, gmax2) < eps) || pj < 0;
         }
+        const int wj = ((pj >> IDX_SHIFT) % NT) >> 5;
+        mg_j = red.pl_mg[wj]; k_ij = red.pl_kv[wj]; alpha_j = red.pl_alpha[wj];
+        return false;
     };
 
     // ---------------- do_shrinking (svm.cpp:1070-1129), m-domain ----------------
@@ -412,7 +456,7 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
         if (na != active) {
             // Two-pointer partition == pair the k-th marked position below na (ascending) with the k-th
             // unmarked position at/above na (descending).
-            int *plist = P.scratch, *qlist = P.scratch + l;
+            int *plist = scratch, *qlist = scratch + l;
             int np = 0, nq = 0;
             for (int base = 0; base < na; base += NT) {
                 const int t = base + tid;
@@ -447,31 +491,35 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
     };
 
     // ---------------- main loop (svm.cpp:742-907) ----------------
+    bool scan_valid = false;
     for (;;) {
         if (iter >= max_iter) { timed_out = 1; break; }
         if (--counter == 0) {
             counter = l < 1000 ? l : 1000;
-            if (P.shrinking) do_shrink();
+            if (use_gbar) { do_shrink(); scan_valid = false; }
             if constexpr (PROF) tprev = clock64();
         }
+        if (!scan_valid) local_scan();
         if (select()) {
             rebuild_gradient();
             active = l;
+            __syncthreads();                                     // selection scratch is rewritten below
+            local_scan();
             if (select()) break;
             counter = 1;
         }
         ++iter;
 
         const int i = pi >> IDX_SHIFT, j = pj >> IDX_SHIFT;
-        const float *__restrict__ Ki = K + (size_t)col[i] * ldk;
         const float *__restrict__ Kj = K + (size_t)col[j] * ldk;
         float kvj[KPT];
 #pragma unroll
         for (int k = 0; k < KPT; k++) {                          // issue the Q_j gather before the scalar update
             const int t = k * NT + tid;
-            kvj[k] = t < active ? load_k<LD>(Kj + col[t]) : 0.f;
+            kvj[k] = t < active ? __ldg(Kj + col[t]) : 0.f;
         }
         if (warp == 0) {                                         // analytic 2-variable update, once per CTA
+            const double C = Pp->C;
             const bool yi = (pi & F_YPOS) != 0, yj = (pj & F_YPOS) != 0;
             const double Gi = yi ? -gmax : gmax;                 // G = -y m (exact)
             const double Gj = yj ? -mg_j : mg_j;
@@ -513,19 +561,31 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
         tick(1);
         const double a = red.bc_d[0], b = red.bc_d[1];
         const int sti = red.bc_i[0], stj = red.bc_i[1];
-        const bool need_i = use_gbar && (((pi & 3) == ST_UPPER) != (sti == ST_UPPER));
-        const bool need_j = use_gbar && (((pj & 3) == ST_UPPER) != (stj == ST_UPPER));
+        // the owners of i and j publish alpha and status FIRST: the fused scan below must see the new sets
+        if (tid == i % NT) { alpha[i] = red.bc_d[2]; fl[i] = (unsigned char)mkflags((pi & F_YPOS) != 0, sti); }
+        if (tid == j % NT) { alpha[j] = red.bc_d[3]; fl[j] = (unsigned char)mkflags((pj & F_YPOS) != 0, stj); }
 
-        // m update over the active set (svm.cpp:866-872)
+        // m update over the active set (svm.cpp:866-872), fused with the next iteration's local scan
+        la = -CUDART_INF; lm = CUDART_INF; la_idx = -1;
 #pragma unroll
         for (int k = 0; k < KPT; k++) {
             const int t = k * NT + tid;
-            if (t < active)
-                mG[t] = __dadd_rn(mG[t], __dadd_rn(__dmul_rn(qi[k], a), __dmul_rn(f2d(kvj[k]), b)));
+            if (t < active) {
+                const double m = __dadd_rn(mG[t], __dadd_rn(__dmul_rn(qi[k], a), __dmul_rn(widen(kvj[k]), b)));
+                mG[t] = m;
+                const int f = fl[t];
+                if ((f & F_UP) && m >= la) { la = m; la_idx = (t << IDX_SHIFT) | f; }
+                if (f & F_LOW) lm = fmin(lm, m);
+            }
         }
+        scan_valid = true;
         // G_bar over all l when a bound status flips (svm.cpp:876-905): i first, then j
+        const bool need_i = use_gbar && (((pi & 3) == ST_UPPER) != (sti == ST_UPPER));
+        const bool need_j = use_gbar && (((pj & 3) == ST_UPPER) != (stj == ST_UPPER));
         if (need_i || need_j) {
             // Gbar -= C Q_i (was upper) / += C Q_i (became upper)  <=>  mbar += fl(c K_i), c = +/- y_i C
+            const double C = Pp->C;
+            const float *__restrict__ Ki = K + (size_t)col[i] * ldk;
             const double ci = (((pi & 3) == ST_UPPER) == ((pi & F_YPOS) != 0)) ? C : -C;
             const double cj = (((pj & 3) == ST_UPPER) == ((pj & F_YPOS) != 0)) ? C : -C;
 #pragma unroll
@@ -534,20 +594,18 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
                 if (t < l) {
                     const bool act = t < active;
                     double gb = mGbar[t];
-                    if (need_i) gb = __dadd_rn(gb, __dmul_rn(ci, act ? qi[k] : f2d(load_k<LD>(Ki + col[t]))));
-                    if (need_j) gb = __dadd_rn(gb, __dmul_rn(cj, act ? f2d(kvj[k]) : f2d(load_k<LD>(Kj + col[t]))));
+                    if (need_i) gb = __dadd_rn(gb, __dmul_rn(ci, act ? qi[k] : widen(__ldg(Ki + col[t]))));
+                    if (need_j) gb = __dadd_rn(gb, __dmul_rn(cj, widen(act ? kvj[k] : __ldg(Kj + col[t]))));
                     mGbar[t] = gb;
                 }
             }
         }
-        // the owners of i and j publish alpha and status (owner-only data until the next barriers)
-        if (tid == i % NT) { alpha[i] = red.bc_d[2]; fl[i] = (unsigned char)mkflags((pi & F_YPOS) != 0, sti); }
-        if (tid == j % NT) { alpha[j] = red.bc_d[3]; fl[j] = (unsigned char)mkflags((pj & F_YPOS) != 0, stj); }
         tick(5);
     }
 
     // ---------------- calculate_rho (svm.cpp:1131-1168): sequential float64 sum in libsvm's order ----
     __syncthreads();
+    const double C = Pp->C;
     if (tid == 0) {
         int nfree = 0;
         double ub = CUDART_INF, lb = -CUDART_INF, sum = 0;
@@ -558,15 +616,18 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
             else if ((f & 3) == ST_LOWER) { if (f & F_YPOS) ub = fmin(ub, yG); else lb = fmax(lb, yG); }
             else { ++nfree; sum = __dadd_rn(sum, yG); }
         }
-        *P.out_rho = nfree > 0 ? __ddiv_rn(sum, (double)nfree) : __ddiv_rn(__dadd_rn(ub, lb), 2.0);
+        *Pp->out_rho = nfree > 0 ? __ddiv_rn(sum, (double)nfree) : __ddiv_rn(__dadd_rn(ub, lb), 2.0);
     }
     // coefficients alpha_k*y_k scattered by dataset row (svm.cpp:922-925, :1641-1642); SV counts
     int nsv = 0, nbsv = 0;
-    for (int t = tid; t < l; t += NT) {
-        const double av = alpha[t];
-        P.coef[col[t]] = (fl[t] & F_YPOS) ? av : -av;
-        nsv += av > 0;
-        nbsv += av >= C;
+    {
+        double *__restrict__ coef = Pp->coef;
+        for (int t = tid; t < l; t += NT) {
+            const double av = alpha[t];
+            coef[col[t]] = (fl[t] & F_YPOS) ? av : -av;
+            nsv += av > 0;
+            nbsv += av >= C;
+        }
     }
 #pragma unroll
     for (int m = 16; m; m >>= 1) {
@@ -578,25 +639,36 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
     if (tid == 0) {
         int s = 0, bs = 0;
         for (int w = 0; w < NW; w++) { s += red.cnt[w]; bs += red.a_idx[w]; }
-        P.out_info[0] = iter; P.out_info[1] = timed_out; P.out_info[2] = s; P.out_info[3] = bs;
+        int *info = Pp->out_info;
+        info[0] = iter; info[1] = timed_out; info[2] = s; info[3] = bs;
         unsigned long long t_end;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
-        P.out_ns[0] = t_start; P.out_ns[1] = t_end;
+        unsigned long long *ns = Pp->out_ns;
+        ns[0] = t_start; ns[1] = t_end;
         if constexpr (PROF)
-            for (int q = 0; q < 6; q++) P.out_ns[2 + q] = (unsigned long long)prof[q];
+            for (int q = 0; q < 6; q++) ns[2 + q] = (unsigned long long)prof[q];
     }
 }
 
-template <int NT, int KPT, bool SMEM_STATE, int LD, bool PROF>
-cudaError_t launch_one(const SmoProblem *probs, const int *order, int n_prob, int lmax, cudaStream_t st)
+template <int NT, int KPT, bool SMEM_STATE, bool FAST, bool PROF>
+cudaError_t launch_one(const SmoProblem *probs, const int *order, int n_prob, cudaStream_t st)
 {
-    const int lcap = (lmax + 15) & ~15;
-    const size_t smem = (size_t)lcap * (SMEM_STATE ? (8 + 8 + 8 + 2 + 1) : (8 + 2 + 1));
-    auto kern = smo_kernel<NT, KPT, SMEM_STATE, LD, PROF>;
+    constexpr int LCAP = NT * KPT;
+    const size_t smem = (size_t)LCAP * (SMEM_STATE ? (8 + 8 + 8 + 2 + 1) : (8 + 2 + 1));
+    auto kern = smo_kernel<NT, KPT, SMEM_STATE, FAST, PROF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<n_prob, NT, smem, st>>>(probs, order, lcap);
+    kern<<<n_prob, NT, smem, st>>>(probs, order);
     return cudaGetLastError();
+}
+
+template <int NT, int KPT, bool SMEM_STATE>
+cudaError_t launch_cfg(const SmoProblem *probs, const int *order, int n_prob, bool fast, bool prof, cudaStream_t st)
+{
+    if (prof) return fast ? launch_one<NT, KPT, SMEM_STATE, true, true>(probs, order, n_prob, st)
+                          : launch_one<NT, KPT, SMEM_STATE, false, true>(probs, order, n_prob, st);
+    return fast ? launch_one<NT, KPT, SMEM_STATE, true, false>(probs, order, n_prob, st)
+                : launch_one<NT, KPT, SMEM_STATE, false, false>(probs, order, n_prob, st);
 }
 
 int env_int(const char *name, int dflt)
@@ -609,25 +681,18 @@ int env_int(const char *name, int dflt)
 
 int smo_max_rows() { return 1024 * 16; }
 
-cudaError_t launch_smo(const SmoProblem *d_probs, const int *d_order, int n_prob, int lmax, cudaStream_t st,
+// fast: every problem is rbf and every kernel matrix of the launch holds only positive normal floats
+cudaError_t launch_smo(const SmoProblem *d_probs, const int *d_order, int n_prob, int lmax, bool fast, cudaStream_t st,
                        std::string *why)
 {
     if (n_prob <= 0) return cudaSuccess;
-    if (lmax <= 512) return launch_one<128, 4, true, 0, false>(d_probs, d_order, n_prob, lmax, st);
-    if (lmax <= 2048) return launch_one<256, 8, true, 0, false>(d_probs, d_order, n_prob, lmax, st);
-    if (lmax <= 4096) return launch_one<512, 8, true, 0, false>(d_probs, d_order, n_prob, lmax, st);
-    if (lmax <= 8192) {
-        // tuning switches (development only): gather flavour / state placement / phase profile
-        const int ld = env_int("B200GS_SMO_LD", 0), state = env_int("B200GS_SMO_STATE", 1), prof = env_int("B200GS_SMO_PROF", 0);
-        if (prof) return state ? launch_one<1024, 8, true, 0, true>(d_probs, d_order, n_prob, lmax, st)
-                               : launch_one<1024, 8, false, 0, true>(d_probs, d_order, n_prob, lmax, st);
-        if (!state) return ld == 1 ? launch_one<1024, 8, false, 1, false>(d_probs, d_order, n_prob, lmax, st)
-                                   : launch_one<1024, 8, false, 0, false>(d_probs, d_order, n_prob, lmax, st);
-        if (ld == 1) return launch_one<1024, 8, true, 1, false>(d_probs, d_order, n_prob, lmax, st);
-        if (ld == 2) return launch_one<1024, 8, true, 2, false>(d_probs, d_order, n_prob, lmax, st);
-        return launch_one<1024, 8, true, 0, false>(d_probs, d_order, n_prob, lmax, st);
-    }
-    if (lmax <= 16384) return launch_one<1024, 16, false, 0, false>(d_probs, d_order, n_prob, lmax, st);
+    const bool prof = env_int("B200GS_SMO_PROF", 0) != 0;          // development switch: per-phase cycle counters
+    if (env_int("B200GS_SMO_NOFAST", 0)) fast = false;
+    if (lmax <= 512) return launch_cfg<128, 4, true>(d_probs, d_order, n_prob, fast, prof, st);
+    if (lmax <= 2048) return launch_cfg<256, 8, true>(d_probs, d_order, n_prob, fast, prof, st);
+    if (lmax <= 4096) return launch_cfg<512, 8, true>(d_probs, d_order, n_prob, fast, prof, st);
+    if (lmax <= 8192) return launch_cfg<1024, 8, true>(d_probs, d_order, n_prob, fast, prof, st);
+    if (lmax <= 16384) return launch_cfg<1024, 16, false>(d_probs, d_order, n_prob, fast, prof, st);
     if (why) *why = "SVC sub-problem larger than 16384 rows is not supported by the resident-state SMO kernel";
     return cudaErrorInvalidValue;
 }

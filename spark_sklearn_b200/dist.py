@@ -36,9 +36,9 @@ def allgather_candidates(local, my, n_cand, n_splits, world):
             buf[:len(my), :, j] = local[k]
     dev = torch.device("cuda", torch.cuda.current_device()) if td.get_backend() == "nccl" else torch.device("cpu")
     t = torch.from_numpy(buf).to(dev)
-    gathered = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=dev)
-    td.all_gather_into_tensor(gathered, t)
-    g = gathered.cpu().numpy()
+    gathered = torch.empty((world * per,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+    td.all_gather_into_tensor(gathered, t.contiguous())
+    g = gathered.cpu().numpy().reshape((world, per) + tuple(t.shape[1:]))
     out = {}
     for j, k in enumerate(keys):
         if local.get(k) is None and k == "train":

@@ -1,0 +1,239 @@
+"""CPU tests of the host side: C-ABI surface, search driver (aggregation, ranking, masked params, refit
+materialisation), error behaviour, and the multi-rank candidate striding + all-gather over gloo.
+
+The GPU engine is replaced by an oracle-backed plan (tests may use oracle/), so everything the Python
+layer does around the CUDA call is exercised without a GPU.
+"""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------ C ABI -------------------------
+def test_cabi_library_exports_every_declared_symbol():
+    import ctypes
+    from spark_sklearn_b200 import build, engine
+    build.build()
+    hdr = open(os.path.join(ROOT, "include", "b200gs.h")).read()
+    names = sorted(set(re.findall(r"\b(gs_[a-z_0-9]+)\s*\(", hdr)))
+    assert {"gs_create", "gs_destroy", "gs_set_data", "gs_svc", "gs_svc_refit", "gs_ridge", "gs_logreg",
+            "gs_get_profile", "gs_last_error"} <= set(names)
+    lib = ctypes.CDLL(engine.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), n
+    assert engine.load_library().gs_version() >= 100
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from spark_sklearn_b200.engine import Engine, EngineError
+    with pytest.raises(EngineError) as e:
+        Engine(0)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_code_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "spark_sklearn_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+# ------------------------------------------------------------------ oracle-backed plan ------------
+class OraclePlan:
+    def __init__(self, estimator, cands, X, y, fold_id, n_splits):
+        self.estimator, self.cands, self.X, self.y, self.fold_id, self.n_splits = estimator, cands, np.asarray(X), y, fold_id, n_splits
+
+    def evaluate(self, my, return_train=True, error_score="raise"):
+        from oracle import oracle as O
+        p0 = self.estimator.get_params()
+        test, train, _ = O.cv_scores_svc(self.X, self.y, self.fold_id, self.n_splits, [self.cands[i] for i in my], p0)
+        z = np.zeros_like(test)
+        return dict(test=test, train=train if return_train else None, fit_time=z + 1e-3, score_time=z + 1e-4)
+
+    def profile(self):
+        return {}
+
+    def refit(self, best):
+        from oracle import oracle as O
+        from sklearn.base import clone
+        from spark_sklearn_b200.estimators import materialize_svc
+        p = self.estimator.get_params(); p.update(best)
+        classes, yc = np.unique(self.y, return_inverse=True)
+        m = O.SVCModel(np.ascontiguousarray(self.X, np.float64), self.y, np.arange(len(self.y)), kernel=p["kernel"],
+                       gamma=p["gamma"], C=p["C"], tol=p["tol"])
+        coef = np.zeros((len(m.pairs), len(self.y)))
+        for q, (_, _, rows, c, _) in enumerate(m.pairs):
+            coef[q, rows] = c
+        return materialize_svc(clone(self.estimator).set_params(**best), self.X, yc, classes, coef,
+                               np.array([p_[4] for p_ in m.pairs]), np.array(m.n_iter), m.gamma)
+
+    def close(self):
+        pass
+
+
+class OracleAdapter:
+    plan = staticmethod(lambda *a: OraclePlan(*a))
+
+
+@pytest.fixture
+def oracle_backend(monkeypatch):
+    from spark_sklearn_b200 import base_search
+    monkeypatch.setattr(base_search._est, "adapter_for", lambda est: OracleAdapter)
+
+
+def _iris():
+    from sklearn.datasets import load_iris
+    d = load_iris()
+    return d.data, d.target
+
+
+def test_search_driver_matches_sklearn_on_the_reference_example(oracle_backend):
+    """reference tests/test_search_2.py:32-45 + doctest grid_search.py:90-116, with numbers."""
+    from sklearn import svm
+    from sklearn.model_selection import GridSearchCV as SkGrid
+    from spark_sklearn_b200 import GridSearchCV
+    X, y = _iris()
+    parameters = {'kernel': ('linear', 'rbf'), 'C': [1, 10]}
+    clf = GridSearchCV(None, svm.SVC(gamma='auto'), parameters).fit(X, y)       # reference default cv=3
+    sk = SkGrid(svm.SVC(gamma='auto'), parameters, cv=3, return_train_score=True).fit(X, y)
+    assert sorted(clf.cv_results_.keys()) == sorted(sk.cv_results_.keys())      # the doctest's key set
+    for k in range(3):
+        np.testing.assert_array_equal(clf.cv_results_["split%d_test_score" % k], sk.cv_results_["split%d_test_score" % k])
+        np.testing.assert_array_equal(clf.cv_results_["split%d_train_score" % k], sk.cv_results_["split%d_train_score" % k])
+    np.testing.assert_allclose(clf.cv_results_["mean_test_score"], [0.9933333333, 0.9733333333, 0.9733333333, 0.98], atol=1e-9)
+    np.testing.assert_array_equal(clf.cv_results_["rank_test_score"], [1, 3, 3, 2])
+    assert clf.cv_results_["rank_test_score"].dtype == np.int32
+    assert clf.best_index_ == 0 and clf.best_params_ == {"C": 1, "kernel": "linear"} and clf.n_splits_ == 3
+    assert list(clf.cv_results_["param_kernel"]) == ["linear", "rbf", "linear", "rbf"]
+    assert clf.cv_results_["params"] == sk.cv_results_["params"]
+    np.testing.assert_array_equal(clf.predict(X), sk.predict(X))
+    np.testing.assert_allclose(clf.decision_function(X), sk.decision_function(X), atol=1e-12)
+    assert clf.score(X, y) == sk.score(X, y)
+    assert clf.estimator.get_params() == svm.SVC(gamma='auto').get_params()      # the reference's own assertion
+    from sklearn.base import clone
+    assert clone(clf).get_params()["param_grid"] == parameters                   # get_params/clone keep working
+
+
+def test_iid_weighting_on_unequal_folds(oracle_backend):
+    """reference base_search.py:115,129-133: iid=True weights fold means by test-set size."""
+    from sklearn import svm
+    from spark_sklearn_b200 import GridSearchCV
+    X, y = _iris()
+    X, y = X[:148], y[:148]
+    g = {"C": [1.0]}
+    a = GridSearchCV(None, svm.SVC(gamma='auto'), g, cv=5, iid=True).fit(X, y)
+    b = GridSearchCV(None, svm.SVC(gamma='auto'), g, cv=5, iid=False).fit(X, y)
+    s = np.array([a.cv_results_["split%d_test_score" % k][0] for k in range(5)])
+    from sklearn.model_selection import StratifiedKFold
+    sizes = np.array([len(te) for _, te in StratifiedKFold(5).split(X, y)])
+    assert a.cv_results_["mean_test_score"][0] == np.average(s, weights=sizes)
+    assert b.cv_results_["mean_test_score"][0] == np.average(s)
+
+
+def test_randomized_search_candidates_and_shape(oracle_backend):
+    """reference tests/test_search_2.py:47-60,81,95: len(params) == n_iter, sampler identical to sklearn's."""
+    from scipy.stats import loguniform
+    from sklearn import svm
+    from sklearn.model_selection import ParameterSampler
+    from spark_sklearn_b200 import RandomizedSearchCV
+    X, y = _iris()
+    dist = {"C": loguniform(0.1, 100), "kernel": ["linear", "rbf"]}
+    r = RandomizedSearchCV(None, svm.SVC(gamma='auto'), dist, n_iter=5, random_state=4, cv=3).fit(X, y)
+    assert len(r.cv_results_["params"]) == 5
+    assert r.cv_results_["params"] == list(ParameterSampler(dist, 5, random_state=4))
+    assert "mean_train_score" in r.cv_results_            # return_train_score is always on (random_search.py:195-199)
+
+
+def test_unsupported_configurations_raise_instead_of_falling_back():
+    from sklearn import svm
+    from sklearn.tree import DecisionTreeClassifier
+    from spark_sklearn_b200 import GridSearchCV
+    X, y = _iris()
+    with pytest.raises(NotImplementedError):
+        GridSearchCV(None, DecisionTreeClassifier(), {"max_depth": [1, 2]}, cv=3).fit(X, y)
+    with pytest.raises(NotImplementedError):
+        GridSearchCV(None, svm.SVC(), {"C": [1.0]}, scoring="f1_macro", cv=3).fit(X, y)
+    with pytest.raises(ValueError):
+        GridSearchCV(None, svm.SVC(), {"C": 1.0})          # _check_param_grid (grid_search.py:226)
+
+
+def test_fold_ids_reject_non_partition_splitters():
+    from sklearn.model_selection import ShuffleSplit, StratifiedKFold
+    from spark_sklearn_b200.estimators import fold_ids_from_splits
+    X, y = _iris()
+    f = fold_ids_from_splits(list(StratifiedKFold(5).split(X, y)), len(y))
+    assert set(f) == {0, 1, 2, 3, 4} and f.dtype == np.int8
+    with pytest.raises(NotImplementedError):
+        fold_ids_from_splits(list(ShuffleSplit(3, test_size=0.5, random_state=0).split(X)), len(y))
+
+
+def test_materialize_svc_binary_equals_sklearn_fit():
+    from sklearn.svm import SVC
+    from oracle import oracle as O
+    from spark_sklearn_b200 import workloads as W
+    from spark_sklearn_b200.estimators import materialize_svc
+    w = W.make_workload("c2_small")
+    X, y = w["X"][:400], w["y"][:400]
+    ref = SVC(C=10.0, gamma=1 / 64).fit(X, y)
+    m = O.SVCModel(X.astype(np.float64), y, np.arange(len(y)), kernel="rbf", gamma=1 / 64, C=10.0)
+    coef = np.zeros((1, len(y))); coef[0, m.pairs[0][2]] = m.pairs[0][3]
+    est = materialize_svc(SVC(C=10.0, gamma=1 / 64), X, y, np.unique(y), coef, np.array([m.pairs[0][4]]), np.array(m.n_iter), 1 / 64)
+    np.testing.assert_array_equal(est.support_, ref.support_)
+    np.testing.assert_array_equal(est.dual_coef_, ref.dual_coef_)
+    np.testing.assert_array_equal(est.intercept_, ref.intercept_)
+    np.testing.assert_array_equal(est.n_support_, ref.n_support_)
+    np.testing.assert_array_equal(est.predict(w["X"][400:600]), ref.predict(w["X"][400:600]))
+    np.testing.assert_array_equal(est.decision_function(w["X"][400:600]), ref.decision_function(w["X"][400:600]))
+    import pickle
+    np.testing.assert_array_equal(pickle.loads(pickle.dumps(est)).predict(X), ref.predict(X))
+
+
+# ------------------------------------------------------------------ multi-rank (gloo, CPU) --------
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sklearn import svm
+    from spark_sklearn_b200 import GridSearchCV, base_search
+    base_search._est.adapter_for = lambda est: OracleAdapter
+    X, y = _iris()
+    grid = {'kernel': ('linear', 'rbf'), 'C': [1, 10, 100]}            # 6 candidates over 2 ranks (and 4 over 3 below)
+    s = GridSearchCV(None, svm.SVC(gamma='auto'), grid, cv=5, refit=False).fit(X, y)
+    q.put((rank, {k: np.asarray(v, float) for k, v in s.cv_results_.items() if "score" in k}))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_candidates_strided_over_ranks_allgather_gloo(world, oracle_backend):
+    """Same search at 1 and N ranks gives identical cv_results_ on every rank (uneven
+    n_cand % N is padded)."""
+    import torch.multiprocessing as mp
+    from sklearn import svm
+    from spark_sklearn_b200 import GridSearchCV
+    X, y = _iris()
+    grid = {'kernel': ('linear', 'rbf'), 'C': [1, 10, 100]}
+    single = GridSearchCV(None, svm.SVC(gamma='auto'), grid, cv=5, refit=False).fit(X, y).cv_results_
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000 + world
+    ps = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    got = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, res in got:
+        for k, v in res.items():
+            np.testing.assert_array_equal(v, np.asarray(single[k], float), err_msg="rank %d %s" % (rank, k))
