@@ -121,6 +121,9 @@ int gs_debug_gram(gs_handle *h, double *S_out, double *xsq_out);
 /* K_out [n][n] float32 kernel matrix (the SMO solver's Q without the y_i*y_j sign), original order. */
 int gs_debug_kernel_matrix(gs_handle *h, int32_t kernel, double gamma, float *K_out);
 
+/* C[M][N] = sum_k A[M][k]*B[N][k] on the tcgen05 tensor-core path (3xTF32 split), host fp32 row-major in/out. */
+int gs_debug_gemm_nt(gs_handle *h, const float *A, int32_t M, const float *B, int32_t N, int32_t K, float *C);
+
 /* ---- measurement ----------------------------------------------------------------------- */
 typedef struct gs_profile {
     /* last search call; device times from CUDA events on the engine's stream */

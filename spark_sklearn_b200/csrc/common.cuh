@@ -100,3 +100,17 @@ struct VoteTask {          // one (candidate, fold) task
 cudaError_t launch_vote(const double *dec, const double *rho, int n, int n_classes, const int *y,
                         const signed char *fold, const VoteTask *tasks, int n_tasks, int *counts,
                         cudaStream_t st);
+
+// ---- gemm_tc.cu: tcgen05 + TMA contraction  C[M][N] = sum_k A[M][k] B[N][k]  (3xTF32 split, fp32 accumulate) ----
+struct alignas(64) TcMap { unsigned char bytes[128]; };            // CUtensorMap
+struct TcBatch {                                                    // one GEMM of a batched launch (blockIdx.z)
+    int a_row0, b_row0;   // first row of the A / B operand inside their tensor maps
+    int k0, k1;           // contraction range [k0, k1) in elements; must be a multiple of 32 long (zero padded)
+    float *c;             // output, row-major
+    int64_t ldc;
+};
+cudaError_t tc_make_map(TcMap *out, const float *base, int64_t rows, int64_t cols, int64_t ld);
+cudaError_t launch_split_tf32(const float *x, float *hi, float *lo, size_t n, cudaStream_t st);
+cudaError_t launch_gemm_nt_tf32x3(const TcMap &a_hi, const TcMap &a_lo, const TcMap &b_hi, const TcMap &b_lo,
+                                  const TcBatch *d_batches, int n_batches, int M, int N, float alpha, bool accumulate,
+                                  cudaStream_t st);

@@ -59,8 +59,9 @@ def load_library():
     L.gs_get_profile.argtypes = [vp, c.POINTER(GsProfile)]
     L.gs_debug_gram.argtypes = [vp, vp, vp]
     L.gs_debug_kernel_matrix.argtypes = [vp, i32, dbl, vp]
+    L.gs_debug_gemm_nt.argtypes = [vp, vp, i32, vp, i32, i32, vp]
     for f in ("gs_create", "gs_set_data", "gs_svc", "gs_svc_refit", "gs_ridge", "gs_ridge_refit", "gs_logreg",
-              "gs_logreg_refit", "gs_get_profile", "gs_debug_gram", "gs_debug_kernel_matrix"):
+              "gs_logreg_refit", "gs_get_profile", "gs_debug_gram", "gs_debug_kernel_matrix", "gs_debug_gemm_nt"):
         getattr(L, f).restype = c.c_int
     _lib = L
     return L
@@ -184,6 +185,13 @@ class Engine:
         k = KERNEL_ID[kernel] if isinstance(kernel, str) else int(kernel)
         self._check(self._L.gs_debug_kernel_matrix(self._h, k, float(gamma), _ptr(K)))
         return K
+
+    def debug_gemm_nt(self, A, B):
+        A = np.ascontiguousarray(A, np.float32)
+        B = np.ascontiguousarray(B, np.float32)
+        C = np.zeros((A.shape[0], B.shape[0]), np.float32)
+        self._check(self._L.gs_debug_gemm_nt(self._h, _ptr(A), A.shape[0], _ptr(B), B.shape[0], A.shape[1], _ptr(C)))
+        return C
 
     def profile(self):
         p = GsProfile()
