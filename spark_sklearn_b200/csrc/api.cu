@@ -132,6 +132,13 @@ int gs_set_data(gs_handle *h, const void *X, int32_t x_dtype, int64_t n, int64_t
         // internal order: by class, then original index -- makes every one-vs-one sub-problem a
         // (nearly) contiguous column range of the kernel matrix, so SMO row gathers coalesce
         std::stable_sort(h->perm.begin(), h->perm.end(), [&](int a, int b) { return y_class[a] < y_class[b]; });
+    } else {
+        // regression: internal order by fold (rows outside every test set last), so every fold is a contiguous
+        // row range = a contiguous K-range of the fold-Gram contractions
+        std::stable_sort(h->perm.begin(), h->perm.end(), [&](int a, int b) {
+            const int fa = fold_id[a] < 0 ? 127 : fold_id[a], fb = fold_id[b] < 0 ? 127 : fold_id[b];
+            return fa < fb;
+        });
     }
     h->yc.assign(n, 0); h->fold.resize(n);
     h->class_start.assign(h->n_classes + 1, 0);

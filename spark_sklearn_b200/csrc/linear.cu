@@ -1,17 +1,457 @@
-// linear.cu -- Ridge / LogisticRegression searches (C ABI entry points).
+// linear.cu -- Ridge search (gs_ridge / gs_ridge_refit) and the LogisticRegression entry points.
+//
+// Ridge path (replaces sklearn Ridge.fit/score reached from reference base_search.py:83-87:
+// linear_model/_ridge.py:919 fit, :964 _preprocess_data centring, :215-227 _solve_cholesky, base.py:716 r2):
+//   1. Z = [X | y | 1]  (n x (d+2)); per CV fold k the Gram  G_k = Z_k^T Z_k  holds X^T X, X^T y, column sums,
+//      y^T y, sum y and the row count of the fold at once.  One tcgen05 contraction per fold (gemm_tc.cu, 3xTF32
+//      split, K-range = the fold's contiguous rows).  scikit-learn recomputes X^T X for each of the
+//      n_alpha x n_folds fits; here it is built ONCE and the training statistics of fold k are
+//      T - G_k with T = sum_k G_k (float64).
+//   2. Per fold: centred normal matrix A_k = X^T X - n xbar xbar^T and rhs (float64 -> float32).
+//   3. (A_k + alpha I) w = rhs for ALL alphas of a fold at once by conjugate gradients whose matrix product is the
+//      same tensor-core contraction (P[alphas x d] times the symmetric A_k); the per-system vector updates and dot
+//      products are one small kernel per iteration.  Converged systems freeze; non-convergence fails loudly.
+//   4. R^2 on the held-out fold and on the training rows from the Gram statistics in float64 (quadratic forms),
+//      no pass over X.
 #include "common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
 #include <vector>
+
+namespace {
+
+constexpr int CG_MAX_ITER = 4000;
+constexpr double CG_TOL = 1e-6;          // relative residual; fp32 Cholesky (sklearn) is accurate to ~cond*6e-8
+
+// Zt[j][poff[b] + r] = X[row][j] (j<d) | y[row] (j==d) | 1 (j==d+1); rows of block b are row0[b] .. row0[b]+cnt[b]
+__global__ void build_zt_kernel(const float *__restrict__ X, const float *__restrict__ y, int d, int n_blocks,
+                                const int *__restrict__ row0, const int *__restrict__ cnt, const int *__restrict__ poff,
+                                float *__restrict__ Zt, int64_t ldz)
+{
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    if (b >= n_blocks) return;
+    const int r0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    if (r0 >= cnt[b]) return;
+    {   // coalesced read along j
+        const int r = r0 + threadIdx.y, j = j0 + threadIdx.x;
+        float v = 0.f;
+        if (r < cnt[b]) {
+            const int row = row0[b] + r;
+            if (j < d) v = X[(size_t)row * d + j];
+            else if (j == d) v = y[row];
+            else if (j == d + 1) v = 1.f;
+        }
+        tile[threadIdx.y][threadIdx.x] = v;
+    }
+    __syncthreads();
+    {   // coalesced write along r
+        const int j = j0 + threadIdx.y, r = r0 + threadIdx.x;
+        if (j < d + 2 && r < cnt[b]) Zt[(size_t)j * ldz + poff[b] + r] = tile[threadIdx.x][threadIdx.y];
+    }
+}
+
+// T = sum_b G_b in float64
+__global__ void sum_grams_kernel(const float *__restrict__ G, int n_blocks, int64_t per, double *__restrict__ T)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0;
+        for (int b = 0; b < n_blocks; b++) s += (double)G[(size_t)b * per + i];
+        T[i] = s;
+    }
+}
+
+// Per system-group g (a fold, or "all rows" for the refit): training statistics S = T - G_test, centred normal matrix
+// A (float32, [dp][dp], zero padded) and rhs (float32 [dp]); means kept in float64 for the intercept.
+__global__ void build_systems_kernel(const double *__restrict__ T, const float *__restrict__ G, const int *__restrict__ test_block,
+                                     int d, int Dp, int dp, int fit_intercept, float *__restrict__ A, float *__restrict__ rhs,
+                                     double *__restrict__ means /* [groups][dp + 2]: xbar[0..d), ybar, n_train */)
+{
+    const int g = blockIdx.z;
+    const int tb = test_block[g];
+    const float *Gt = tb >= 0 ? G + (size_t)tb * Dp * Dp : nullptr;
+    auto S = [&](int a, int b) -> double { return T[(size_t)a * Dp + b] - (Gt ? (double)Gt[(size_t)a * Dp + b] : 0.0); };
+    const double ntr = S(d + 1, d + 1);
+    const double ybar = fit_intercept ? S(d, d + 1) / ntr : 0.0;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= dp || l >= dp) return;
+    double v = 0.0;
+    if (j < d && l < d) {
+        v = S(j, l);
+        if (fit_intercept) v -= S(j, d + 1) * S(l, d + 1) / ntr;            // n xbar_j xbar_l
+    }
+    A[((size_t)g * dp + j) * dp + l] = (float)v;
+    if (l == 0) {
+        double r = 0.0;
+        if (j < d) {
+            r = S(j, d);
+            if (fit_intercept) r -= S(j, d + 1) * ybar;                     // n xbar_j ybar
+            means[(size_t)g * (dp + 2) + j] = fit_intercept ? S(j, d + 1) / ntr : 0.0;
+        }
+        rhs[(size_t)g * dp + j] = (float)r;
+        if (j == 0) { means[(size_t)g * (dp + 2) + dp] = ybar; means[(size_t)g * (dp + 2) + dp + 1] = ntr; }
+    }
+}
+
+__device__ __forceinline__ double block_sum(double v, double *sh)
+{
+#pragma unroll
+    for (int m = 16; m; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) r += sh[w];
+    return r;
+}
+
+__device__ __forceinline__ void split_store(float v, float *hi, float *lo, size_t i)
+{
+    const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    hi[i] = h; lo[i] = v - h;
+}
+
+// one CTA per system s = g * n_cand + c:  x = 0, r = p = rhs_g
+__global__ void cg_init_kernel(const float *__restrict__ rhs, int n_cand, int dp, float *__restrict__ Xs, float *__restrict__ R,
+                               float *__restrict__ P, float *__restrict__ Ph, float *__restrict__ Pl, double *__restrict__ rr,
+                               double *__restrict__ bb, int *__restrict__ done)
+{
+    __shared__ double sh[32];
+    const int s = blockIdx.x, g = s / n_cand;
+    double acc = 0;
+    for (int j = threadIdx.x; j < dp; j += blockDim.x) {
+        const float v = rhs[(size_t)g * dp + j];
+        const size_t i = (size_t)s * dp + j;
+        Xs[i] = 0.f; R[i] = v; P[i] = v;
+        split_store(v, Ph, Pl, i);
+        acc += (double)v * v;
+    }
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) { rr[s] = acc; bb[s] = acc; done[s] = acc == 0.0; }
+}
+
+// q = Q + alpha_c p;  a = rr / p.q;  x += a p;  r -= a q;  beta = rr' / rr;  p = r + beta p   (Hestenes-Stiefel CG)
+__global__ void cg_step_kernel(const float *__restrict__ Q, const double *__restrict__ alphas, int n_cand, int dp,
+                               float *__restrict__ Xs, float *__restrict__ R, float *__restrict__ P, float *__restrict__ Ph,
+                               float *__restrict__ Pl, double *__restrict__ rr, const double *__restrict__ bb,
+                               int *__restrict__ done, int *__restrict__ n_open, double tol2)
+{
+    __shared__ double sh[32];
+    const int s = blockIdx.x, c = s % n_cand;
+    if (done[s]) return;
+    const float al = (float)alphas[c];
+    float q[8], p[8], r[8];                                      // dp <= 8 * blockDim.x (256 threads)
+    double pq = 0;
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const int j = threadIdx.x + u * 256;
+        p[u] = q[u] = r[u] = 0.f;
+        if (j < dp) {
+            const size_t i = (size_t)s * dp + j;
+            p[u] = P[i];
+            q[u] = Q[i] + al * p[u];
+            pq += (double)p[u] * q[u];
+        }
+    }
+    pq = block_sum(pq, sh);
+    const double rr0 = rr[s];
+    if (!(pq > 0)) {                                             // breakdown: only possible when p == 0 (already solved)
+        if (threadIdx.x == 0) done[s] = 1;
+        return;
+    }
+    const float a = (float)(rr0 / pq);
+    double rn = 0;
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const int j = threadIdx.x + u * 256;
+        if (j < dp) {
+            const size_t i = (size_t)s * dp + j;
+            Xs[i] += a * p[u];
+            r[u] = R[i] - a * q[u];
+            R[i] = r[u];
+            rn += (double)r[u] * r[u];
+        }
+    }
+    rn = block_sum(rn, sh);
+    const float beta = (float)(rn / rr0);
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const int j = threadIdx.x + u * 256;
+        if (j < dp) {
+            const size_t i = (size_t)s * dp + j;
+            const float pn = r[u] + beta * p[u];
+            P[i] = pn;
+            split_store(pn, Ph, Pl, i);
+        }
+    }
+    if (threadIdx.x == 0) {
+        rr[s] = rn;
+        if (rn <= tol2 * bb[s]) done[s] = 1; else atomicAdd(n_open, 1);
+    }
+}
+
+// R^2 of system s on its test block and on its training rows, from Gram statistics (float64 quadratic forms)
+__global__ void ridge_r2_kernel(const float *__restrict__ Xs, const double *__restrict__ T, const float *__restrict__ G,
+                                const int *__restrict__ test_block, const double *__restrict__ means, int n_cand, int d, int Dp,
+                                int dp, int fit_intercept, double *__restrict__ out /* [systems][2] */)
+{
+    __shared__ double sh[32];
+    extern __shared__ double wsh[];                               // w in float64
+    const int s = blockIdx.x, g = s / n_cand;
+    const int tb = test_block[g];
+    const float *Gk = G + (size_t)tb * Dp * Dp;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) wsh[j] = (double)Xs[(size_t)s * dp + j];
+    __syncthreads();
+    // quadratic forms w^T Gk w and w^T T w: one warp per row, lanes along the row (coalesced)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    double qk = 0, qt = 0;
+    for (int j = warp; j < d; j += nw) {
+        double ak = 0, at = 0;
+        for (int l = lane; l < d; l += 32) {
+            const double wl = wsh[l];
+            ak += (double)Gk[(size_t)j * Dp + l] * wl;
+            at += T[(size_t)j * Dp + l] * wl;
+        }
+        qk += ak * wsh[j]; qt += at * wsh[j];
+    }
+    double wxy_k = 0, wxy_t = 0, ws_k = 0, ws_t = 0, xbw = 0;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) {
+        const double w = wsh[j];
+        wxy_k += w * (double)Gk[(size_t)j * Dp + d]; wxy_t += w * T[(size_t)j * Dp + d];
+        ws_k += w * (double)Gk[(size_t)j * Dp + d + 1]; ws_t += w * T[(size_t)j * Dp + d + 1];
+        xbw += w * means[(size_t)g * (dp + 2) + j];
+    }
+    qk = block_sum(qk, sh); qt = block_sum(qt, sh);
+    wxy_k = block_sum(wxy_k, sh); wxy_t = block_sum(wxy_t, sh);
+    ws_k = block_sum(ws_k, sh); ws_t = block_sum(ws_t, sh);
+    xbw = block_sum(xbw, sh);
+    if (threadIdx.x == 0) {
+        const double b0 = fit_intercept ? means[(size_t)g * (dp + 2) + dp] - xbw : 0.0;
+        auto r2 = [&](double yy, double ys, double nn, double q, double wxy, double ws) {
+            const double res = yy - 2 * wxy - 2 * b0 * ys + q + 2 * b0 * ws + nn * b0 * b0;
+            const double tot = yy - ys * ys / nn;
+            return 1.0 - res / tot;
+        };
+        const double yy_k = Gk[(size_t)d * Dp + d], ys_k = Gk[(size_t)d * Dp + d + 1], n_k = Gk[(size_t)(d + 1) * Dp + d + 1];
+        const double yy_t = T[(size_t)d * Dp + d], ys_t = T[(size_t)d * Dp + d + 1], n_t = T[(size_t)(d + 1) * Dp + d + 1];
+        out[(size_t)s * 2] = r2(yy_k, ys_k, n_k, qk, wxy_k, ws_k);
+        out[(size_t)s * 2 + 1] = r2(yy_t - yy_k, ys_t - ys_k, n_t - n_k, qt - qk, wxy_t - wxy_k, ws_t - ws_k);
+    }
+}
+
+struct RidgeTimers { float gram = 0, solve = 0, score = 0, total = 0; };
+
+// groups: fold k (test block k) for the search; one group with test block -1 for the refit
+int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, bool refit,
+              double *test_scores, double *train_scores, double *coef_out, RidgeTimers *tmr)
+{
+    if (!h) return GS_ERR_ARG;
+    if (h->n == 0) { gs_set_error(h, "gs_ridge: no dataset (call gs_set_data first)"); return GS_ERR_NO_DATA; }
+    if (h->classification) { gs_set_error(h, "gs_ridge: dataset has no regression targets"); return GS_ERR_ARG; }
+    if (n_cand <= 0 || !alpha) { gs_set_error(h, "gs_ridge: bad arguments"); return GS_ERR_ARG; }
+    for (int c = 0; c < n_cand; c++)
+        if (!(alpha[c] >= 0)) { gs_set_error(h, "gs_ridge: alpha must be >= 0"); return GS_ERR_ARG; }
+    GS_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int n = (int)h->n, d = (int)h->d, ns = h->n_splits;
+    const int D = d + 2, Dp = (D + 31) & ~31, dp = (d + 31) & ~31;
+    if (dp > 8 * 256) { gs_set_error(h, "gs_ridge: more than 2048 features is not supported by the CG kernels"); return GS_ERR_UNSUPPORTED; }
+
+    // row blocks (rows are sorted by fold; fold -1 rows, never tested, form a trailing block)
+    std::vector<int> row0, cnt;
+    {
+        int r = 0;
+        for (int k = 0; k < ns; k++) {
+            int c = 0;
+            while (r + c < n && h->fold[r + c] == k) c++;
+            row0.push_back(r); cnt.push_back(c); r += c;
+        }
+        if (r < n) { row0.push_back(r); cnt.push_back(n - r); }
+    }
+    const int nb = (int)row0.size();
+    std::vector<int> poff(nb + 1, 0);
+    for (int b = 0; b < nb; b++) poff[b + 1] = poff[b] + ((cnt[b] + 31) & ~31);
+    const int64_t ldz = poff[nb];
+    const int groups = refit ? 1 : ns;
+    const int nsys = groups * n_cand;
+
+    cudaEvent_t ev[5];
+    for (auto &e : ev) cudaEventCreate(&e);
+    cudaEventRecord(ev[0], st);
+
+    // ---- buffers ----
+    DevBuf &bZ = h->dWork[0], &bZh = h->dWork[1], &bZl = h->dWork[2], &bG = h->dWork[3], &bMisc = h->dWork[4],
+           &bA = h->dWork[5], &bV = h->dWork[6], &bMeta = h->dWork[7];
+    GS_CUDA(bZ.reserve((size_t)Dp * ldz * 4)); GS_CUDA(bZh.reserve((size_t)Dp * ldz * 4)); GS_CUDA(bZl.reserve((size_t)Dp * ldz * 4));
+    GS_CUDA(bG.reserve((size_t)nb * Dp * Dp * 4));
+    const size_t tBytes = (size_t)Dp * Dp * 8, meansBytes = (size_t)groups * (dp + 2) * 8;
+    GS_CUDA(bMisc.reserve(tBytes + meansBytes + (size_t)nsys * (8 + 8 + 16) + (size_t)n_cand * 8 + 256));
+    GS_CUDA(bA.reserve((size_t)groups * dp * dp * 4 * 3 + (size_t)groups * dp * 4));
+    GS_CUDA(bV.reserve((size_t)nsys * dp * 4 * 6));
+    GS_CUDA(bMeta.reserve((size_t)(nb * 3 + groups) * 4 + (size_t)(nb + groups) * sizeof(TcBatch) + (size_t)nsys * 4 + 64));
+    double *dT = bMisc.as<double>();
+    double *dMeans = dT + (size_t)Dp * Dp;
+    double *dRR = dMeans + (size_t)groups * (dp + 2), *dBB = dRR + nsys, *dOut = dBB + nsys, *dAlpha = dOut + 2 * (size_t)nsys;
+    float *dA = bA.as<float>(), *dAh = dA + (size_t)groups * dp * dp, *dAl = dAh + (size_t)groups * dp * dp,
+          *dRhs = dAl + (size_t)groups * dp * dp;
+    float *dX = bV.as<float>(), *dR = dX + (size_t)nsys * dp, *dP = dR + (size_t)nsys * dp, *dPh = dP + (size_t)nsys * dp,
+          *dPl = dPh + (size_t)nsys * dp, *dQ = dPl + (size_t)nsys * dp;
+    int *dRow0 = bMeta.as<int>(), *dCnt = dRow0 + nb, *dPoff = dCnt + nb, *dTestBlock = dPoff + nb;
+    int *dDone = dTestBlock + groups;
+    int *dOpen = dDone + nsys;
+    TcBatch *dBatchG = reinterpret_cast<TcBatch *>(((uintptr_t)(dOpen + 4) + 15) & ~(uintptr_t)15);
+    TcBatch *dBatchCG = dBatchG + nb;
+
+    std::vector<int> testBlock(groups);
+    for (int g = 0; g < groups; g++) testBlock[g] = refit ? -1 : g;
+    GS_CUDA(cudaMemcpyAsync(dRow0, row0.data(), nb * 4, cudaMemcpyHostToDevice, st));
+    GS_CUDA(cudaMemcpyAsync(dCnt, cnt.data(), nb * 4, cudaMemcpyHostToDevice, st));
+    GS_CUDA(cudaMemcpyAsync(dPoff, poff.data(), nb * 4, cudaMemcpyHostToDevice, st));
+    GS_CUDA(cudaMemcpyAsync(dTestBlock, testBlock.data(), groups * 4, cudaMemcpyHostToDevice, st));
+    GS_CUDA(cudaMemcpyAsync(dAlpha, alpha, (size_t)n_cand * 8, cudaMemcpyHostToDevice, st));
+    std::vector<TcBatch> bg(nb), bc(groups);
+    for (int b = 0; b < nb; b++) bg[b] = TcBatch{0, 0, poff[b], poff[b + 1], bG.as<float>() + (size_t)b * Dp * Dp, (int64_t)Dp};
+    for (int g = 0; g < groups; g++) bc[g] = TcBatch{g * n_cand, g * dp, 0, dp, dQ + (size_t)g * n_cand * dp, (int64_t)dp};
+    GS_CUDA(cudaMemcpyAsync(dBatchG, bg.data(), nb * sizeof(TcBatch), cudaMemcpyHostToDevice, st));
+    GS_CUDA(cudaMemcpyAsync(dBatchCG, bc.data(), groups * sizeof(TcBatch), cudaMemcpyHostToDevice, st));
+    int64_t launches = 0;
+
+    // ---- 1. Z^T, split, fold Grams on tensor cores ----
+    GS_CUDA(cudaMemsetAsync(bZ.p, 0, (size_t)Dp * ldz * 4, st));
+    {
+        int maxc = 0;
+        for (int c : cnt) maxc = std::max(maxc, c);
+        dim3 grid((maxc + 31) / 32, (D + 31) / 32, nb), block(32, 32);
+        build_zt_kernel<<<grid, block, 0, st>>>(h->dX.as<float>(), h->dYt.as<float>(), d, nb, dRow0, dCnt, dPoff, bZ.as<float>(), ldz);
+        GS_CUDA(cudaGetLastError());
+    }
+    GS_CUDA(launch_split_tf32(bZ.as<float>(), bZh.as<float>(), bZl.as<float>(), (size_t)Dp * ldz, st));
+    TcMap mzh, mzl;
+    GS_CUDA(tc_make_map(&mzh, bZh.as<float>(), Dp, ldz, ldz));
+    GS_CUDA(tc_make_map(&mzl, bZl.as<float>(), Dp, ldz, ldz));
+    GS_CUDA(launch_gemm_nt_tf32x3(mzh, mzl, mzh, mzl, dBatchG, nb, D, D, 1.0f, false, st));
+    sum_grams_kernel<<<296, 256, 0, st>>>(bG.as<float>(), nb, (int64_t)Dp * Dp, dT);
+    GS_CUDA(cudaGetLastError());
+    launches += 4;
+    cudaEventRecord(ev[1], st);
+
+    // ---- 2. per-group centred systems ----
+    {
+        dim3 block(32, 8), grid((dp + 31) / 32, (dp + 7) / 8, groups);
+        build_systems_kernel<<<grid, block, 0, st>>>(dT, bG.as<float>(), dTestBlock, d, Dp, dp, fit_intercept, dA, dRhs, dMeans);
+        GS_CUDA(cudaGetLastError());
+    }
+    GS_CUDA(launch_split_tf32(dA, dAh, dAl, (size_t)groups * dp * dp, st));
+    TcMap mah, mal, mph, mpl;
+    GS_CUDA(tc_make_map(&mah, dAh, (int64_t)groups * dp, dp, dp));
+    GS_CUDA(tc_make_map(&mal, dAl, (int64_t)groups * dp, dp, dp));
+    GS_CUDA(tc_make_map(&mph, dPh, nsys, dp, dp));
+    GS_CUDA(tc_make_map(&mpl, dPl, nsys, dp, dp));
+    launches += 2;
+
+    // ---- 3. batched CG: Q = P A_g on tensor cores, vector updates in cg_step_kernel ----
+    cg_init_kernel<<<nsys, 256, 0, st>>>(dRhs, n_cand, dp, dX, dR, dP, dPh, dPl, dRR, dBB, dDone);
+    GS_CUDA(cudaGetLastError());
+    launches++;
+    int open = 1, it = 0;
+    while (open > 0 && it < CG_MAX_ITER) {
+        for (int rep = 0; rep < 4; rep++, it++) {
+            GS_CUDA(launch_gemm_nt_tf32x3(mph, mpl, mah, mal, dBatchCG, groups, n_cand, dp, 1.0f, false, st));
+            GS_CUDA(cudaMemsetAsync(dOpen, 0, 4, st));
+            cg_step_kernel<<<nsys, 256, 0, st>>>(dQ, dAlpha, n_cand, dp, dX, dR, dP, dPh, dPl, dRR, dBB, dDone, dOpen, CG_TOL * CG_TOL);
+            GS_CUDA(cudaGetLastError());
+            launches += 2;
+        }
+        GS_CUDA(cudaMemcpyAsync(&open, dOpen, 4, cudaMemcpyDeviceToHost, st));
+        GS_CUDA(cudaStreamSynchronize(st));
+    }
+    if (open > 0) {
+        gs_set_error(h, "gs_ridge: conjugate gradients did not converge in " + std::to_string(CG_MAX_ITER) + " iterations for " +
+                            std::to_string(open) + " systems (ill-conditioned normal matrix)");
+        return GS_ERR_NUMERIC;
+    }
+    cudaEventRecord(ev[2], st);
+
+    // ---- 4. scores / coefficients ----
+    if (!refit) {
+        ridge_r2_kernel<<<nsys, 256, (size_t)d * 8, st>>>(dX, dT, bG.as<float>(), dTestBlock, dMeans, n_cand, d, Dp, dp, fit_intercept, dOut);
+        GS_CUDA(cudaGetLastError());
+        launches++;
+        std::vector<double> out((size_t)nsys * 2);
+        GS_CUDA(cudaMemcpyAsync(out.data(), dOut, out.size() * 8, cudaMemcpyDeviceToHost, st));
+        cudaEventRecord(ev[3], st);
+        GS_CUDA(cudaStreamSynchronize(st));
+        for (int g = 0; g < groups; g++)
+            for (int c = 0; c < n_cand; c++) {
+                const size_t s = (size_t)g * n_cand + c;
+                test_scores[(size_t)c * ns + g] = out[s * 2];
+                if (train_scores) train_scores[(size_t)c * ns + g] = out[s * 2 + 1];
+            }
+        h->prof.d2h_bytes = (int64_t)out.size() * 8;
+    } else {
+        std::vector<float> w(dp);
+        std::vector<double> means(dp + 2);
+        GS_CUDA(cudaMemcpyAsync(w.data(), dX, (size_t)dp * 4, cudaMemcpyDeviceToHost, st));
+        GS_CUDA(cudaMemcpyAsync(means.data(), dMeans, (size_t)(dp + 2) * 8, cudaMemcpyDeviceToHost, st));
+        cudaEventRecord(ev[3], st);
+        GS_CUDA(cudaStreamSynchronize(st));
+        double b0 = means[dp];
+        for (int j = 0; j < d; j++) {
+            const int o = j;                                       // feature order is unchanged
+            coef_out[o] = (double)w[j];
+            b0 -= means[j] * (double)w[j];
+        }
+        coef_out[d] = fit_intercept ? b0 : 0.0;
+    }
+    cudaEventRecord(ev[4], st);
+    GS_CUDA(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&tmr->gram, ev[0], ev[1]);
+    cudaEventElapsedTime(&tmr->solve, ev[1], ev[2]);
+    cudaEventElapsedTime(&tmr->score, ev[2], ev[3]);
+    cudaEventElapsedTime(&tmr->total, ev[0], ev[4]);
+    for (auto &e : ev) cudaEventDestroy(e);
+    gs_profile &pf = h->prof;
+    const float keep_h2d = pf.ms_h2d; const int64_t keep_b = pf.h2d_bytes, keep_d2h = pf.d2h_bytes;
+    memset(&pf, 0, sizeof pf);
+    pf.ms_h2d = keep_h2d; pf.h2d_bytes = keep_b; pf.d2h_bytes = keep_d2h;
+    pf.ms_total = tmr->total; pf.ms_gram = tmr->gram; pf.ms_solve = tmr->solve; pf.ms_score = tmr->score;
+    pf.launches = launches;
+    pf.smo_iterations = it;                                        // CG iterations
+    pf.gram_flops = 2.0 * (double)n * D * D;
+    pf.gram_bytes = (double)n * D * 4 + (double)nb * D * D * 4;
+    pf.solve_bytes = 0;
+    return GS_OK;
+}
+
+}  // namespace
 
 extern "C" {
 
-int gs_ridge(gs_handle *h, int32_t, const double *, int32_t, uint32_t, double *, double *, float *, float *)
+int gs_ridge(gs_handle *h, int32_t n_cand, const double *alpha, int32_t fit_intercept, uint32_t flags, double *test_scores,
+             double *train_scores, float *fit_ms, float *score_ms)
 {
-    gs_set_error(h, "gs_ridge: not implemented in this build"); return GS_ERR_UNSUPPORTED;
+    if (h && !test_scores) { gs_set_error(h, "gs_ridge: test_scores is NULL"); return GS_ERR_ARG; }
+    RidgeTimers t;
+    const int st = ridge_run(h, n_cand, alpha, fit_intercept, false, test_scores, (flags & GS_RETURN_TRAIN) ? train_scores : nullptr,
+                             nullptr, &t);
+    if (st) return st;
+    const int nt = n_cand * h->n_splits;
+    for (int i = 0; i < nt; i++) {
+        if (fit_ms) fit_ms[i] = (t.gram + t.solve) / (float)nt;
+        if (score_ms) score_ms[i] = t.score / (float)nt;
+    }
+    return GS_OK;
 }
-int gs_ridge_refit(gs_handle *h, double, int32_t, double *)
+
+int gs_ridge_refit(gs_handle *h, double alpha, int32_t fit_intercept, double *coef_out)
 {
-    gs_set_error(h, "gs_ridge_refit: not implemented in this build"); return GS_ERR_UNSUPPORTED;
+    if (h && !coef_out) { gs_set_error(h, "gs_ridge_refit: coef_out is NULL"); return GS_ERR_ARG; }
+    RidgeTimers t;
+    return ridge_run(h, 1, &alpha, fit_intercept, true, nullptr, nullptr, coef_out, &t);
 }
+
 int gs_logreg(gs_handle *h, int32_t, const double *, double, int32_t, int32_t, uint32_t, double *, double *, int32_t *, float *, float *)
 {
     gs_set_error(h, "gs_logreg: not implemented in this build"); return GS_ERR_UNSUPPORTED;
@@ -21,10 +461,8 @@ int gs_logreg_refit(gs_handle *h, double, double, int32_t, int32_t, double *, in
     gs_set_error(h, "gs_logreg_refit: not implemented in this build"); return GS_ERR_UNSUPPORTED;
 }
 
-}
-
 // ---- test hook: one tensor-core GEMM with host buffers ----
-extern "C" int gs_debug_gemm_nt(gs_handle *h, const float *A, int32_t M, const float *B, int32_t N, int32_t K, float *C)
+int gs_debug_gemm_nt(gs_handle *h, const float *A, int32_t M, const float *B, int32_t N, int32_t K, float *C)
 {
     if (!h || !A || !B || !C || M <= 0 || N <= 0 || K <= 0) return GS_ERR_ARG;
     GS_CUDA(cudaSetDevice(h->device));
@@ -51,3 +489,5 @@ extern "C" int gs_debug_gemm_nt(gs_handle *h, const float *A, int32_t M, const f
     a.release(); ah.release(); al.release(); b.release(); bh.release(); bl.release(); c.release(); bt.release();
     return GS_OK;
 }
+
+}  // extern "C"
