@@ -111,6 +111,8 @@ struct TcBatch {                                                    // one GEMM 
 };
 cudaError_t tc_make_map(TcMap *out, const float *base, int64_t rows, int64_t cols, int64_t ld);
 cudaError_t launch_split_tf32(const float *x, float *hi, float *lo, size_t n, cudaStream_t st);
+constexpr int TC_KCHUNK = 512;   // longest accumulation chain kept inside the (truncating) TMEM accumulator
+cudaError_t launch_sum_partials(const float *partial, int n_chunks, int64_t per, float *out, cudaStream_t st);
 cudaError_t launch_gemm_nt_tf32x3(const TcMap &a_hi, const TcMap &a_lo, const TcMap &b_hi, const TcMap &b_lo,
                                   const TcBatch *d_batches, int n_batches, int M, int N, float alpha, bool accumulate,
                                   cudaStream_t st);

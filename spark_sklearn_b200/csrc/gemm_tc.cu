@@ -12,6 +12,11 @@
 // Replaces (reference path -> scikit-learn): safe_sparse_dot(X.T, X) of _solve_cholesky (_ridge.py:219),
 // X @ w and X.T @ grad of the logistic objective (_linear_loss.py), and -- opt-in -- the libsvm kernel rows.
 //
+// The TMEM accumulator adds with truncation, so a long contraction drifts by ~sqrt(K)*2^-24 of sum|a||b| -- harmless
+// for a Gram diagonal, ruinous for a heavily cancelled sum such as a gradient near its zero.  Callers therefore
+// bound every accumulation chain to TC_KCHUNK terms (one TcBatch per K-chunk) and add the partial tiles in float64
+// on the CUDA cores (launch_sum_partials).
+//
 // Tile: 128 x 128 x 32 (fp32) per stage; one CTA (4 warps) per output tile:
 //   warp 0 / lane 0: TMA producer        warp 1 / lane 0: MMA issuer (12 MMAs per stage)
 //   all 4 warps: epilogue (tcgen05.ld 32x32b.x32 -> registers -> global, optional scale/accumulate)
@@ -19,6 +24,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cstdio>
+#include <algorithm>
 
 namespace {
 
@@ -195,6 +201,16 @@ __global__ void split_tf32_kernel(const float *__restrict__ x, float *__restrict
     }
 }
 
+// out[i] = (float) sum_c partial[c][i] accumulated in float64 (round-to-nearest), i < per
+__global__ void sum_partials_kernel(const float *__restrict__ partial, int n_chunks, int64_t per, float *__restrict__ out)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0;
+        for (int c = 0; c < n_chunks; c++) s += (double)partial[(size_t)c * per + i];
+        out[i] = (float)s;
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -227,6 +243,12 @@ cudaError_t tc_make_map(TcMap *out, const float *base, int64_t rows, int64_t col
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+cudaError_t launch_sum_partials(const float *partial, int n_chunks, int64_t per, float *out, cudaStream_t st)
+{
+    sum_partials_kernel<<<(unsigned)std::min<int64_t>((per + 255) / 256, 1184), 256, 0, st>>>(partial, n_chunks, per, out);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_split_tf32(const float *x, float *hi, float *lo, size_t n, cudaStream_t st)

@@ -1,4 +1,4 @@
-// linear.cu -- Ridge search (gs_ridge / gs_ridge_refit) and the LogisticRegression entry points.
+// linear.cu -- Ridge search (gs_ridge / gs_ridge_refit).
 //
 // Ridge path (replaces sklearn Ridge.fit/score reached from reference base_search.py:83-87:
 // linear_model/_ridge.py:919 fit, :964 _preprocess_data centring, :215-227 _solve_cholesky, base.py:716 r2):
@@ -52,13 +52,20 @@ __global__ void build_zt_kernel(const float *__restrict__ X, const float *__rest
     }
 }
 
-// T = sum_b G_b in float64
-__global__ void sum_grams_kernel(const float *__restrict__ G, int n_blocks, int64_t per, double *__restrict__ T)
+// The Gram of a row block is contracted in chunks of <= TC_KCHUNK rows (the TMEM accumulator truncates); the chunk
+// partials Gq are added here in float64: G_b = sum of the chunks of block b (chunks qs[b] .. qs[b+1]), T = sum_b G_b.
+__global__ void sum_grams_kernel(const float *__restrict__ Gq, const int *__restrict__ qs, int n_blocks, int64_t per,
+                                 float *__restrict__ G, double *__restrict__ T)
 {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x) {
-        double s = 0;
-        for (int b = 0; b < n_blocks; b++) s += (double)G[(size_t)b * per + i];
-        T[i] = s;
+        double tot = 0;
+        for (int b = 0; b < n_blocks; b++) {
+            double s = 0;
+            for (int q = qs[b]; q < qs[b + 1]; q++) s += (double)Gq[(size_t)q * per + i];
+            G[(size_t)b * per + i] = (float)s;
+            tot += s;
+        }
+        T[i] = tot;
     }
 }
 
@@ -271,9 +278,16 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
         if (r < n) { row0.push_back(r); cnt.push_back(n - r); }
     }
     const int nb = (int)row0.size();
-    std::vector<int> poff(nb + 1, 0);
-    for (int b = 0; b < nb; b++) poff[b + 1] = poff[b] + ((cnt[b] + 31) & ~31);
-    const int64_t ldz = poff[nb];
+    // contraction chunks: <= TC_KCHUNK rows each, zero-padded to a multiple of 32 columns of Z^T
+    std::vector<int> crow0, ccnt, qs(nb + 1, 0);
+    for (int b = 0; b < nb; b++) {
+        for (int r = 0; r < cnt[b]; r += TC_KCHUNK) { crow0.push_back(row0[b] + r); ccnt.push_back(std::min(TC_KCHUNK, cnt[b] - r)); }
+        qs[b + 1] = (int)crow0.size();
+    }
+    const int nq = (int)crow0.size();
+    std::vector<int> poff(nq + 1, 0);
+    for (int q = 0; q < nq; q++) poff[q + 1] = poff[q] + ((ccnt[q] + 31) & ~31);
+    const int64_t ldz = poff[nq];
     const int groups = refit ? 1 : ns;
     const int nsys = groups * n_cand;
 
@@ -285,54 +299,58 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     DevBuf &bZ = h->dWork[0], &bZh = h->dWork[1], &bZl = h->dWork[2], &bG = h->dWork[3], &bMisc = h->dWork[4],
            &bA = h->dWork[5], &bV = h->dWork[6], &bMeta = h->dWork[7];
     GS_CUDA(bZ.reserve((size_t)Dp * ldz * 4)); GS_CUDA(bZh.reserve((size_t)Dp * ldz * 4)); GS_CUDA(bZl.reserve((size_t)Dp * ldz * 4));
-    GS_CUDA(bG.reserve((size_t)nb * Dp * Dp * 4));
+    GS_CUDA(bG.reserve((size_t)(nb + nq) * Dp * Dp * 4));                   // per-block Grams, then the chunk partials
     const size_t tBytes = (size_t)Dp * Dp * 8, meansBytes = (size_t)groups * (dp + 2) * 8;
     GS_CUDA(bMisc.reserve(tBytes + meansBytes + (size_t)nsys * (8 + 8 + 16) + (size_t)n_cand * 8 + 256));
     GS_CUDA(bA.reserve((size_t)groups * dp * dp * 4 * 3 + (size_t)groups * dp * 4));
-    GS_CUDA(bV.reserve((size_t)nsys * dp * 4 * 6));
-    GS_CUDA(bMeta.reserve((size_t)(nb * 3 + groups) * 4 + (size_t)(nb + groups) * sizeof(TcBatch) + (size_t)nsys * 4 + 64));
+    GS_CUDA(bV.reserve((size_t)nsys * dp * 4 * (6 + (size_t)((dp + TC_KCHUNK - 1) / TC_KCHUNK))));
+    const int nkc = (dp + TC_KCHUNK - 1) / TC_KCHUNK;                          // K-chunks of the CG product
+    GS_CUDA(bMeta.reserve((size_t)(nq * 3 + nb + 1 + groups) * 4 + (size_t)(nq + groups * nkc) * sizeof(TcBatch) + (size_t)nsys * 4 + 128));
     double *dT = bMisc.as<double>();
     double *dMeans = dT + (size_t)Dp * Dp;
     double *dRR = dMeans + (size_t)groups * (dp + 2), *dBB = dRR + nsys, *dOut = dBB + nsys, *dAlpha = dOut + 2 * (size_t)nsys;
     float *dA = bA.as<float>(), *dAh = dA + (size_t)groups * dp * dp, *dAl = dAh + (size_t)groups * dp * dp,
           *dRhs = dAl + (size_t)groups * dp * dp;
     float *dX = bV.as<float>(), *dR = dX + (size_t)nsys * dp, *dP = dR + (size_t)nsys * dp, *dPh = dP + (size_t)nsys * dp,
-          *dPl = dPh + (size_t)nsys * dp, *dQ = dPl + (size_t)nsys * dp;
-    int *dRow0 = bMeta.as<int>(), *dCnt = dRow0 + nb, *dPoff = dCnt + nb, *dTestBlock = dPoff + nb;
+          *dPl = dPh + (size_t)nsys * dp, *dQ = dPl + (size_t)nsys * dp, *dQp = dQ + (size_t)nsys * dp;
+    float *dGq = bG.as<float>() + (size_t)nb * Dp * Dp;
+    int *dRow0 = bMeta.as<int>(), *dCnt = dRow0 + nq, *dPoff = dCnt + nq, *dQs = dPoff + nq, *dTestBlock = dQs + nb + 1;
     int *dDone = dTestBlock + groups;
     int *dOpen = dDone + nsys;
     TcBatch *dBatchG = reinterpret_cast<TcBatch *>(((uintptr_t)(dOpen + 4) + 15) & ~(uintptr_t)15);
-    TcBatch *dBatchCG = dBatchG + nb;
+    TcBatch *dBatchCG = dBatchG + nq;
 
     std::vector<int> testBlock(groups);
     for (int g = 0; g < groups; g++) testBlock[g] = refit ? -1 : g;
-    GS_CUDA(cudaMemcpyAsync(dRow0, row0.data(), nb * 4, cudaMemcpyHostToDevice, st));
-    GS_CUDA(cudaMemcpyAsync(dCnt, cnt.data(), nb * 4, cudaMemcpyHostToDevice, st));
-    GS_CUDA(cudaMemcpyAsync(dPoff, poff.data(), nb * 4, cudaMemcpyHostToDevice, st));
+    GS_CUDA(cudaMemcpyAsync(dRow0, crow0.data(), nq * 4, cudaMemcpyHostToDevice, st));
+    GS_CUDA(cudaMemcpyAsync(dCnt, ccnt.data(), nq * 4, cudaMemcpyHostToDevice, st));
+    GS_CUDA(cudaMemcpyAsync(dPoff, poff.data(), nq * 4, cudaMemcpyHostToDevice, st));
+    GS_CUDA(cudaMemcpyAsync(dQs, qs.data(), (nb + 1) * 4, cudaMemcpyHostToDevice, st));
     GS_CUDA(cudaMemcpyAsync(dTestBlock, testBlock.data(), groups * 4, cudaMemcpyHostToDevice, st));
     GS_CUDA(cudaMemcpyAsync(dAlpha, alpha, (size_t)n_cand * 8, cudaMemcpyHostToDevice, st));
-    std::vector<TcBatch> bg(nb), bc(groups);
-    for (int b = 0; b < nb; b++) bg[b] = TcBatch{0, 0, poff[b], poff[b + 1], bG.as<float>() + (size_t)b * Dp * Dp, (int64_t)Dp};
-    for (int g = 0; g < groups; g++) bc[g] = TcBatch{g * n_cand, g * dp, 0, dp, dQ + (size_t)g * n_cand * dp, (int64_t)dp};
-    GS_CUDA(cudaMemcpyAsync(dBatchG, bg.data(), nb * sizeof(TcBatch), cudaMemcpyHostToDevice, st));
-    GS_CUDA(cudaMemcpyAsync(dBatchCG, bc.data(), groups * sizeof(TcBatch), cudaMemcpyHostToDevice, st));
+    std::vector<TcBatch> bg(nq), bc;
+    for (int q = 0; q < nq; q++) bg[q] = TcBatch{0, 0, poff[q], poff[q + 1], dGq + (size_t)q * Dp * Dp, (int64_t)Dp};
+    for (int kc = 0; kc < nkc; kc++)                                               // partial kc of Q = P A_g
+        for (int g = 0; g < groups; g++)
+            bc.push_back(TcBatch{g * n_cand, g * dp, kc * TC_KCHUNK, std::min(dp, (kc + 1) * TC_KCHUNK),
+                                 dQp + (size_t)kc * nsys * dp + (size_t)g * n_cand * dp, (int64_t)dp});
+    GS_CUDA(cudaMemcpyAsync(dBatchG, bg.data(), nq * sizeof(TcBatch), cudaMemcpyHostToDevice, st));
+    GS_CUDA(cudaMemcpyAsync(dBatchCG, bc.data(), bc.size() * sizeof(TcBatch), cudaMemcpyHostToDevice, st));
     int64_t launches = 0;
 
     // ---- 1. Z^T, split, fold Grams on tensor cores ----
     GS_CUDA(cudaMemsetAsync(bZ.p, 0, (size_t)Dp * ldz * 4, st));
     {
-        int maxc = 0;
-        for (int c : cnt) maxc = std::max(maxc, c);
-        dim3 grid((maxc + 31) / 32, (D + 31) / 32, nb), block(32, 32);
-        build_zt_kernel<<<grid, block, 0, st>>>(h->dX.as<float>(), h->dYt.as<float>(), d, nb, dRow0, dCnt, dPoff, bZ.as<float>(), ldz);
+        dim3 grid((TC_KCHUNK + 31) / 32, (D + 31) / 32, nq), block(32, 32);
+        build_zt_kernel<<<grid, block, 0, st>>>(h->dX.as<float>(), h->dYt.as<float>(), d, nq, dRow0, dCnt, dPoff, bZ.as<float>(), ldz);
         GS_CUDA(cudaGetLastError());
     }
     GS_CUDA(launch_split_tf32(bZ.as<float>(), bZh.as<float>(), bZl.as<float>(), (size_t)Dp * ldz, st));
     TcMap mzh, mzl;
     GS_CUDA(tc_make_map(&mzh, bZh.as<float>(), Dp, ldz, ldz));
     GS_CUDA(tc_make_map(&mzl, bZl.as<float>(), Dp, ldz, ldz));
-    GS_CUDA(launch_gemm_nt_tf32x3(mzh, mzl, mzh, mzl, dBatchG, nb, D, D, 1.0f, false, st));
-    sum_grams_kernel<<<296, 256, 0, st>>>(bG.as<float>(), nb, (int64_t)Dp * Dp, dT);
+    GS_CUDA(launch_gemm_nt_tf32x3(mzh, mzl, mzh, mzl, dBatchG, nq, D, D, 1.0f, false, st));
+    sum_grams_kernel<<<592, 256, 0, st>>>(dGq, dQs, nb, (int64_t)Dp * Dp, bG.as<float>(), dT);
     GS_CUDA(cudaGetLastError());
     launches += 4;
     cudaEventRecord(ev[1], st);
@@ -358,9 +376,10 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     int open = 1, it = 0;
     while (open > 0 && it < CG_MAX_ITER) {
         for (int rep = 0; rep < 4; rep++, it++) {
-            GS_CUDA(launch_gemm_nt_tf32x3(mph, mpl, mah, mal, dBatchCG, groups, n_cand, dp, 1.0f, false, st));
+            GS_CUDA(launch_gemm_nt_tf32x3(mph, mpl, mah, mal, dBatchCG, groups * nkc, n_cand, dp, 1.0f, false, st));
+            if (nkc > 1) GS_CUDA(launch_sum_partials(dQp, nkc, (int64_t)nsys * dp, dQ, st));
             GS_CUDA(cudaMemsetAsync(dOpen, 0, 4, st));
-            cg_step_kernel<<<nsys, 256, 0, st>>>(dQ, dAlpha, n_cand, dp, dX, dR, dP, dPh, dPl, dRR, dBB, dDone, dOpen, CG_TOL * CG_TOL);
+            cg_step_kernel<<<nsys, 256, 0, st>>>(nkc > 1 ? dQ : dQp, dAlpha, n_cand, dp, dX, dR, dP, dPh, dPl, dRR, dBB, dDone, dOpen, CG_TOL * CG_TOL);
             GS_CUDA(cudaGetLastError());
             launches += 2;
         }
@@ -420,7 +439,7 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     pf.launches = launches;
     pf.smo_iterations = it;                                        // CG iterations
     pf.gram_flops = 2.0 * (double)n * D * D;
-    pf.gram_bytes = (double)n * D * 4 + (double)nb * D * D * 4;
+    pf.gram_bytes = (double)n * D * 4 + (double)nq * D * D * 4;
     pf.solve_bytes = 0;
     return GS_OK;
 }
@@ -450,15 +469,6 @@ int gs_ridge_refit(gs_handle *h, double alpha, int32_t fit_intercept, double *co
     if (h && !coef_out) { gs_set_error(h, "gs_ridge_refit: coef_out is NULL"); return GS_ERR_ARG; }
     RidgeTimers t;
     return ridge_run(h, 1, &alpha, fit_intercept, true, nullptr, nullptr, coef_out, &t);
-}
-
-int gs_logreg(gs_handle *h, int32_t, const double *, double, int32_t, int32_t, uint32_t, double *, double *, int32_t *, float *, float *)
-{
-    gs_set_error(h, "gs_logreg: not implemented in this build"); return GS_ERR_UNSUPPORTED;
-}
-int gs_logreg_refit(gs_handle *h, double, double, int32_t, int32_t, double *, int32_t *)
-{
-    gs_set_error(h, "gs_logreg_refit: not implemented in this build"); return GS_ERR_UNSUPPORTED;
 }
 
 // ---- test hook: one tensor-core GEMM with host buffers ----

@@ -59,3 +59,12 @@ def test_ridge_python_api_and_refit(engine):
     np.testing.assert_array_equal(a.cv_results_["rank_test_score"], b.cv_results_["rank_test_score"])
     assert np.abs(a.best_estimator_.coef_ - b.best_estimator_.coef_).max() <= 2e-4 * np.abs(b.best_estimator_.coef_).max()
     assert np.abs(a.predict(X) - b.predict(X)).max() <= 1e-3 * np.abs(y).max()
+
+
+def test_ridge_c5_full_size_vs_golden(engine):
+    """BASELINE config 5 at full size: 512 alphas x 10 folds on 20000x1024 -- the 1e-4 bar on mean_test_score."""
+    w, fold_id, ns = _setup(engine, "c5")
+    g = golden("c5_ridge_512")
+    r = engine.ridge([c["alpha"] for c in W.candidates(w)])
+    assert np.abs(r["test"].mean(1) - g["test_scores"].mean(1)).max() <= 5e-5
+    assert np.abs(r["train"].mean(1) - g["train_scores"].mean(1)).max() <= 5e-5
