@@ -24,23 +24,29 @@ def test_logreg_c3_small_vs_golden(engine):
     assert np.mean(r["n_iter"] == it_gold) >= 0.9, (r["n_iter"], it_gold)      # same L-BFGS-B trajectory
     assert np.abs(r["test"] - g["test_scores"]).max() <= 2 * 1.25e-3 + 1e-12       # at most two flips on an 800-row fold
     assert np.abs(r["test"].mean(1) - g["test_scores"].mean(1)).max() <= 5e-4 + 1e-12
-    assert np.abs(r["train"] - g["train_scores"]).max() <= 3 * 3.2e-4 + 1e-12
+    assert np.abs(r["train"] - g["train_scores"]).max() <= 4 * 3.2e-4 + 1e-12      # <= 4 flips on 3200 training rows
 
 
 def test_logreg_python_api_and_refit(engine):
+    """Public API + refit.  The optimiser is trajectory-identical to scipy's (coefficients agree to ~1e-6) except when
+    the gtol stopping test is borderline: |g|_inf within float32 rounding of 1e-4 stops one iteration earlier or later
+    than scikit-learn's own float32 BLAS run does (measured: 1 of 40 reduced-size fits), worth a flip or two."""
     from sklearn.linear_model import LogisticRegression
     from sklearn.model_selection import GridSearchCV as SkGrid
     from spark_sklearn_b200 import GridSearchCV
     w = W.make_workload("c3_small")
     X, y = w["X"], w["y"]
-    grid = {"C": [1e-3, 1e-1, 10.0]}
+    grid = {"C": [1e-3, 1e-1, 50.0]}
     a = GridSearchCV(None, LogisticRegression(), grid, cv=5).fit(X, y)
     b = SkGrid(LogisticRegression(), grid, cv=5, return_train_score=True).fit(X, y)
     assert np.abs(a.cv_results_["mean_test_score"] - b.cv_results_["mean_test_score"]).max() <= 5e-4 + 1e-12   # <= 2 flips / 4000
     ca, cb = a.best_estimator_.coef_, b.best_estimator_.coef_
+    assert a.best_params_ == b.best_params_
     assert a.best_estimator_.n_iter_[0] == b.best_estimator_.n_iter_[0]
-    assert np.abs(ca - cb).max() <= 1e-3 * np.abs(cb).max()
-    assert np.mean(a.predict(X) == b.predict(X)) >= 0.999
+    assert np.abs(ca - cb).max() <= 1e-5 * np.abs(cb).max()
+    assert abs(a.best_estimator_.intercept_[0] - b.best_estimator_.intercept_[0]) <= 1e-6
+    np.testing.assert_array_equal(a.predict(X), b.predict(X))
+    assert a.predict_proba(X).shape == (len(y), 2)
 
 
 def test_logreg_c3_full_size_vs_golden(engine):
