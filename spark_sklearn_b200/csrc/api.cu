@@ -93,6 +93,13 @@ int gs_create(int device, gs_handle **out)
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         g_create_error = cudaGetErrorString(e); delete h; return GS_ERR_CUDA;
     }
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if ((e = cudaStreamCreateWithPriority(&h->stream_hi, cudaStreamNonBlocking, hi)) != cudaSuccess) {
+            g_create_error = cudaGetErrorString(e); cudaStreamDestroy(h->stream); delete h; return GS_ERR_CUDA;
+        }
+    }
     memset(&h->prof, 0, sizeof h->prof);
     *out = h;
     return GS_OK;
@@ -106,6 +113,7 @@ void gs_destroy(gs_handle *h)
     h->dS.release(); h->dXsq.release(); h->dK.release(); h->dX64.release();
     for (auto &w : h->dWork) w.release();
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream_hi) cudaStreamDestroy(h->stream_hi);
     delete h;
 }
 
@@ -255,7 +263,7 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
             }
     }
     sp_off.back() = (int)rows_all.size();
-    if (lmax > smo_max_rows()) {
+    if (lmax > smo_max_rows() && lmax > smo_cluster_max_rows(4)) {
         gs_set_error(h, "gs_svc: sub-problem with " + std::to_string(lmax) + " rows exceeds the resident-state SMO kernel limit of " +
                             std::to_string(smo_max_rows()));
         return GS_ERR_UNSUPPORTED;
@@ -370,15 +378,20 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
             P.coef = h->dWork[3].as<double>() + (size_t)q * n;
             P.out_rho = d_rho + q; P.out_info = d_info + 4 * (size_t)q; P.out_ns = d_ns + 8 * (size_t)q;
         }
-        // longest-first launch order: iterations grow with C and with 1/gamma
+        // Longest-first launch order.  SMO iteration counts grow with C until the box constraint stops binding, and
+        // that saturation level grows with 1/gamma (config 2: ~C^0.8 up to C_sat ~ 12.5/(gamma*d), measured); the
+        // predicted-longest problems lead the order so that they start first and get the cluster kernel.
+        std::vector<double> cost(np);
+        for (int q = 0; q < np; q++) {
+            const int t = prob_task[q];
+            const double Cq = Cv[t / n_splits];
+            const auto &grp = groups[task_group[t]];
+            const double sat = grp.first == GS_KERNEL_RBF ? 12.5 / (grp.second * (double)d) : Cq;
+            cost[q] = std::min(Cq, sat) * (double)probs[q].l * (grp.first == GS_KERNEL_RBF ? std::pow(grp.second * d, -0.35) : 1.0);
+        }
         std::vector<int> order(np);
         std::iota(order.begin(), order.end(), 0);
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-            const int ta = prob_task[a], tb = prob_task[b];
-            const double ca = Cv[ta / n_splits] * probs[a].l, cb = Cv[tb / n_splits] * probs[b].l;
-            if (ca != cb) return ca > cb;
-            return groups[task_group[ta]].second < groups[task_group[tb]].second;
-        });
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
         unsigned char *dmeta = h->dWork[6].as<unsigned char>();
         SmoProblem *d_probs = (SmoProblem *)dmeta;
         int *d_order = (int *)(dmeta + (size_t)np * sizeof(SmoProblem));
@@ -396,10 +409,48 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
         pf.h2d_bytes += (size_t)np * sizeof(SmoProblem) + (size_t)np * 4 + vtasks.size() * sizeof(VoteTask);
         tm.mark(4);
         // -- solve --
+        // The step is bounded by its longest sub-problems.  The predicted-longest share of the problems is solved by
+        // the cluster kernel (one problem over `cl` SMs, high-priority stream, launched first); the rest by the
+        // single-CTA kernel.  Development switches: B200GS_SMO_CLUSTER (0/2/4), B200GS_SMO_CLUSTER_PCT.
         std::string why;
-        cudaError_t ce = launch_smo(d_probs, d_order, np, lmax, fast, st, &why);
-        if (ce != cudaSuccess) { gs_set_error(h, why.empty() ? std::string("launch_smo: ") + cudaGetErrorString(ce) : why); return why.empty() ? GS_ERR_CUDA : GS_ERR_UNSUPPORTED; }
-        pf.launches++;
+        // Policy (measured on config 2, profiles/): a cluster CTA set cuts the per-iteration latency of one problem
+        // (7.1 us on one SM -> 5.7 us on 4 SMs -> 4.7 us on 8 SMs) but not the SM-time per iteration, so clusters go to
+        // the problems that bound the makespan: everything when there are fewer problems than SMs to fill, else the
+        // predicted-longest 6 %.
+        int cl = 0, pct = 0;
+        if (lmax > 2048) {
+            if (np * 8 <= h->sm_count) { cl = 8; pct = 100; }
+            else if (np * 4 <= h->sm_count) { cl = 4; pct = 100; }
+            else if (np * 2 <= h->sm_count) { cl = 2; pct = 100; }
+            else { cl = 4; pct = 6; }
+        }
+        if (const char *e = getenv("B200GS_SMO_CLUSTER")) cl = atoi(e);
+        if (const char *e = getenv("B200GS_SMO_CLUSTER_PCT")) pct = atoi(e);
+        int n_cl = 0;
+        if ((cl == 2 || cl == 4 || cl == 8) && lmax <= smo_cluster_max_rows(cl) && lmax > 2048)
+            n_cl = std::max(pct > 0 ? 1 : 0, (int)((int64_t)np * pct / 100));
+        if (n_cl > 0) {
+            cudaEvent_t ready, done;
+            cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
+            cudaEventRecord(ready, st);
+            cudaStreamWaitEvent(h->stream_hi, ready, 0);
+            cudaError_t ce = launch_smo_cluster(d_probs, d_order, n_cl, lmax, cl, fast, h->stream_hi);
+            if (ce != cudaSuccess) { gs_set_error(h, std::string("launch_smo_cluster: ") + cudaGetErrorString(ce)); return GS_ERR_CUDA; }
+            cudaEventRecord(done, h->stream_hi);
+            pf.launches++;
+            if (np - n_cl > 0) {
+                ce = launch_smo(d_probs, d_order + n_cl, np - n_cl, lmax, fast, st, &why);
+                if (ce != cudaSuccess) { gs_set_error(h, why.empty() ? std::string("launch_smo: ") + cudaGetErrorString(ce) : why); return why.empty() ? GS_ERR_CUDA : GS_ERR_UNSUPPORTED; }
+                pf.launches++;
+            }
+            cudaStreamWaitEvent(st, done, 0);
+            cudaEventDestroy(ready); cudaEventDestroy(done);
+        } else {
+            cudaError_t ce = launch_smo(d_probs, d_order, np, lmax, fast, st, &why);
+            if (ce != cudaSuccess) { gs_set_error(h, why.empty() ? std::string("launch_smo: ") + cudaGetErrorString(ce) : why); return why.empty() ? GS_ERR_CUDA : GS_ERR_UNSUPPORTED; }
+            pf.launches++;
+        }
         tm.mark(2);
         // -- score (skipped for refit) --
         if (!refit) {

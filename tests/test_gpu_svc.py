@@ -158,3 +158,30 @@ def test_python_api_iris(engine):
     np.testing.assert_allclose(clf.decision_function(X), sk.decision_function(X), rtol=0, atol=1e-12)
     assert clf.score(X, y) == sk.score(X, y)
     assert clf.estimator.get_params() == clone(svm.SVC(gamma='auto')).get_params()   # the reference's assertion
+
+
+@pytest.mark.parametrize("cl", [2, 4, 8])
+def test_cluster_smo_bitexact(engine, monkeypatch, cl):
+    """Every sub-problem through the thread-block-cluster solver (one problem over 2 / 4 / 8 SMs, DSMEM exchange):
+    same trajectory, same scores as scikit-learn."""
+    monkeypatch.setenv("B200GS_SMO_CLUSTER", str(cl))
+    monkeypatch.setenv("B200GS_SMO_CLUSTER_PCT", "100")
+    w, fold_id, ns = _setup(engine, "c2_mid")
+    g = golden("c2_mid")
+    r = _run(engine, w, W.candidates(w))
+    np.testing.assert_array_equal(r["n_iter"], g["diag"][:, :, 0].astype(np.int32))
+    np.testing.assert_array_equal(r["n_sv"], g["diag"][:, :, 1].astype(np.int32))
+    np.testing.assert_array_equal(r["test"], g["test_scores"])
+    np.testing.assert_array_equal(r["train"], g["train_scores"])
+
+
+def test_c2_full_size_vs_golden(engine):
+    """BASELINE config 2 at full size (10000x512, 8x8 grid, cv=5 = 320 fits): every split score equals scikit-learn's."""
+    w, fold_id, ns = _setup(engine, "c2")
+    g = golden("c2_svc_rbf_8x8")
+    r = _run(engine, w, W.candidates(w))
+    np.testing.assert_array_equal(r["test"], g["test_scores"])
+    np.testing.assert_array_equal(r["train"], g["train_scores"])
+    np.testing.assert_array_equal(r["n_sv"], g["diag"][:, :, 1].astype(np.int32))
+    assert np.mean(r["n_iter"] == g["diag"][:, :, 0].astype(np.int32)) >= 0.98     # a float64-exp last bit moves ~1 trajectory in 320
+    assert np.abs(r["test"].mean(1) - g["test_scores"].mean(1)).max() <= 1e-4     # the BASELINE bar (observed: 0)

@@ -59,6 +59,11 @@ def main(key, reps=2):
         it = out["n_iter"]
         print("n_iter: min %d median %d max %d total %d; fit_ms max %.1f" % (it.min(), np.median(it), it.max(), it.sum(), out["fit_ms"].max()))
 
+    if "n_iter" in out and os.environ.get("B200GS_PRINT_US"):
+        us = out["fit_ms"] * 1e3 / np.maximum(out["n_iter"], 1)
+        o = np.argsort(-out["n_iter"].ravel())
+        print("us/iter: longest10 %s | median all %.2f | min %.2f max %.2f" % (np.round(us.ravel()[o[:10]], 2), np.median(us), us.min(), us.max()))
+
 
 if __name__ == "__main__":
     main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 2)
