@@ -206,7 +206,6 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
     if (h->n == 0) { gs_set_error(h, "gs_svc: no dataset (call gs_set_data first)"); return GS_ERR_NO_DATA; }
     if (!h->classification) { gs_set_error(h, "gs_svc: dataset has no class labels"); return GS_ERR_ARG; }
     if (h->n_classes < 2 || h->n_classes > 32) { gs_set_error(h, "gs_svc: need 2..32 classes"); return GS_ERR_UNSUPPORTED; }
-    if (flags & GS_GRAM_TENSOR) { gs_set_error(h, "gs_svc: GS_GRAM_TENSOR is not available in this build"); return GS_ERR_UNSUPPORTED; }
     if (n_cand <= 0 || !kernel || !Cv || !gamma) { gs_set_error(h, "gs_svc: bad arguments"); return GS_ERR_ARG; }
     GS_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
@@ -231,13 +230,36 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
     cudaEventRecord(ev_begin, st);
     tm.mark(-1);
 
-    // ---- 1. float64 Gram (shared by every candidate, fold and pair) ----
+    // ---- 1. Gram X X^T (shared by every candidate, fold and pair) ----
+    // default: float64 on the FP64 pipe (libsvm-faithful, gram.cu).  GS_GRAM_TENSOR: tcgen05 tensor cores, 3xTF32 split,
+    // TMA-fed (gemm_tc.cu) -- fp32-faithful, so scores agree with scikit-learn to solver tolerance, not bit for bit.
     GS_CUDA(h->dS.reserve((size_t)n * n * 8));
     GS_CUDA(h->dXsq.reserve((size_t)n * 8));
-    GS_CUDA(launch_gram_f64(h->x_dtype == GS_F64 ? h->dX64.p : h->dX.p, h->x_dtype, n, d, h->dS.as<double>(), h->dXsq.as<double>(), st));
-    pf.launches++;
+    if (flags & GS_GRAM_TENSOR) {
+        const int dpad = (d + 31) & ~31;
+        const int64_t ld32 = ((int64_t)n + 3) & ~3LL;
+        DevBuf &bx = h->dWork[1], &bs = h->dWork[2], &bb = h->dWork[6];
+        GS_CUDA(bx.reserve((size_t)n * dpad * 4 * 3));
+        GS_CUDA(bs.reserve((size_t)n * ld32 * 4));
+        GS_CUDA(bb.reserve(sizeof(TcBatch) + 64));
+        float *xp = bx.as<float>(), *xh = xp + (size_t)n * dpad, *xl = xh + (size_t)n * dpad;
+        GS_CUDA(cudaMemsetAsync(xp, 0, (size_t)n * dpad * 4, st));
+        GS_CUDA(cudaMemcpy2DAsync(xp, (size_t)dpad * 4, h->dX.p, (size_t)d * 4, (size_t)d * 4, n, cudaMemcpyDeviceToDevice, st));
+        GS_CUDA(launch_split_tf32(xp, xh, xl, (size_t)n * dpad, st));
+        TcMap mh, ml;
+        GS_CUDA(tc_make_map(&mh, xh, n, dpad, dpad));
+        GS_CUDA(tc_make_map(&ml, xl, n, dpad, dpad));
+        TcBatch hb{0, 0, 0, dpad, bs.as<float>(), ld32};
+        GS_CUDA(cudaMemcpyAsync(bb.p, &hb, sizeof hb, cudaMemcpyHostToDevice, st));
+        GS_CUDA(launch_gemm_nt_tf32x3(mh, ml, mh, ml, bb.as<TcBatch>(), 1, n, n, 1.0f, false, st));
+        GS_CUDA(launch_widen_gram(bs.as<float>(), n, ld32, h->dS.as<double>(), h->dXsq.as<double>(), st));
+        pf.launches += 3;
+    } else {
+        GS_CUDA(launch_gram_f64(h->x_dtype == GS_F64 ? h->dX64.p : h->dX.p, h->x_dtype, n, d, h->dS.as<double>(), h->dXsq.as<double>(), st));
+        pf.launches++;
+    }
     pf.gram_flops = 2.0 * n * (double)n * d;
-    pf.gram_bytes = (double)n * d * 4 + (double)n * n * 8;
+    pf.gram_bytes = (double)n * d * 4 + (double)n * n * ((flags & GS_GRAM_TENSOR) ? 4 : 8);
     tm.mark(0);
 
     // ---- 2. sub-problem row lists per (fold, pair): class a rows then class b rows, train rows only ----

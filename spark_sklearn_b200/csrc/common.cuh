@@ -62,6 +62,7 @@ void gs_set_error(gs_handle *h, const std::string &msg);
 // ---- gram.cu ----
 // S = X X^T in float64 from float32 X (exact products, float64 accumulation); xsq = diag(S).
 cudaError_t launch_gram_f64(const void *X, int x_dtype, int n, int d, double *S, double *xsq, cudaStream_t st);
+cudaError_t launch_widen_gram(const float *S32, int n, int64_t ld32, double *S, double *xsq, cudaStream_t st);
 // K[r][c] = (float) k(x_r, x_c) from S: rbf exp(-gamma*(xsq_r + xsq_c - 2 S_rc)) or linear S_rc.
 // *special (device int, pre-zeroed, may be null) is set when an entry is not a positive normal float.
 cudaError_t launch_kernel_matrix(const double *S, const double *xsq, int n, int kernel, double gamma,

@@ -135,7 +135,27 @@ kernel_matrix_kernel(const double *__restrict__ S, const double *__restrict__ xs
     if (special && __any_sync(0xffffffffu, odd) && (threadIdx.x & 31) == 0) atomicOr(special, 1);
 }
 
+// tensor-core mode: widen the float32 Gram of gemm_tc.cu to the float64 layout the other kernels read, taking the
+// diagonal as the squared norms; the two triangles of a tensor-core result can differ in the last bit, so the
+// upper one is mirrored to keep K symmetric exactly as libsvm's is.
+__global__ void widen_gram_kernel(const float *__restrict__ S32, int n, int64_t ld32, double *__restrict__ S, double *__restrict__ xsq)
+{
+    const int r = blockIdx.y;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        const float v = r <= c ? S32[(size_t)r * ld32 + c] : S32[(size_t)c * ld32 + r];
+        S[(size_t)r * n + c] = (double)v;
+        if (r == c) xsq[r] = (double)v;
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_widen_gram(const float *S32, int n, int64_t ld32, double *S, double *xsq, cudaStream_t st)
+{
+    dim3 grid((n + 1023) / 1024, n);
+    widen_gram_kernel<<<grid, 256, 0, st>>>(S32, n, ld32, S, xsq);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_gram_f64(const void *X, int x_dtype, int n, int d, double *S, double *xsq, cudaStream_t st)
 {

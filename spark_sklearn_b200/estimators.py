@@ -173,8 +173,11 @@ class SVCPlan(_Plan):
             C = [float(params[j]["C"]) for j in idx]
             gam = np.array([[self._gamma(params[j]["gamma"], k) if params[j]["kernel"] == "rbf" else 0.0
                              for k in range(ns)] for j in idx])
+            # B200GS_GRAM=tensor: opt-in tcgen05 Gram (fp32-faithful; scores match to solver tolerance, not bit for bit)
+            import os
+            flags = 2 if os.environ.get("B200GS_GRAM", "exact") == "tensor" else 0
             r = self.engine.svc(kern, C, gam, tol=tol, max_iter=max_iter, shrinking=shrinking,
-                                return_train=return_train)
+                                return_train=return_train, flags=flags)
             for key in ("test", "fit_ms", "score_ms", "n_iter"):
                 res[key][idx] = r[key]
             if return_train:

@@ -185,3 +185,18 @@ def test_c2_full_size_vs_golden(engine):
     np.testing.assert_array_equal(r["n_sv"], g["diag"][:, :, 1].astype(np.int32))
     assert np.mean(r["n_iter"] == g["diag"][:, :, 0].astype(np.int32)) >= 0.98     # a float64-exp last bit moves ~1 trajectory in 320
     assert np.abs(r["test"].mean(1) - g["test_scores"].mean(1)).max() <= 1e-4     # the BASELINE bar (observed: 0)
+
+
+def test_tensor_core_gram_mode(engine):
+    """GS_GRAM_TENSOR: the Gram on tcgen05 tensor cores (3xTF32).  fp32-faithful Q entries differ from libsvm's by an
+    ulp or two, so trajectories diverge within libsvm's own stopping tolerance: scores agree to a few margin flips."""
+    from spark_sklearn_b200.engine import GS_GRAM_TENSOR
+    w, fold_id, ns = _setup(engine, "c2_mid")
+    g = golden("c2_mid")
+    cands = W.candidates(w)
+    r = engine.svc(["rbf"] * len(cands), [c["C"] for c in cands], np.array([c["gamma"] for c in cands])[:, None],
+                   flags=GS_GRAM_TENSOR)
+    assert np.abs(r["test"] - g["test_scores"]).max() <= 5 / 600 + 1e-12            # <= 5 flips on a 600-row fold
+    assert np.abs(r["test"].mean(1) - g["test_scores"].mean(1)).max() <= 3e-3
+    rel = np.abs(r["n_iter"] - g["diag"][:, :, 0]) / g["diag"][:, :, 0]
+    assert np.median(rel) < 0.05
