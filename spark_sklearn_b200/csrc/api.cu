@@ -462,14 +462,14 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
             cudaEventRecord(done, h->stream_hi);
             pf.launches++;
             if (np - n_cl > 0) {
-                ce = launch_smo(d_probs, d_order + n_cl, np - n_cl, lmax, fast, st, &why);
+                ce = launch_smo(d_probs, d_order + n_cl, np - n_cl, lmax, fast, (int)ldk, st, &why);
                 if (ce != cudaSuccess) { gs_set_error(h, why.empty() ? std::string("launch_smo: ") + cudaGetErrorString(ce) : why); return why.empty() ? GS_ERR_CUDA : GS_ERR_UNSUPPORTED; }
                 pf.launches++;
             }
             cudaStreamWaitEvent(st, done, 0);
             cudaEventDestroy(ready); cudaEventDestroy(done);
         } else {
-            cudaError_t ce = launch_smo(d_probs, d_order, np, lmax, fast, st, &why);
+            cudaError_t ce = launch_smo(d_probs, d_order, np, lmax, fast, (int)ldk, st, &why);
             if (ce != cudaSuccess) { gs_set_error(h, why.empty() ? std::string("launch_smo: ") + cudaGetErrorString(ce) : why); return why.empty() ? GS_ERR_CUDA : GS_ERR_UNSUPPORTED; }
             pf.launches++;
         }

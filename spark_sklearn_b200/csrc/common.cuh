@@ -85,7 +85,7 @@ struct SmoProblem {
     int l, n_pos, max_iter, shrinking;
 };
 // Solve problems order[0..n_prob) (one CTA each); lmax = max l (selects the template instance).
-cudaError_t launch_smo(const SmoProblem *d_probs, const int *d_order, int n_prob, int lmax, bool fast,
+cudaError_t launch_smo(const SmoProblem *d_probs, const int *d_order, int n_prob, int lmax, bool fast, int rowcap,
                        cudaStream_t st, std::string *why);
 int smo_max_rows();   // largest sub-problem the resident-state kernel supports
 // smo_cluster.cu: the same solver with one sub-problem spread over a thread-block cluster of cl CTAs (DSMEM exchange)

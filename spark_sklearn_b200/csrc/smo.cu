@@ -42,9 +42,13 @@ using namespace smo;
 
 // FAST: every problem of the launch is rbf (QD == 1) and its K matrix holds only positive normal floats,
 // so the widening is three integer instructions and quad = 2 - 2K needs no diagonal lookups.
-template <int NT, int KPT, bool SMEM_STATE, bool FAST, bool PROF>
+// ROWBUF: the two K rows of an iteration are brought into shared memory by ONE bulk asynchronous copy each
+// (cp.async.bulk, mbarrier-signalled) and gathered from there.  A row gathered with per-thread LDGs is throttled by
+// the SM's outstanding-miss capacity (~64 lines x ~900 cycles of DRAM latency = ~18 GB/s per SM, 2.5 us per 32 KB row,
+// measured); the bulk copy streams the whole 40 KB row at the SM's full fill rate.  G_bar then lives in global memory.
+template <int NT, int KPT, bool SMEM_STATE, bool FAST, bool PROF, bool ROWBUF>
 __global__ void __launch_bounds__(NT, 1)
-smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order)
+smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, int rowcap)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ Red red;
@@ -58,7 +62,10 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order)
     double *const mG = reinterpret_cast<double *>(smem_raw);                // m_t = -y_t G_t
     double *mGbar, *alpha;
     unsigned short *col;                                                    // dataset row of each position
-    if constexpr (SMEM_STATE) {
+    if constexpr (ROWBUF) {
+        alpha = mG + LCAP; mGbar = Pp->Gbar;
+        col = reinterpret_cast<unsigned short *>(mG + 2 * LCAP);
+    } else if constexpr (SMEM_STATE) {
         mGbar = mG + LCAP; alpha = mG + 2 * LCAP;
         col = reinterpret_cast<unsigned short *>(mG + 3 * LCAP);
     } else {
@@ -66,6 +73,9 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order)
         col = reinterpret_cast<unsigned short *>(mG + LCAP);
     }
     unsigned char *const fl = reinterpret_cast<unsigned char *>(col + LCAP);
+    float *const rowbuf = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(fl + LCAP) + 127) & ~(uintptr_t)127);
+    __shared__ unsigned long long rowbar;
+    unsigned rowphase = 0;
     const float *__restrict__ const K = Pp->K;
     const int64_t ldk = Pp->ldk;
     const double eps = Pp->eps;
@@ -88,8 +98,40 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order)
             alpha[t] = 0.0;
             if (use_gbar) mGbar[t] = 0.0;
         }
+        for (int t = l + tid; t < LCAP; t += NT) { mG[t] = 0.0; col[t] = 0; fl[t] = 0; }   // slots past l: inert
+    }
+    if constexpr (ROWBUF) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&rowbar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
     }
     __syncthreads();
+
+    // bulk fetch of dataset row `r` of K into rowbuf (issued by one thread) and the matching wait (all threads)
+    auto fetch_row = [&](int r) {
+        if constexpr (ROWBUF) {
+            if (tid == 0) {
+                const unsigned bar = (unsigned)__cvta_generic_to_shared(&rowbar);
+                const unsigned bytes = (unsigned)rowcap * 4u;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"((unsigned)__cvta_generic_to_shared(rowbuf)), "l"(K + (size_t)r * ldk), "r"(bytes), "r"(bar) : "memory");
+            }
+        }
+    };
+    auto wait_row = [&]() {
+        if constexpr (ROWBUF) {
+            const unsigned bar = (unsigned)__cvta_generic_to_shared(&rowbar);
+            unsigned done = 0;
+            for (unsigned spin = 0; !done; ++spin) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(bar), "r"(rowphase) : "memory");
+                if (spin > (1u << 26)) __trap();
+            }
+            rowphase ^= 1u;
+        }
+    };
 
     int active = l, iter = 0, timed_out = 0;
     int counter = (l < 1000 ? l : 1000) + 1;
@@ -214,10 +256,12 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order)
         const float *__restrict__ Ki = K + (size_t)col[i] * ldk;
         {
             float kv[KPT];
+            if constexpr (ROWBUF) { fetch_row(col[i]); wait_row(); }
 #pragma unroll
             for (int k = 0; k < KPT; k++) {                                  // issue the whole gather first
                 const int t = k * NT + tid;
-                kv[k] = t < active ? __ldg(Ki + col[t]) : 0.f;
+                if constexpr (ROWBUF) kv[k] = t < active ? rowbuf[col[t]] : 0.f;
+                else kv[k] = t < active ? __ldg(Ki + col[t]) : 0.f;
             }
 #pragma unroll
             for (int k = 0; k < KPT; k++) qi[k] = widen(kv[k]);
@@ -408,10 +452,13 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order)
         const int i = pi >> IDX_SHIFT, j = pj >> IDX_SHIFT;
         const float *__restrict__ Kj = K + (size_t)col[j] * ldk;
         float kvj[KPT];
+        if constexpr (ROWBUF) fetch_row(col[j]);                 // everybody is past barrier 2: row i is no longer read
+        else {
 #pragma unroll
-        for (int k = 0; k < KPT; k++) {                          // issue the Q_j gather before the scalar update
-            const int t = k * NT + tid;
-            kvj[k] = t < active ? __ldg(Kj + col[t]) : 0.f;
+            for (int k = 0; k < KPT; k++) {                      // issue the Q_j gather before the scalar update
+                const int t = k * NT + tid;
+                kvj[k] = t < active ? __ldg(Kj + col[t]) : 0.f;
+            }
         }
         if (warp == 0) {                                         // analytic 2-variable update, once per CTA
             const double C = Pp->C;
@@ -454,6 +501,14 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order)
         tick(4);
         __syncthreads();                                                          // barrier 3
         tick(1);
+        if constexpr (ROWBUF) {
+            wait_row();
+#pragma unroll
+            for (int k = 0; k < KPT; k++) {
+                const int t = k * NT + tid;
+                kvj[k] = t < active ? rowbuf[col[t]] : 0.f;
+            }
+        }
         const double a = red.bc_d[0], b = red.bc_d[1];
         const int sti = red.bc_i[0], stj = red.bc_i[1];
         // the owners of i and j publish alpha and status FIRST: the fused scan below must see the new sets
@@ -545,25 +600,26 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order)
     }
 }
 
-template <int NT, int KPT, bool SMEM_STATE, bool FAST, bool PROF>
-cudaError_t launch_one(const SmoProblem *probs, const int *order, int n_prob, cudaStream_t st)
+template <int NT, int KPT, bool SMEM_STATE, bool FAST, bool PROF, bool ROWBUF>
+cudaError_t launch_one(const SmoProblem *probs, const int *order, int n_prob, int rowcap, cudaStream_t st)
 {
     constexpr int LCAP = NT * KPT;
-    const size_t smem = (size_t)LCAP * (SMEM_STATE ? (8 + 8 + 8 + 2 + 1) : (8 + 2 + 1));
-    auto kern = smo_kernel<NT, KPT, SMEM_STATE, FAST, PROF>;
+    const size_t smem = ROWBUF ? (size_t)LCAP * (8 + 8 + 2 + 1) + 128 + (size_t)rowcap * 4
+                               : (size_t)LCAP * (SMEM_STATE ? (8 + 8 + 8 + 2 + 1) : (8 + 2 + 1));
+    auto kern = smo_kernel<NT, KPT, SMEM_STATE, FAST, PROF, ROWBUF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<n_prob, NT, smem, st>>>(probs, order);
+    kern<<<n_prob, NT, smem, st>>>(probs, order, rowcap);
     return cudaGetLastError();
 }
 
-template <int NT, int KPT, bool SMEM_STATE>
-cudaError_t launch_cfg(const SmoProblem *probs, const int *order, int n_prob, bool fast, bool prof, cudaStream_t st)
+template <int NT, int KPT, bool SMEM_STATE, bool ROWBUF = false>
+cudaError_t launch_cfg(const SmoProblem *probs, const int *order, int n_prob, bool fast, bool prof, int rowcap, cudaStream_t st)
 {
-    if (prof) return fast ? launch_one<NT, KPT, SMEM_STATE, true, true>(probs, order, n_prob, st)
-                          : launch_one<NT, KPT, SMEM_STATE, false, true>(probs, order, n_prob, st);
-    return fast ? launch_one<NT, KPT, SMEM_STATE, true, false>(probs, order, n_prob, st)
-                : launch_one<NT, KPT, SMEM_STATE, false, false>(probs, order, n_prob, st);
+    if (prof) return fast ? launch_one<NT, KPT, SMEM_STATE, true, true, ROWBUF>(probs, order, n_prob, rowcap, st)
+                          : launch_one<NT, KPT, SMEM_STATE, false, true, ROWBUF>(probs, order, n_prob, rowcap, st);
+    return fast ? launch_one<NT, KPT, SMEM_STATE, true, false, ROWBUF>(probs, order, n_prob, rowcap, st)
+                : launch_one<NT, KPT, SMEM_STATE, false, false, ROWBUF>(probs, order, n_prob, rowcap, st);
 }
 
 int env_int(const char *name, int dflt)
@@ -577,17 +633,24 @@ int env_int(const char *name, int dflt)
 int smo_max_rows() { return 1024 * 16; }
 
 // fast: every problem is rbf and every kernel matrix of the launch holds only positive normal floats
-cudaError_t launch_smo(const SmoProblem *d_probs, const int *d_order, int n_prob, int lmax, bool fast, cudaStream_t st,
+// rowcap: row length of the K matrices in floats (ldk); enables the bulk-copy row path when the row fits in shared memory
+cudaError_t launch_smo(const SmoProblem *d_probs, const int *d_order, int n_prob, int lmax, bool fast, int rowcap, cudaStream_t st,
                        std::string *why)
 {
     if (n_prob <= 0) return cudaSuccess;
     const bool prof = env_int("B200GS_SMO_PROF", 0) != 0;          // development switch: per-phase cycle counters
     if (env_int("B200GS_SMO_NOFAST", 0)) fast = false;
-    if (lmax <= 512) return launch_cfg<128, 4, true>(d_probs, d_order, n_prob, fast, prof, st);
-    if (lmax <= 2048) return launch_cfg<256, 8, true>(d_probs, d_order, n_prob, fast, prof, st);
-    if (lmax <= 4096) return launch_cfg<512, 8, true>(d_probs, d_order, n_prob, fast, prof, st);
-    if (lmax <= 8192) return launch_cfg<1024, 8, true>(d_probs, d_order, n_prob, fast, prof, st);
-    if (lmax <= 16384) return launch_cfg<1024, 16, false>(d_probs, d_order, n_prob, fast, prof, st);
+    if (lmax <= 512) return launch_cfg<128, 4, true>(d_probs, d_order, n_prob, fast, prof, 0, st);
+    if (lmax <= 2048) return launch_cfg<256, 8, true>(d_probs, d_order, n_prob, fast, prof, 0, st);
+    if (lmax <= 4096) return launch_cfg<512, 8, true>(d_probs, d_order, n_prob, fast, prof, 0, st);
+    if (lmax <= 8192) {
+        // 8192 rows of state without G_bar = 152 KB; the row buffer may use what is left of the 227 KB
+        const bool rowbuf_fits = (size_t)8192 * 19 + 128 + (size_t)rowcap * 4 + 4096 <= 227 * 1024;
+        if (rowbuf_fits && env_int("B200GS_SMO_ROWBUF", 1))
+            return launch_cfg<1024, 8, true, true>(d_probs, d_order, n_prob, fast, prof, rowcap, st);
+        return launch_cfg<1024, 8, true>(d_probs, d_order, n_prob, fast, prof, 0, st);
+    }
+    if (lmax <= 16384) return launch_cfg<1024, 16, false>(d_probs, d_order, n_prob, fast, prof, 0, st);
     if (why) *why = "SVC sub-problem larger than 16384 rows is not supported by the resident-state SMO kernel";
     return cudaErrorInvalidValue;
 }
