@@ -266,7 +266,12 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
 #pragma unroll
             for (int k = 0; k < KPT; k++) qi[k] = widen(kv[k]);
         }
-        double best1 = -CUDART_INF, best2 = -CUDART_INF, m1 = 0, q1 = 0;
+        // Approximate gd^2/quad is tracked by the HIGH WORD of the (non-negative) double only: 32-bit compares and
+        // moves instead of 64-bit ones.  High words order like the doubles to 2^-20; the band test below (514 units
+        // >= 2^-12 relative) sends every near-tie to the exact libsvm quotients, so the choice stays bit-identical.
+        unsigned b1k = 0u, b2k = 0u;                    // keys of the best and second-best candidate (0 = none)
+        int k1 = -1;
+        double m1 = 0, q1 = 0;
         int idx1 = -1;
 #pragma unroll
         for (int k = 0; k < KPT; k++) {
@@ -280,41 +285,44 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
                                              : __dsub_rn(__dadd_rn(QDi, QD(t)), __dmul_rn(2.0, qi[k]));
                     const double g2 = __dmul_rn(gd, gd);
                     const double ap = quad > 0 ? g2 * rcp_approx(quad) : g2 * 1e12;
-                    if (ap > best1) { best2 = best1; best1 = ap; idx1 = (t << IDX_SHIFT) | f; m1 = m; q1 = qi[k]; }
-                    else if (ap > best2) best2 = ap;
+                    const unsigned key = (unsigned)__double2hiint(ap) + 1u;      // +1: a valid candidate is never 0
+                    const bool gt = key > b1k;
+                    b2k = gt ? b1k : max(b2k, key);
+                    b1k = gt ? key : b1k;
+                    k1 = gt ? k : k1;
                 }
             }
         }
-        double top1, top2;
+        if (k1 >= 0) {
+            const int t1 = k1 * NT + tid, s1 = t1;
+            idx1 = (t1 << IDX_SHIFT) | fl[s1];
+            m1 = mG[s1];
+#pragma unroll
+            for (int k = 0; k < KPT; k++) q1 = k == k1 ? qi[k] : q1;
+        }
+        unsigned top1k, top2k;
         {
-            const unsigned long long key = dkey(best1);
-            const KArg w = warp_argmax((unsigned)(key >> 32), (unsigned)key, idx1);
-            const unsigned long long k2 = warp_keymax(dkey(idx1 == w.idx ? best2 : best1));
-            if (idx1 >= 0 && idx1 == w.idx) {                                  // this lane owns the warp's winner
+            const unsigned w1 = __reduce_max_sync(0xffffffffu, b1k);
+            const int widx = __reduce_max_sync(0xffffffffu, (b1k == w1) ? idx1 : -1);
+            const unsigned w2 = __reduce_max_sync(0xffffffffu, (idx1 == widx) ? b2k : b1k);
+            if (idx1 >= 0 && idx1 == widx) {                                   // this lane owns the warp's winner
                 red.pl_mg[warp] = m1; red.pl_kv[warp] = q1; red.pl_alpha[warp] = alpha[idx1 >> IDX_SHIFT];
             }
-            if (lane == 0) {
-                red.b_hi[warp] = w.hi; red.b_lo[warp] = w.lo; red.b_idx[warp] = w.idx;
-                red.t_hi[warp] = (unsigned)(k2 >> 32); red.t_lo[warp] = (unsigned)k2;
-            }
+            if (lane == 0) { red.b_hi[warp] = w1; red.b_idx[warp] = widx; red.t_hi[warp] = w2; }
             tick(2);
             __syncthreads();                                                      // barrier 2
             tick(3);
             const bool v = lane < NW;
-            const unsigned bh = v ? red.b_hi[lane] : 0u, bl = v ? red.b_lo[lane] : 0u;
+            const unsigned bk = v ? red.b_hi[lane] : 0u;
             const int bi = v ? red.b_idx[lane] : -1;
-            const KArg b = warp_argmax(bh, bl, bi);
-            const unsigned long long mine = ((unsigned long long)bh << 32) | bl;
-            const unsigned long long ru = v ? (((unsigned long long)red.t_hi[lane] << 32) | red.t_lo[lane]) : 0ull;
-            const unsigned long long k3 = warp_keymax((v && bi == b.idx) ? ru : mine);
-            pj = b.idx;
+            top1k = __reduce_max_sync(0xffffffffu, bk);
+            pj = __reduce_max_sync(0xffffffffu, (bk == top1k) ? bi : -1);
+            top2k = __reduce_max_sync(0xffffffffu, (v && bi == pj) ? red.t_hi[lane] : bk);
             if (pj < 0) return true;                                               // Gmin_idx == -1
-            top1 = dkey_inv(((unsigned long long)b.hi << 32) | b.lo);
-            top2 = dkey_inv(k3);
         }
-        if (top2 >= top1 * BAND) {
+        if (top1k - top2k <= 514u) {
             // ---- exact tie-break: libsvm's correctly rounded quotients for every element in the band ----
-            const double thrx = top1 * BAND;
+            const unsigned thrk = top1k > 514u ? top1k - 514u : 1u;
             double bestn = -CUDART_INF;
             int bidx = -1;
 #pragma unroll
@@ -328,7 +336,7 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
                         const double quad = __dsub_rn(__dadd_rn(QDi, QD(t)), __dmul_rn(2.0, qi[k]));
                         const double g2 = __dmul_rn(gd, gd);
                         const double ap = quad > 0 ? g2 * rcp_approx(quad) : g2 * 1e12;
-                        if (ap >= thrx) {
+                        if ((unsigned)__double2hiint(ap) + 1u >= thrk) {
                             const double nod = quad > 0 ? __ddiv_rn(g2, quad) : __ddiv_rn(g2, TAU);   // == -obj_diff
                             if (nod >= bestn) { bestn = nod; bidx = (t << IDX_SHIFT) | f; m1 = m; q1 = qi[k]; }
                         }

@@ -256,7 +256,12 @@ smo_cluster_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__
 #pragma unroll
             for (int k = 0; k < KPT; k++) qi[k] = widen(kv[k]);
         }
-        double best1 = -CUDART_INF, best2 = -CUDART_INF, m1 = 0, q1 = 0;
+        // Approximate gd^2/quad is tracked by the HIGH WORD of the (non-negative) double only: 32-bit compares and
+        // moves instead of 64-bit ones.  High words order like the doubles to 2^-20; the band test below (514 units
+        // >= 2^-12 relative) sends every near-tie to the exact libsvm quotients, so the choice stays bit-identical.
+        unsigned b1k = 0u, b2k = 0u;                    // keys of the best and second-best candidate (0 = none)
+        int k1 = -1;
+        double m1 = 0, q1 = 0;
         int idx1 = -1;
 #pragma unroll
         for (int k = 0; k < KPT; k++) {
@@ -270,37 +275,43 @@ smo_cluster_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__
                                              : __dsub_rn(__dadd_rn(QDi, QDc(col[s])), __dmul_rn(2.0, qi[k]));
                     const double g2 = __dmul_rn(gd, gd);
                     const double ap = quad > 0 ? g2 * rcp_approx(quad) : g2 * 1e12;
-                    if (ap > best1) { best2 = best1; best1 = ap; idx1 = (t << IDX_SHIFT) | f; m1 = m; q1 = qi[k]; }
-                    else if (ap > best2) best2 = ap;
+                    const unsigned key = (unsigned)__double2hiint(ap) + 1u;      // +1: a valid candidate is never 0
+                    const bool gt = key > b1k;
+                    b2k = gt ? b1k : max(b2k, key);
+                    b1k = gt ? key : b1k;
+                    k1 = gt ? k : k1;
                 }
             }
         }
-        double top1, top2;
+        if (k1 >= 0) {
+            const int t1 = (k1 * CL + (int)rank) * NT + tid, s1 = k1 * NT + tid;
+            idx1 = (t1 << IDX_SHIFT) | fl[s1];
+            m1 = mG[s1];
+#pragma unroll
+            for (int k = 0; k < KPT; k++) q1 = k == k1 ? qi[k] : q1;
+        }
+        unsigned top1k, top2k;
         {
-            const unsigned long long key = dkey(best1);
-            const KArg w = warp_argmax((unsigned)(key >> 32), (unsigned)key, idx1);
-            const unsigned long long k2 = warp_keymax(dkey(idx1 == w.idx ? best2 : best1));
-            if (idx1 >= 0 && idx1 == w.idx) {
+            const unsigned w1 = __reduce_max_sync(0xffffffffu, b1k);
+            const int widx = __reduce_max_sync(0xffffffffu, (b1k == w1) ? idx1 : -1);
+            const unsigned w2 = __reduce_max_sync(0xffffffffu, (idx1 == widx) ? b2k : b1k);
+            if (idx1 >= 0 && idx1 == widx) {
                 const int s = slot_of(idx1 >> IDX_SHIFT);
                 red.pl_mg[warp] = m1; red.pl_kv[warp] = q1; red.pl_alpha[warp] = alpha[s];
                 red.cnt[warp] = (int)col[s];
             }
-            if (lane == 0) {
-                red.b_hi[warp] = w.hi; red.b_lo[warp] = w.lo; red.b_idx[warp] = w.idx;
-                red.t_hi[warp] = (unsigned)(k2 >> 32); red.t_lo[warp] = (unsigned)k2;
-            }
+            if (lane == 0) { red.b_hi[warp] = w1; red.b_idx[warp] = widx; red.t_hi[warp] = w2; }
             __syncthreads();
             const bool v = lane < NW;
-            const unsigned bh = v ? red.b_hi[lane] : 0u, bl = v ? red.b_lo[lane] : 0u;
+            const unsigned bk = v ? red.b_hi[lane] : 0u;
             const int bi = v ? red.b_idx[lane] : -1;
-            const KArg b = warp_argmax(bh, bl, bi);
-            const unsigned long long mine = ((unsigned long long)bh << 32) | bl;
-            const unsigned long long ru = v ? (((unsigned long long)red.t_hi[lane] << 32) | red.t_lo[lane]) : 0ull;
-            const unsigned long long k3 = warp_keymax((v && bi == b.idx) ? ru : mine);
+            const unsigned c1 = __reduce_max_sync(0xffffffffu, bk);
+            const int cidx = __reduce_max_sync(0xffffffffu, (bk == c1) ? bi : -1);
+            const unsigned c2 = __reduce_max_sync(0xffffffffu, (v && bi == cidx) ? red.t_hi[lane] : bk);
             unsigned rec[XW] = {0};
-            rec[0] = b.hi; rec[1] = b.lo; rec[2] = (unsigned)b.idx; rec[3] = (unsigned)(k3 >> 32); rec[4] = (unsigned)k3;
-            if (b.idx >= 0) {
-                const int wj = ((b.idx >> IDX_SHIFT) % NT) >> 5;
+            rec[0] = c1; rec[2] = (unsigned)cidx; rec[3] = c2;
+            if (cidx >= 0) {
+                const int wj = ((cidx >> IDX_SHIFT) % NT) >> 5;
                 const double a = red.pl_mg[wj], bb = red.pl_kv[wj], c = red.pl_alpha[wj];
                 rec[5] = lo32(a); rec[6] = hi32(a); rec[7] = lo32(bb); rec[8] = hi32(bb); rec[9] = lo32(c); rec[10] = hi32(c);
                 rec[11] = (unsigned)red.cnt[wj];
@@ -308,28 +319,20 @@ smo_cluster_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__
             const unsigned (*r)[XW] = exchange(rec);
             int best = 0;
 #pragma unroll
-            for (int c = 1; c < CL; c++) {
-                const unsigned long long kb = ((unsigned long long)r[best][0] << 32) | r[best][1];
-                const unsigned long long kc = ((unsigned long long)r[c][0] << 32) | r[c][1];
-                if (kc > kb || (kc == kb && (int)r[c][2] > (int)r[best][2])) best = c;
-            }
-            unsigned long long kru = 0;
+            for (int c = 1; c < CL; c++)
+                if (r[c][0] > r[best][0] || (r[c][0] == r[best][0] && (int)r[c][2] > (int)r[best][2])) best = c;
+            top2k = 0u;
 #pragma unroll
-            for (int c = 0; c < CL; c++) {
-                const unsigned long long kc = c == best ? (((unsigned long long)r[c][3] << 32) | r[c][4])
-                                                        : (((unsigned long long)r[c][0] << 32) | r[c][1]);
-                kru = kc > kru ? kc : kru;
-            }
+            for (int c = 0; c < CL; c++) { const unsigned kc = c == best ? r[c][3] : r[c][0]; top2k = kc > top2k ? kc : top2k; }
+            top1k = r[best][0];
             pj = (int)r[best][2];
             if (pj < 0) return true;
-            top1 = dkey_inv(((unsigned long long)r[best][0] << 32) | r[best][1]);
-            top2 = dkey_inv(kru);
             mg_j = mk64(r[best][5], r[best][6]); k_ij = mk64(r[best][7], r[best][8]); alpha_j = mk64(r[best][9], r[best][10]);
             col_j = (int)r[best][11];
         }
-        if (top2 >= top1 * BAND) {
+        if (top1k - top2k <= 514u) {
             // exact tie-break among the elements of the band (rare)
-            const double thrx = top1 * BAND;
+            const unsigned thrk = top1k > 514u ? top1k - 514u : 1u;
             double bestn = -CUDART_INF;
             int bidx = -1;
 #pragma unroll
@@ -343,7 +346,7 @@ smo_cluster_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__
                         const double quad = __dsub_rn(__dadd_rn(QDi, QDc(col[s])), __dmul_rn(2.0, qi[k]));
                         const double g2 = __dmul_rn(gd, gd);
                         const double ap = quad > 0 ? g2 * rcp_approx(quad) : g2 * 1e12;
-                        if (ap >= thrx) {
+                        if ((unsigned)__double2hiint(ap) + 1u >= thrk) {
                             const double nod = quad > 0 ? __ddiv_rn(g2, quad) : __ddiv_rn(g2, TAU);
                             if (nod >= bestn) { bestn = nod; bidx = (t << IDX_SHIFT) | f; m1 = m; q1 = qi[k]; }
                         }

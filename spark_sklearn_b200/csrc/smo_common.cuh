@@ -10,7 +10,6 @@ constexpr int ST_LOWER = 0, ST_UPPER = 1, ST_FREE = 2;
 constexpr int F_YPOS = 4, F_UP = 8, F_LOW = 16, F_MARK = 32;
 constexpr int IDX_SHIFT = 5;                 // packed index = (position << 5) | (flags & 31)
 constexpr int SAFETY_MAX_ITER = 10000000;    // max_iter=-1 is "no limit" in libsvm; bound a runaway solve
-constexpr double BAND = 1.0 - 1.0 / 4096.0;  // filter band 2^-12 >> 2 * (rcp.approx error ~2^-20 + two roundings)
 
 __device__ __forceinline__ int mkflags(bool ypos, int st)
 {
