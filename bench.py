@@ -115,6 +115,8 @@ def cpu_sample(cands, n_splits, steps_total):
         idx = [(3 * side // 8) * side + (2 * side // 8), (6 * side // 8) * side + (3 * side // 8)]
     else:
         idx = [n // 3, (2 * n) // 3]
+    if steps_total > 4:
+        idx = idx[:1]                                  # many steps asked: one mid-grid candidate (5 fits, ~25 s) per step
     return idx, "%d of %d candidates (mid-grid, mean cost ~ grid mean), all %d folds: %d fits" % (
         len(idx), n, n_splits, len(idx) * n_splits)
 
@@ -279,12 +281,14 @@ def main():
     per_launch_bytes = sbytes / max(a.steps, 1) / max(world, 1)
     per_launch_s = solve_ms / max(a.steps, 1) * 1e-3
     achieved = per_launch_bytes / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
-    roofline = {"kernel": "smo_kernel (batched C-SVC SMO, one CTA per (candidate, fold))", "bound": "hbm",
+    roofline = {"kernel": "smo_kernel + smo_cluster_kernel (batched C-SVC SMO: one CTA, or one 4-CTA cluster, per (candidate, fold))", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "traffic": None,
                 "algorithmic_bytes_per_launch": per_launch_bytes,
-                "note": "algorithmic bytes = sum over sub-problems of n_iter * 2 rows * l * 4 B (SURVEY.md 8d); "
-                        "the kernel is issue/latency-bound, not bandwidth-bound (profiles/)"}
+                "note": "algorithmic bytes = sum over sub-problems of n_iter * 2 rows * l * 4 B (SURVEY.md 8d); the solver is "
+                        "instruction-issue/latency-bound, not bandwidth-bound (profiles/r01_smo_rowbuf_ncu_summary.txt: issue 58 %, "
+                        "DRAM 45 KB per iteration on a 10-problem capture = 0.7x the algorithmic 64 KB); traffic is null because the "
+                        "full-workload launch was not captured under ncu --set full"}
     result = {
         "metric": "candidate-fits/sec", "value": a.steps * fits / (ev_ms * 1e-3), "unit": "fits/s", "n_gpus": max(world, 1),
         "steps": a.steps, "warmup": W_, "ms_per_step": ev_ms / max(a.steps, 1), "higher_is_better": True,
