@@ -187,6 +187,25 @@ def test_c2_full_size_vs_golden(engine):
     assert np.abs(r["test"].mean(1) - g["test_scores"].mean(1)).max() <= 1e-4     # the BASELINE bar (observed: 0)
 
 
+def test_c4_full_size_vs_golden(engine):
+    """BASELINE config 4 (10000x512, 16x16 grid, cv=5 = 1280 fits; 1.9 h of scikit-learn on 6 cores): every split score
+    equals scikit-learn's."""
+    w, fold_id, ns = _setup(engine, "c4")
+    g = golden("c4_svc_rbf_16x16")
+    r = _run(engine, w, W.candidates(w))
+    assert np.abs(r["test"].mean(1) - g["test_scores"].mean(1)).max() <= 1e-4     # the BASELINE bar
+    print("c4: test-score mismatches %d/1280, train %d/1280, n_iter equal %d/1280" % (
+        (r["test"] != g["test_scores"]).sum(), (r["train"] != g["train_scores"]).sum(),
+        (r["n_iter"] == g["diag"][:, :, 0].astype(np.int32)).sum()))
+    np.testing.assert_array_equal(r["test"], g["test_scores"])
+    np.testing.assert_array_equal(r["train"], g["train_scores"])
+    # a float64-exp last bit changes ~2^-29 of the float32 Q entries: a handful of the 1280 trajectories end a few
+    # iterations apart, within libsvm's stopping tolerance (observed: 1 fit with one more support vector, no score change)
+    dsv = np.abs(r["n_sv"] - g["diag"][:, :, 1].astype(np.int32))
+    assert (dsv != 0).mean() <= 0.005 and dsv.max() <= 2
+    assert np.mean(r["n_iter"] == g["diag"][:, :, 0].astype(np.int32)) >= 0.98
+
+
 def test_tensor_core_gram_mode(engine):
     """GS_GRAM_TENSOR: the Gram on tcgen05 tensor cores (3xTF32).  fp32-faithful Q entries differ from libsvm's by an
     ulp or two, so trajectories diverge within libsvm's own stopping tolerance: scores agree to a few margin flips."""
