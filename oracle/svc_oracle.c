@@ -211,6 +211,11 @@ static double bias_term(const smo_t *s)                               /* svm.cpp
  *   hand the solver the very matrix a GPU kernel produced.
  * Outputs: coef[l] = alpha_k*y_k in sub-problem order, *rho, *n_iter, *obj; returns 1 if max_iter hit.
  */
+/* Optional working-set trace (development aid for cache studies): pairs of sub-problem row ids per iteration. */
+static int *g_trace; static long g_trace_cap, g_trace_len;
+void oracle_svc_set_trace(int *buf, long cap) { g_trace = buf; g_trace_cap = cap; g_trace_len = 0; }
+long oracle_svc_trace_len(void) { return g_trace_len; }
+
 int oracle_svc_solve(const double *X, int n, int d, const int *rows, int l, int n_pos,
                      int kernel, double gamma, double C, double eps, int shrinking, int max_iter,
                      const float *Kpre, long ldk,
@@ -250,6 +255,7 @@ int oracle_svc_solve(const double *X, int n, int d, const int *rows, int l, int 
             counter = 1;
         }
         iter++;
+        if (g_trace && g_trace_len + 2 <= g_trace_cap) { g_trace[g_trace_len++] = s.orig[i]; g_trace[g_trace_len++] = s.orig[j]; }
         const float *Qi = q_row(&q, s.orig[i]), *Qj = q_row(&q, s.orig[j]);
         double Ci = s.Cv[i], Cj = s.Cv[j], oai = s.alpha[i], oaj = s.alpha[j];
         if (s.y[i] != s.y[j]) {                                /* svm.cpp:772-815 */

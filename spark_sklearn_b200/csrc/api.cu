@@ -387,18 +387,19 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
         GS_CUDA(h->dWork[2].reserve(ws * 4));
         GS_CUDA(h->dWork[3].reserve((size_t)np * n * 8));                 // coef columns
         GS_CUDA(h->dWork[4].reserve((size_t)np * n * 8));                 // decision columns
-        GS_CUDA(h->dWork[5].reserve((size_t)np * (8 + 16 + 64) + 64));    // rho, info[4], ns[8]
+        GS_CUDA(h->dWork[5].reserve((size_t)np * (8 + 16 + 96) + 64));    // rho, info[4], ns[12]
         GS_CUDA(h->dWork[6].reserve((size_t)np * sizeof(SmoProblem) + (size_t)np * 4 + vtasks.size() * (sizeof(VoteTask) + 16) + 256));
         double *d_rho = h->dWork[5].as<double>();
         int *d_info = (int *)(d_rho + np);
         unsigned long long *d_ns = (unsigned long long *)(d_info + 4 * (size_t)np);
+        GS_CUDA(cudaMemsetAsync(d_ns, 0, (size_t)np * 12 * 8, st));
         for (int q = 0; q < np; q++) {
             SmoProblem &P = probs[q];
             P.alpha = h->dWork[1].as<double>() + (size_t)P.alpha;
             P.Gbar = h->dWork[1].as<double>() + (size_t)P.Gbar;
             P.scratch = h->dWork[2].as<int>() + (size_t)P.scratch;
             P.coef = h->dWork[3].as<double>() + (size_t)q * n;
-            P.out_rho = d_rho + q; P.out_info = d_info + 4 * (size_t)q; P.out_ns = d_ns + 8 * (size_t)q;
+            P.out_rho = d_rho + q; P.out_info = d_info + 4 * (size_t)q; P.out_ns = d_ns + 12 * (size_t)q;
         }
         // Longest-first launch order.  SMO iteration counts grow with C until the box constraint stops binding, and
         // that saturation level grows with 1/gamma (config 2: ~C^0.8 up to C_sat ~ 12.5/(gamma*d), measured); the
@@ -457,7 +458,9 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
             cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
             cudaEventRecord(ready, st);
             cudaStreamWaitEvent(h->stream_hi, ready, 0);
-            cudaError_t ce = launch_smo_cluster(d_probs, d_order, n_cl, lmax, cl, fast, h->stream_hi);
+            const char *co = getenv("B200GS_SMO_CO");                           // development switch: 0 = position-owned cluster kernel
+            cudaError_t ce = (co && atoi(co) == 0) ? launch_smo_cluster(d_probs, d_order, n_cl, lmax, cl, fast, (int)ldk, h->stream_hi)
+                                                   : launch_smo_colown(d_probs, d_order, n_cl, lmax, cl, fast, h->stream_hi);
             if (ce != cudaSuccess) { gs_set_error(h, std::string("launch_smo_cluster: ") + cudaGetErrorString(ce)); return GS_ERR_CUDA; }
             cudaEventRecord(done, h->stream_hi);
             pf.launches++;
@@ -490,7 +493,7 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
         tm.mark(3);
         // -- results of this batch --
         std::vector<int> info((size_t)np * 4), counts(vtasks.size() * 4);
-        std::vector<unsigned long long> ns((size_t)np * 8);
+        std::vector<unsigned long long> ns((size_t)np * 12);
         std::vector<double> rho(np);
         GS_CUDA(cudaMemcpyAsync(info.data(), d_info, info.size() * 4, cudaMemcpyDeviceToHost, st));
         GS_CUDA(cudaMemcpyAsync(ns.data(), d_ns, ns.size() * 8, cudaMemcpyDeviceToHost, st));
@@ -508,7 +511,7 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
         for (int q = 0; q < np; q++) {
             const int t = prob_task[q];
             task_iter[t] += info[(size_t)q * 4]; task_sv[t] += info[(size_t)q * 4 + 2];
-            task_fit_ms[t] += (double)(ns[(size_t)q * 8 + 1] - ns[(size_t)q * 8]) * 1e-6;
+            task_fit_ms[t] += (double)(ns[(size_t)q * 12 + 1] - ns[(size_t)q * 12]) * 1e-6;
             total_iter += info[(size_t)q * 4];
             // two gathered K rows of the problem's (initially full) active set per iteration
             solve_bytes += (double)info[(size_t)q * 4] * 2.0 * probs[q].l * 4.0;
@@ -517,10 +520,14 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
         if (getenv("B200GS_SMO_PROF") && atoi(getenv("B200GS_SMO_PROF"))) {
             int qmax = 0;
             for (int q = 1; q < np; q++) if (info[(size_t)q * 4] > info[(size_t)qmax * 4]) qmax = q;
-            const unsigned long long *pn = &ns[(size_t)qmax * 8];
+            const unsigned long long *pn = &ns[(size_t)qmax * 12];
             const double it = (double)info[(size_t)qmax * 4];
-            fprintf(stderr, "[smo prof] longest problem: %d iters, %.1f ms; cycles/iter: scanA %.0f | bar1+redA %.0f | phaseB %.0f | bar2 %.0f | gatherJ+scalar %.0f | update %.0f\n",
-                    info[(size_t)qmax * 4], (double)(pn[1] - pn[0]) * 1e-6, pn[2] / it, pn[3] / it, pn[4] / it, pn[5] / it, pn[6] / it, pn[7] / it);
+            // single-CTA kernel slots: scanA | bar1+redA | rowI+phaseB | bar2 | fetchJ+scalar | update
+            // cluster kernel slots:    redA | xchg1 | rowI | phaseB | xchg2 | scalar | bar3 | rowJ | update
+            fprintf(stderr, "[smo prof] longest problem: %d iters, %.1f ms (%.2f us/iter); cycles/iter by slot:", info[(size_t)qmax * 4],
+                    (double)(pn[1] - pn[0]) * 1e-6, (double)(pn[1] - pn[0]) * 1e-3 / it);
+            for (int e = 0; e < 10; e++) fprintf(stderr, " %.0f", pn[2 + e] / it);
+            fprintf(stderr, "\n");
         }
         for (size_t v = 0; v < vtasks.size(); v++)
             for (int e = 0; e < 4; e++) all_counts[(size_t)vtask_id[v] * 4 + e] = counts[v * 4 + e];

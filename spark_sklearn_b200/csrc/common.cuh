@@ -90,7 +90,10 @@ cudaError_t launch_smo(const SmoProblem *d_probs, const int *d_order, int n_prob
 int smo_max_rows();   // largest sub-problem the resident-state kernel supports
 // smo_cluster.cu: the same solver with one sub-problem spread over a thread-block cluster of cl CTAs (DSMEM exchange)
 int smo_cluster_max_rows(int cl);
-cudaError_t launch_smo_cluster(const SmoProblem *d_probs, const int *d_order, int n_prob, int lmax, int cl, bool fast, cudaStream_t st);
+int smo_colown_max_rows(int cl);
+cudaError_t launch_smo_colown(const SmoProblem *d_probs, const int *d_order, int n_prob, int lmax, int cl, bool fast, cudaStream_t st);
+cudaError_t launch_smo_cluster(const SmoProblem *d_probs, const int *d_order, int n_prob, int lmax, int cl, bool fast, int rowcap,
+                               cudaStream_t st);
 
 // ---- score.cu ----
 // dec[c][r] = sum_j k64(r, j) * coef[c][j]  (float64 kernel values recomputed from S, not the

@@ -2,12 +2,22 @@
 //
 // Why: a search is bounded by its longest sub-problem (config 2: 68,716 dependent iterations), and one iteration of
 // the single-CTA kernel is issue-bound on the rows a CTA owns.  Here CL CTAs (CL SMs) each own 1/CL of the rows --
-// state in their own shared memory, K-row gathers from their own L1/L2 path -- and only the two arg-reductions of
-// working-set selection cross CTAs: every CTA reduces its rows, publishes one 48-byte record into every peer's
-// shared memory (DSMEM stores), and a cluster barrier makes the CL records visible; all CTAs then combine them
-// identically and redundantly run the scalar two-variable update.  Arithmetic, tie-breaking, shrinking schedule and
-// swap permutation are those of smo.cu (bit-identical results; see that file's header for the restatement of
-// libsvm svm.cpp:629-1168).
+// state in their own shared memory -- and only the two arg-reductions of working-set selection cross CTAs: every CTA
+// reduces its rows and publishes one 64-byte record into every peer's shared memory with st.async (DSMEM stores that
+// complete_tx on the RECEIVER's mbarrier); a CTA waits only on its own mbarrier, so the all-gather costs one DSMEM
+// latency instead of a cluster-wide barrier.  All CTAs then combine the CL records identically and redundantly run
+// the scalar two-variable update.  The two K rows of an iteration are brought into EVERY CTA's shared memory by
+// multicast bulk copies (cp.async.bulk ... .multicast::cluster): each CTA requests 1/CL of the row from L2/HBM and the
+// copy engine delivers it to all CL shared memories (block-cyclic ownership over shrunk positions means every CTA
+// needs columns from all over the row; per-thread gathers made every SM pull the whole row through its own L1 miss
+// path).  Arithmetic, tie-breaking, shrinking schedule and swap permutation are those of smo.cu (bit-identical
+// results; see that file's header for the restatement of libsvm svm.cpp:629-1168).
+//
+// Ordering argument for the barrier-free exchange (records double-buffered by parity, one row buffer): a CTA can
+// finish exchange n only after every peer SENT record n, and a peer sends record n only after all its warps passed the
+// CTA barrier that precedes the send -- i.e. after they finished reading exchange n-1's records and the row buffer
+// contents of the previous phase.  So a peer's record n+1 never overwrites a slot still being read (other parity), and a
+// multicast row write issued after exchange n never lands in a buffer a peer still gathers from.
 //
 // Row ownership is block-cyclic: position t lives in CTA (t / NT) % CL, local slot (t / (NT*CL)) * NT + t % NT, so the
 // active prefix [0, active) stays balanced over the CTAs as shrinking proceeds.
@@ -24,21 +34,45 @@ using namespace smo;
 constexpr int XW = 16;                       // words per exchange record
 
 template <int CL>
-struct Xch {                                 // double-buffered all-gather slots: [parity][source rank][word]
+struct __align__(16) Xch {                   // double-buffered all-gather slots: [parity][source rank][word]
     unsigned w[2][CL][XW];
 };
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned cta)
+{
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    unsigned done = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spin > (1u << 26)) __trap();                                    // a lost signal must not hang the GPU
+    }
+}
 
 __device__ __forceinline__ unsigned lo32(double x) { return (unsigned)__double_as_longlong(x); }
 __device__ __forceinline__ unsigned hi32(double x) { return (unsigned)((unsigned long long)__double_as_longlong(x) >> 32); }
 __device__ __forceinline__ double mk64(unsigned lo, unsigned hi) { return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo)); }
 
-template <int NT, int KPT, int CL, bool FAST>
+// ROWBUF: K rows by multicast bulk copy into shared memory (row length rowcap floats); otherwise per-thread gathers.
+template <int NT, int KPT, int CL, bool FAST, bool ROWBUF, bool PROF>
 __global__ void __launch_bounds__(NT, (NT >= 1024 ? 1 : (NT >= 512 ? 2 : 3)))
-smo_cluster_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order)
+smo_cluster_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, int rowcap, int fmode)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ Red red;
     __shared__ Xch<CL> xch;
+    __shared__ __align__(8) unsigned long long xbar[2];                      // one mbarrier per exchange parity
+    __shared__ __align__(8) unsigned long long rowbar;                       // row-buffer fill
     __shared__ int chunk_cnt[2][KPT * CL];                                   // shrink / rebuild chunk counts (all chunks)
     constexpr int NW = NT / 32;
     constexpr int LCAP = NT * KPT;                                          // rows owned by this CTA
@@ -53,6 +87,7 @@ smo_cluster_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__
     double *const alpha = mG + 2 * LCAP;
     unsigned short *const col = reinterpret_cast<unsigned short *>(mG + 3 * LCAP);
     unsigned char *const fl = reinterpret_cast<unsigned char *>(col + LCAP);
+    float *const rowbuf = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(fl + LCAP) + 127) & ~(uintptr_t)127);
     const float *__restrict__ const K = Pp->K;
     const int64_t ldk = Pp->ldk;
     const double eps = Pp->eps;
@@ -86,7 +121,23 @@ smo_cluster_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__
             }
         }
     }
-    cluster.sync();
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&xbar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&xbar[1])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&rowbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster.sync();                                                         // every CTA's barriers exist before any remote signal
+
+    long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = PROF ? clock64() : 0;
+    auto tick = [&](int slot) {
+        if constexpr (PROF) {
+            const long long now = clock64();
+            prof[slot] += now - tprev;
+            tprev = now;
+        }
+    };
 
     int active = l, iter = 0, timed_out = 0;
     int counter = (l < 1000 ? l : 1000) + 1;
@@ -108,16 +159,67 @@ smo_cluster_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__
     };
 
     // publish this CTA's record into every CTA of the cluster, then make all records visible
+    // (v must be warp-uniform in warp 0: it is built from REDUX results and broadcast shared-memory reads)
+    unsigned xphase = 0;                                                    // bit p: parity the next wait on xbar[p] uses
     auto exchange = [&](const unsigned (&v)[XW]) -> const unsigned (*)[XW] {
-        if (tid < CL) {
-            unsigned *dst = cluster.map_shared_rank(&xch.w[par][rank][0], tid);
-#pragma unroll
-            for (int w = 0; w < XW; w++) dst[w] = v[w];
+        const unsigned bar = smem_u32(&xbar[par]);
+        if (warp == 0) {
+            if (lane == 0) mbar_expect_tx(bar, CL * XW * 4);
+            if (lane < CL * 4) {                                             // lane -> (destination CTA, 16-byte chunk)
+                const int c = lane & 3;
+                const unsigned dst = (unsigned)lane >> 2;
+                const unsigned a0 = c == 0 ? v[0] : (c == 1 ? v[4] : (c == 2 ? v[8] : v[12]));
+                const unsigned a1 = c == 0 ? v[1] : (c == 1 ? v[5] : (c == 2 ? v[9] : v[13]));
+                const unsigned a2 = c == 0 ? v[2] : (c == 1 ? v[6] : (c == 2 ? v[10] : v[14]));
+                const unsigned a3 = c == 0 ? v[3] : (c == 1 ? v[7] : (c == 2 ? v[11] : v[15]));
+                const unsigned raddr = mapa_u32(smem_u32(&xch.w[par][rank][c * 4]), dst);
+                const unsigned rbar = mapa_u32(bar, dst);
+                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                             ::"r"(raddr), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(rbar) : "memory");
+            }
         }
-        cluster.sync();
+        mbar_wait(bar, (xphase >> par) & 1u);
+        xphase ^= 1u << par;
         const unsigned (*r)[XW] = xch.w[par];
         par ^= 1;
         return r;
+    };
+
+    // K row `r` (dataset row) into every CTA's row buffer: this CTA requests slice `rank`, multicast to all CL CTAs
+    unsigned rowphase = 0;
+    auto fetch_row = [&](int r) {
+        if constexpr (ROWBUF) {
+            const unsigned bar = smem_u32(&rowbar);
+            if (fmode == 1) {                                                // experiment: unicast, every CTA pulls the whole row
+                if (tid == 0) {
+                    mbar_expect_tx(bar, (unsigned)rowcap * 4u);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(smem_u32(rowbuf)), "l"(K + (size_t)r * ldk), "r"((unsigned)rowcap * 4u), "r"(bar) : "memory");
+                }
+            } else if (fmode == 2) {                                         // experiment: slice split over 4 copies
+                if (tid == 0) mbar_expect_tx(bar, (unsigned)rowcap * 4u);
+                if (tid < 4) {
+                    const unsigned slice = (unsigned)rowcap / CL, sub = slice / 4;
+                    const unsigned off = rank * slice + tid * sub;
+                    const unsigned short mask = (unsigned short)((1u << CL) - 1u);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                                 ::"r"(smem_u32(rowbuf + off)), "l"(K + (size_t)r * ldk + off), "r"(sub * 4u), "r"(bar), "h"(mask) : "memory");
+                }
+            } else if (tid == 0) {
+                mbar_expect_tx(bar, (unsigned)rowcap * 4u);                  // all CL slices land here
+                const unsigned slice = (unsigned)rowcap / CL;               // rowcap % 32 == 0: 16-byte multiples
+                const unsigned off = rank * slice;
+                const unsigned short mask = (unsigned short)((1u << CL) - 1u);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                             ::"r"(smem_u32(rowbuf + off)), "l"(K + (size_t)r * ldk + off), "r"(slice * 4u), "r"(bar), "h"(mask) : "memory");
+            }
+        }
+    };
+    auto wait_row = [&]() {
+        if constexpr (ROWBUF) {
+            mbar_wait(smem_u32(&rowbar), rowphase);
+            rowphase ^= 1u;
+        }
     };
 
     // ---------------- local scan (normally fused into the update loop) ----------------
@@ -225,7 +327,9 @@ smo_cluster_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__
                 const double ai = alpha[s];
                 rec[5] = lo32(ai); rec[6] = hi32(ai); rec[7] = (unsigned)col[s];
             }
+            tick(0);
             const unsigned (*r)[XW] = exchange(rec);
+            tick(1);
             int best = 0;
             unsigned long long kmax = ((unsigned long long)r[0][3] << 32) | r[0][4];
 #pragma unroll
@@ -248,10 +352,13 @@ smo_cluster_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__
         const float *__restrict__ Ki = K + (size_t)col_i * ldk;
         {
             float kv[KPT];
+            if constexpr (ROWBUF) { fetch_row(col_i); wait_row(); }
+            tick(2);
 #pragma unroll
             for (int k = 0; k < KPT; k++) {
                 const int t = gpos(k), s = k * NT + tid;
-                kv[k] = t < active ? __ldg(Ki + col[s]) : 0.f;
+                if constexpr (ROWBUF) kv[k] = t < active ? rowbuf[col[s]] : 0.f;
+                else kv[k] = t < active ? __ldg(Ki + col[s]) : 0.f;
             }
 #pragma unroll
             for (int k = 0; k < KPT; k++) qi[k] = widen(kv[k]);
@@ -316,7 +423,9 @@ smo_cluster_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__
                 rec[5] = lo32(a); rec[6] = hi32(a); rec[7] = lo32(bb); rec[8] = hi32(bb); rec[9] = lo32(c); rec[10] = hi32(c);
                 rec[11] = (unsigned)red.cnt[wj];
             }
+            tick(3);
             const unsigned (*r)[XW] = exchange(rec);
+            tick(4);
             int best = 0;
 #pragma unroll
             for (int c = 1; c < CL; c++)
@@ -332,6 +441,7 @@ smo_cluster_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__
         }
         if (top1k - top2k <= 514u) {
             // exact tie-break among the elements of the band (rare)
+            __syncthreads();                                 // slower warps may still be reading red.pl_* / red.cnt above
             const unsigned thrk = top1k > 514u ? top1k - 514u : 1u;
             double bestn = -CUDART_INF;
             int bidx = -1;
@@ -514,6 +624,7 @@ smo_cluster_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__
         if (--counter == 0) {
             counter = l < 1000 ? l : 1000;
             if (use_gbar) { do_shrink(); scan_valid = false; }
+            if constexpr (PROF) tprev = clock64();
         }
         if (!scan_valid) local_scan();
         if (select()) {
@@ -529,10 +640,13 @@ smo_cluster_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__
         const int i = pi >> IDX_SHIFT, j = pj >> IDX_SHIFT;
         const float *__restrict__ Kj = K + (size_t)col_j * ldk;
         float kvj[KPT];
+        if constexpr (ROWBUF) fetch_row(col_j);                  // every CTA is past exchange 2: row i is in registers everywhere
+        else {
 #pragma unroll
-        for (int k = 0; k < KPT; k++) {
-            const int t = gpos(k), s = k * NT + tid;
-            kvj[k] = t < active ? __ldg(Kj + col[s]) : 0.f;
+            for (int k = 0; k < KPT; k++) {
+                const int t = gpos(k), s = k * NT + tid;
+                kvj[k] = t < active ? __ldg(Kj + col[s]) : 0.f;
+            }
         }
         if (warp == 0) {                                         // every CTA runs the identical scalar update
             const double C = Pp->C;
@@ -572,7 +686,18 @@ smo_cluster_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__
                 red.bc_i[1] = aj >= C ? ST_UPPER : (aj <= 0 ? ST_LOWER : ST_FREE);
             }
         }
+        tick(5);
         __syncthreads();
+        tick(6);
+        if constexpr (ROWBUF) {
+            wait_row();
+            tick(7);
+#pragma unroll
+            for (int k = 0; k < KPT; k++) {
+                const int t = gpos(k), s = k * NT + tid;
+                kvj[k] = t < active ? rowbuf[col[s]] : 0.f;
+            }
+        }
         const double a = red.bc_d[0], b = red.bc_d[1];
         const int sti = red.bc_i[0], stj = red.bc_i[1];
         if (owner_of(i) == rank && tid == i % NT) { const int s = slot_of(i); alpha[s] = red.bc_d[2]; fl[s] = (unsigned char)mkflags((pi & F_YPOS) != 0, sti); }
@@ -610,6 +735,7 @@ smo_cluster_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__
                 }
             }
         }
+        tick(8);
     }
 
     // ---------------- calculate_rho: sequential float64 sum in libsvm's (position) order, via DSMEM ----------------
@@ -672,17 +798,19 @@ smo_cluster_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
             unsigned long long *ns = Pp->out_ns;
             ns[0] = t_start; ns[1] = t_end;
+            if constexpr (PROF)
+                for (int q = 0; q < 10; q++) ns[2 + q] = (unsigned long long)prof[q];
         }
     }
     cluster.sync();                                              // no CTA may exit while a peer still reads its shared memory
 }
 
-template <int NT, int KPT, int CL, bool FAST>
-cudaError_t launch_cluster(const SmoProblem *probs, const int *order, int n_prob, cudaStream_t st)
+template <int NT, int KPT, int CL, bool FAST, bool ROWBUF, bool PROF>
+cudaError_t launch_cluster(const SmoProblem *probs, const int *order, int n_prob, int rowcap, cudaStream_t st)
 {
     constexpr int LCAP = NT * KPT;
-    const size_t smem = (size_t)LCAP * (8 + 8 + 8 + 2 + 1);
-    auto kern = smo_cluster_kernel<NT, KPT, CL, FAST>;
+    const size_t smem = (size_t)LCAP * (8 + 8 + 8 + 2 + 1) + (ROWBUF ? 128 + (size_t)rowcap * 4 : 0);
+    auto kern = smo_cluster_kernel<NT, KPT, CL, FAST, ROWBUF, PROF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
@@ -694,7 +822,15 @@ cudaError_t launch_cluster(const SmoProblem *probs, const int *order, int n_prob
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, probs, order);
+    int fmode = 0;
+    if (const char *e = getenv("B200GS_SMO_FMODE")) fmode = atoi(e);           // development switch
+    return cudaLaunchKernelEx(&cfg, kern, probs, order, rowcap, fmode);
+}
+
+int env_int_c(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
 }
 
 }  // namespace
@@ -703,33 +839,44 @@ cudaError_t launch_cluster(const SmoProblem *probs, const int *order, int n_prob
 int smo_cluster_max_rows(int cl) { return cl == 2 ? 8192 : ((cl == 4 || cl == 8) ? 16384 : 0); }
 
 template <int NT, int KPT, int CL>
-static cudaError_t launch_cluster_f(const SmoProblem *p, const int *o, int n, bool fast, cudaStream_t st)
+static cudaError_t launch_cluster_f(const SmoProblem *p, const int *o, int n, bool fast, int rowcap, cudaStream_t st)
 {
-    return fast ? launch_cluster<NT, KPT, CL, true>(p, o, n, st) : launch_cluster<NT, KPT, CL, false>(p, o, n, st);
+    // the row buffer shares the 227 KB of shared memory with the state (27 B per owned row) and ~3 KB of static scratch
+    const bool fits = rowcap > 0 && rowcap % 32 == 0 &&
+                      (size_t)NT * KPT * 27 + 128 + (size_t)rowcap * 4 + 4096 <= 227 * 1024;
+    const bool rowbuf = fits && env_int_c("B200GS_SMO_ROWBUF", 1);
+    const bool prof = env_int_c("B200GS_SMO_PROF", 0) != 0;
+    if (prof && rowbuf) return fast ? launch_cluster<NT, KPT, CL, true, true, true>(p, o, n, rowcap, st)
+                                    : launch_cluster<NT, KPT, CL, false, true, true>(p, o, n, rowcap, st);
+    if (rowbuf) return fast ? launch_cluster<NT, KPT, CL, true, true, false>(p, o, n, rowcap, st)
+                            : launch_cluster<NT, KPT, CL, false, true, false>(p, o, n, rowcap, st);
+    return fast ? launch_cluster<NT, KPT, CL, true, false, false>(p, o, n, 0, st)
+                : launch_cluster<NT, KPT, CL, false, false, false>(p, o, n, 0, st);
 }
 
-// Shape = (threads per CTA) x (rows per thread) x (CTAs per problem).  Smaller CTAs let several sub-problems share an
-// SM (their latencies overlap) while each problem's dependent chain runs on cl SMs at once.
-cudaError_t launch_smo_cluster(const SmoProblem *d_probs, const int *d_order, int n_prob, int lmax, int cl, bool fast, cudaStream_t st)
+// Shape = (threads per CTA) x (rows per thread) x (CTAs per problem).
+cudaError_t launch_smo_cluster(const SmoProblem *d_probs, const int *d_order, int n_prob, int lmax, int cl, bool fast, int rowcap,
+                               cudaStream_t st)
 {
     if (n_prob <= 0) return cudaSuccess;
     if (lmax > smo_cluster_max_rows(cl)) return cudaErrorInvalidValue;
     int nt = 0;
     if (const char *e = getenv("B200GS_SMO_NT")) nt = atoi(e);                  // development switch
     if (cl == 2) {
-        if (nt == 512) return launch_cluster_f<512, 8, 2>(d_probs, d_order, n_prob, fast, st);
-        return launch_cluster_f<1024, 4, 2>(d_probs, d_order, n_prob, fast, st);
+        if (nt == 512) return launch_cluster_f<512, 8, 2>(d_probs, d_order, n_prob, fast, rowcap, st);
+        return launch_cluster_f<1024, 4, 2>(d_probs, d_order, n_prob, fast, rowcap, st);
     }
     if (cl == 4) {
-        if (lmax > 8192) return launch_cluster_f<1024, 4, 4>(d_probs, d_order, n_prob, fast, st);
-        if (nt == 256) return launch_cluster_f<256, 8, 4>(d_probs, d_order, n_prob, fast, st);
-        if (nt == 512) return launch_cluster_f<512, 4, 4>(d_probs, d_order, n_prob, fast, st);
-        return launch_cluster_f<1024, 2, 4>(d_probs, d_order, n_prob, fast, st);      // one SM per CTA: co-exists with the single-CTA kernel
+        if (lmax > 8192) return launch_cluster_f<1024, 4, 4>(d_probs, d_order, n_prob, fast, rowcap, st);
+        if (nt == 256) return launch_cluster_f<256, 8, 4>(d_probs, d_order, n_prob, fast, rowcap, st);
+        if (nt == 512) return launch_cluster_f<512, 4, 4>(d_probs, d_order, n_prob, fast, rowcap, st);
+        return launch_cluster_f<1024, 2, 4>(d_probs, d_order, n_prob, fast, rowcap, st);      // one SM per CTA: co-exists with the single-CTA kernel
     }
     if (cl == 8) {
-        if (lmax > 8192) return launch_cluster_f<512, 4, 8>(d_probs, d_order, n_prob, fast, st);
-        if (nt == 128) return launch_cluster_f<128, 8, 8>(d_probs, d_order, n_prob, fast, st);
-        return launch_cluster_f<256, 4, 8>(d_probs, d_order, n_prob, fast, st);
+        if (lmax > 8192) return launch_cluster_f<512, 4, 8>(d_probs, d_order, n_prob, fast, rowcap, st);
+        if (nt == 128) return launch_cluster_f<128, 8, 8>(d_probs, d_order, n_prob, fast, rowcap, st);
+        if (nt == 1024) return launch_cluster_f<1024, 1, 8>(d_probs, d_order, n_prob, fast, rowcap, st);
+        return launch_cluster_f<256, 4, 8>(d_probs, d_order, n_prob, fast, rowcap, st);
     }
     return cudaErrorInvalidValue;
 }
