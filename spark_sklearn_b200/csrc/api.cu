@@ -96,6 +96,9 @@ int gs_create(int device, gs_handle **out)
     {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if ((e = cudaStreamCreateWithPriority(&h->stream_mid, cudaStreamNonBlocking, hi)) != cudaSuccess) {
+            g_create_error = cudaGetErrorString(e); cudaStreamDestroy(h->stream); delete h; return GS_ERR_CUDA;
+        }
         if ((e = cudaStreamCreateWithPriority(&h->stream_hi, cudaStreamNonBlocking, hi)) != cudaSuccess) {
             g_create_error = cudaGetErrorString(e); cudaStreamDestroy(h->stream); delete h; return GS_ERR_CUDA;
         }
@@ -114,6 +117,7 @@ void gs_destroy(gs_handle *h)
     for (auto &w : h->dWork) w.release();
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream_hi) cudaStreamDestroy(h->stream_hi);
+    if (h->stream_mid) cudaStreamDestroy(h->stream_mid);
     delete h;
 }
 
@@ -436,41 +440,59 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
         // the cluster kernel (one problem over `cl` SMs, high-priority stream, launched first); the rest by the
         // single-CTA kernel.  Development switches: B200GS_SMO_CLUSTER (0/2/4), B200GS_SMO_CLUSTER_PCT.
         std::string why;
-        // Policy (measured on config 2, profiles/): a cluster CTA set cuts the per-iteration latency of one problem
-        // (7.1 us on one SM -> 5.7 us on 4 SMs -> 4.7 us on 8 SMs) but not the SM-time per iteration, so clusters go to
-        // the problems that bound the makespan: everything when there are fewer problems than SMs to fill, else the
-        // predicted-longest 6 %.
-        int cl = 0, pct = 0;
+        // Policy (measured on config 2, profiles/): a cluster cuts the per-iteration LATENCY of one problem (6.6 us on one
+        // SM, 5.4 us on 2 SMs, 4.2 us on 4, 4.1 us on 8) but costs more SM-time per iteration, so clusters go to the
+        // problems that bound the makespan.  With fewer problems than SMs everything runs on the widest cluster that
+        // fits; otherwise the predicted-longest `pct4` % run on 4-CTA clusters, the next `pct2` % on 2-CTA clusters
+        // (launched first, on high-priority streams) and the rest on the single-CTA kernel.
+        // Development switches: B200GS_SMO_CLUSTER (0/2/4/8), B200GS_SMO_CLUSTER_PCT, B200GS_SMO_CL2_PCT, B200GS_SMO_CO.
+        int cl = 0, pct = 0, pct2 = 0;
         if (lmax > 2048) {
             if (np * 8 <= h->sm_count) { cl = 8; pct = 100; }
             else if (np * 4 <= h->sm_count) { cl = 4; pct = 100; }
             else if (np * 2 <= h->sm_count) { cl = 2; pct = 100; }
-            else { cl = 4; pct = 6; }
+            else { cl = 4; pct = 6; pct2 = 0; }
         }
         if (const char *e = getenv("B200GS_SMO_CLUSTER")) cl = atoi(e);
         if (const char *e = getenv("B200GS_SMO_CLUSTER_PCT")) pct = atoi(e);
-        int n_cl = 0;
+        if (const char *e = getenv("B200GS_SMO_CL2_PCT")) pct2 = atoi(e);
+        const char *co_env = getenv("B200GS_SMO_CO");
+        const bool colown = !(co_env && atoi(co_env) == 0);                 // 0 = position-owned cluster kernel (smo_cluster.cu)
+        int n_cl = 0, n_cl2 = 0;
         if ((cl == 2 || cl == 4 || cl == 8) && lmax <= smo_cluster_max_rows(cl) && lmax > 2048)
-            n_cl = std::max(pct > 0 ? 1 : 0, (int)((int64_t)np * pct / 100));
+            n_cl = std::min(np, std::max(pct > 0 ? 1 : 0, (int)((int64_t)np * pct / 100)));
+        if (n_cl > 0 && cl != 2 && pct2 > 0 && lmax <= smo_cluster_max_rows(2))
+            n_cl2 = std::min(np - n_cl, (int)((int64_t)np * pct2 / 100));
+        auto launch_tier = [&](int first, int count, int width, cudaStream_t s) -> cudaError_t {
+            return colown ? launch_smo_colown(d_probs, d_order + first, count, lmax, width, fast, s)
+                          : launch_smo_cluster(d_probs, d_order + first, count, lmax, width, fast, (int)ldk, s);
+        };
         if (n_cl > 0) {
-            cudaEvent_t ready, done;
+            cudaEvent_t ready, done, done2;
             cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
             cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&done2, cudaEventDisableTiming);
             cudaEventRecord(ready, st);
             cudaStreamWaitEvent(h->stream_hi, ready, 0);
-            const char *co = getenv("B200GS_SMO_CO");                           // development switch: 0 = position-owned cluster kernel
-            cudaError_t ce = (co && atoi(co) == 0) ? launch_smo_cluster(d_probs, d_order, n_cl, lmax, cl, fast, (int)ldk, h->stream_hi)
-                                                   : launch_smo_colown(d_probs, d_order, n_cl, lmax, cl, fast, h->stream_hi);
+            cudaError_t ce = launch_tier(0, n_cl, cl, h->stream_hi);
             if (ce != cudaSuccess) { gs_set_error(h, std::string("launch_smo_cluster: ") + cudaGetErrorString(ce)); return GS_ERR_CUDA; }
             cudaEventRecord(done, h->stream_hi);
             pf.launches++;
-            if (np - n_cl > 0) {
-                ce = launch_smo(d_probs, d_order + n_cl, np - n_cl, lmax, fast, (int)ldk, st, &why);
+            if (n_cl2 > 0) {
+                cudaStreamWaitEvent(h->stream_mid, ready, 0);
+                ce = launch_tier(n_cl, n_cl2, 2, h->stream_mid);
+                if (ce != cudaSuccess) { gs_set_error(h, std::string("launch_smo_cluster (2): ") + cudaGetErrorString(ce)); return GS_ERR_CUDA; }
+                cudaEventRecord(done2, h->stream_mid);
+                pf.launches++;
+            }
+            if (np - n_cl - n_cl2 > 0) {
+                ce = launch_smo(d_probs, d_order + n_cl + n_cl2, np - n_cl - n_cl2, lmax, fast, (int)ldk, st, &why);
                 if (ce != cudaSuccess) { gs_set_error(h, why.empty() ? std::string("launch_smo: ") + cudaGetErrorString(ce) : why); return why.empty() ? GS_ERR_CUDA : GS_ERR_UNSUPPORTED; }
                 pf.launches++;
             }
             cudaStreamWaitEvent(st, done, 0);
-            cudaEventDestroy(ready); cudaEventDestroy(done);
+            if (n_cl2 > 0) cudaStreamWaitEvent(st, done2, 0);
+            cudaEventDestroy(ready); cudaEventDestroy(done); cudaEventDestroy(done2);
         } else {
             cudaError_t ce = launch_smo(d_probs, d_order, np, lmax, fast, (int)ldk, st, &why);
             if (ce != cudaSuccess) { gs_set_error(h, why.empty() ? std::string("launch_smo: ") + cudaGetErrorString(ce) : why); return why.empty() ? GS_ERR_CUDA : GS_ERR_UNSUPPORTED; }

@@ -38,6 +38,7 @@ struct gs_handle {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t stream_hi = nullptr;   // high priority: cluster SMO launches (the critical-path problems)
+    cudaStream_t stream_mid = nullptr;  // high priority: second tier of cluster SMO launches
     std::string err;
     // dataset (rows stored in INTERNAL order: sorted by class, then by original index)
     int64_t n = 0, d = 0;

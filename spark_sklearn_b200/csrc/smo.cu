@@ -23,9 +23,9 @@
 //
 // Throughput design (B200: 64 FP64 lanes/SM, 4 issue slots/clk/SM -- this kernel is FP64-pipe and
 // issue bound, then latency bound):
-//   * the exact float64 division of WSS2 is evaluated only for elements that survive a 20-bit
-//     reciprocal filter (rcp.approx.ftz.f64) with a provably safe band; the winner is still chosen
-//     from exactly-rounded libsvm values, so the selection is bit-identical;
+//   * the exact float64 division of WSS2 is evaluated only for elements that survive an approximate
+//     filter (float32 arithmetic for rbf, a 20-bit reciprocal otherwise) with a provably safe band; the
+//     winner is still chosen from exactly-rounded libsvm values, so the selection is bit-identical;
 //   * float32->float64 widening of the K entries uses integer bit operations (ALU pipe) instead of
 //     F2F (quarter-rate on the FP64 pipe);
 //   * block arg-reductions run on REDUX.MAX over order-preserving 64-bit integer keys, not on
@@ -111,12 +111,15 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
     // bulk fetch of dataset row `r` of K into rowbuf (issued by one thread) and the matching wait (all threads)
     auto fetch_row = [&](int r) {
         if constexpr (ROWBUF) {
-            if (tid == 0) {
-                const unsigned bar = (unsigned)__cvta_generic_to_shared(&rowbar);
-                const unsigned bytes = (unsigned)rowcap * 4u;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            // four quarter-row copies in flight at once: 1.7k cycles from HBM instead of 2.05k for one 40 KB copy (measured)
+            const unsigned bar = (unsigned)__cvta_generic_to_shared(&rowbar);
+            const unsigned part = ((unsigned)rowcap / 4u) & ~3u;            // floats per part, 16-byte multiple
+            if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)rowcap * 4u) : "memory");
+            if (tid < 4) {
+                const unsigned off = (unsigned)tid * part;
+                const unsigned cnt = tid == 3 ? (unsigned)rowcap - 3u * part : part;
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"((unsigned)__cvta_generic_to_shared(rowbuf)), "l"(K + (size_t)r * ldk), "r"(bytes), "r"(bar) : "memory");
+                             ::"r"((unsigned)__cvta_generic_to_shared(rowbuf + off)), "l"(K + (size_t)r * ldk + off), "r"(cnt * 4u), "r"(bar) : "memory");
             }
         }
     };
@@ -148,7 +151,7 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
         }
     };
 
-    double qi[KPT];      // unsigned K_i row (widened) at the owned active positions t = k*NT + tid
+    float kvi[KPT];      // unsigned K_i row (float32 as stored) at the owned active positions t = k*NT + tid; widened on use
 
     auto QD = [&](int t) -> double {                                        // svm.cpp:1436-1437
         if constexpr (FAST) return 1.0;
@@ -255,20 +258,40 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
         const double QDi = QD(i);
         const float *__restrict__ Ki = K + (size_t)col[i] * ldk;
         {
-            float kv[KPT];
             if constexpr (ROWBUF) { fetch_row(col[i]); wait_row(); }
 #pragma unroll
             for (int k = 0; k < KPT; k++) {                                  // issue the whole gather first
                 const int t = k * NT + tid;
-                if constexpr (ROWBUF) kv[k] = t < active ? rowbuf[col[t]] : 0.f;
-                else kv[k] = t < active ? __ldg(Ki + col[t]) : 0.f;
+                if constexpr (ROWBUF) kvi[k] = t < active ? rowbuf[col[t]] : 0.f;
+                else kvi[k] = t < active ? __ldg(Ki + col[t]) : 0.f;
             }
-#pragma unroll
-            for (int k = 0; k < KPT; k++) qi[k] = widen(kv[k]);
         }
-        // Approximate gd^2/quad is tracked by the HIGH WORD of the (non-negative) double only: 32-bit compares and
-        // moves instead of 64-bit ones.  High words order like the doubles to 2^-20; the band test below (514 units
-        // >= 2^-12 relative) sends every near-tie to the exact libsvm quotients, so the choice stays bit-identical.
+        // Approximate gd^2/quad is tracked by a 32-bit order-preserving key; every near-tie (keys within BAND units) is
+        // decided by the exact libsvm quotients below, so the choice stays bit-identical.
+        //   FAST (rbf, 0 < K normal): the key is the bit pattern of a FLOAT32 evaluation (gd rounded to float, quad =
+        //     2 - 2K exact-then-rounded, rcp.approx.f32, two products): relative error < 7 * 2^-24 < 2^-21 per candidate,
+        //     one key unit >= 2^-24 relative, BAND = 64 units = 2^-18 > 2 * 2^-21.  Three FP64-pipe instructions per
+        //     element instead of ten.  Below 2^-100 (flush-to-zero territory) every candidate goes to the exact path.
+        //   otherwise: the HIGH WORD of a double evaluation with rcp.approx.f64 (2^-20-accurate), BAND = 514 units >= 2^-12.
+        constexpr unsigned BAND = FAST ? 64u : 514u;
+        constexpr unsigned KEY_TINY = 0x0D800000u;                          // float bits of 2^-100
+        auto approx_key = [&](double gd, float kvf, int t) -> unsigned {
+            if constexpr (FAST) {
+                const float gdf = __double2float_rn(gd);
+                const float quadf = __fmaf_rn(-2.f, kvf, 2.f);              // == fl32(2 - 2K): 2K is exact
+                const float g2f = __fmul_rn(gdf, gdf);
+                float r;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(quadf));
+                const float apf = quadf > 0.f ? __fmul_rn(g2f, r) : __fmul_rn(g2f, 1e12f);
+                return __float_as_uint(apf) + 1u;                           // +1: a valid candidate is never 0
+            } else {
+                const double q = widen(kvf);
+                const double quad = __dsub_rn(__dadd_rn(QDi, QD(t)), __dmul_rn(2.0, q));
+                const double g2 = __dmul_rn(gd, gd);
+                const double ap = quad > 0 ? g2 * rcp_approx(quad) : g2 * 1e12;
+                return (unsigned)__double2hiint(ap) + 1u;
+            }
+        };
         unsigned b1k = 0u, b2k = 0u;                    // keys of the best and second-best candidate (0 = none)
         int k1 = -1;
         double m1 = 0, q1 = 0;
@@ -281,11 +304,7 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
                 const double m = mG[t];
                 const double gd = __dsub_rn(gmax, m);
                 if ((f & F_LOW) && gd > 0) {
-                    const double quad = FAST ? __dsub_rn(2.0, __dadd_rn(qi[k], qi[k]))
-                                             : __dsub_rn(__dadd_rn(QDi, QD(t)), __dmul_rn(2.0, qi[k]));
-                    const double g2 = __dmul_rn(gd, gd);
-                    const double ap = quad > 0 ? g2 * rcp_approx(quad) : g2 * 1e12;
-                    const unsigned key = (unsigned)__double2hiint(ap) + 1u;      // +1: a valid candidate is never 0
+                    const unsigned key = approx_key(gd, kvi[k], t);
                     const bool gt = key > b1k;
                     b2k = gt ? b1k : max(b2k, key);
                     b1k = gt ? key : b1k;
@@ -297,8 +316,10 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
             const int t1 = k1 * NT + tid, s1 = t1;
             idx1 = (t1 << IDX_SHIFT) | fl[s1];
             m1 = mG[s1];
+            float kq = kvi[0];
 #pragma unroll
-            for (int k = 0; k < KPT; k++) q1 = k == k1 ? qi[k] : q1;
+            for (int k = 1; k < KPT; k++) kq = k == k1 ? kvi[k] : kq;
+            q1 = widen(kq);
         }
         unsigned top1k, top2k;
         {
@@ -320,9 +341,9 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
             top2k = __reduce_max_sync(0xffffffffu, (v && bi == pj) ? red.t_hi[lane] : bk);
             if (pj < 0) return true;                                               // Gmin_idx == -1
         }
-        if (top1k - top2k <= 514u) {
+        if (top1k - top2k <= BAND || (FAST && top1k <= KEY_TINY)) {
             // ---- exact tie-break: libsvm's correctly rounded quotients for every element in the band ----
-            const unsigned thrk = top1k > 514u ? top1k - 514u : 1u;
+            const unsigned thrk = (top1k > BAND && !(FAST && top1k <= KEY_TINY)) ? top1k - BAND : 1u;
             double bestn = -CUDART_INF;
             int bidx = -1;
 #pragma unroll
@@ -333,12 +354,12 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
                     const double m = mG[t];
                     const double gd = __dsub_rn(gmax, m);
                     if ((f & F_LOW) && gd > 0) {
-                        const double quad = __dsub_rn(__dadd_rn(QDi, QD(t)), __dmul_rn(2.0, qi[k]));
-                        const double g2 = __dmul_rn(gd, gd);
-                        const double ap = quad > 0 ? g2 * rcp_approx(quad) : g2 * 1e12;
-                        if ((unsigned)__double2hiint(ap) + 1u >= thrk) {
+                        if (approx_key(gd, kvi[k], t) >= thrk) {
+                            const double q = widen(kvi[k]);
+                            const double quad = __dsub_rn(__dadd_rn(QDi, QD(t)), __dmul_rn(2.0, q));
+                            const double g2 = __dmul_rn(gd, gd);
                             const double nod = quad > 0 ? __ddiv_rn(g2, quad) : __ddiv_rn(g2, TAU);   // == -obj_diff
-                            if (nod >= bestn) { bestn = nod; bidx = (t << IDX_SHIFT) | f; m1 = m; q1 = qi[k]; }
+                            if (nod >= bestn) { bestn = nod; bidx = (t << IDX_SHIFT) | f; m1 = m; q1 = q; }
                         }
                     }
                 }
@@ -529,7 +550,7 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
         for (int k = 0; k < KPT; k++) {
             const int t = k * NT + tid;
             if (t < active) {
-                const double m = __dadd_rn(mG[t], __dadd_rn(__dmul_rn(qi[k], a), __dmul_rn(widen(kvj[k]), b)));
+                const double m = __dadd_rn(mG[t], __dadd_rn(__dmul_rn(widen(kvi[k]), a), __dmul_rn(widen(kvj[k]), b)));
                 mG[t] = m;
                 const int f = fl[t];
                 if ((f & F_UP) && m >= la) { la = m; la_idx = (t << IDX_SHIFT) | f; }
@@ -552,7 +573,7 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
                 if (t < l) {
                     const bool act = t < active;
                     double gb = mGbar[t];
-                    if (need_i) gb = __dadd_rn(gb, __dmul_rn(ci, act ? qi[k] : widen(__ldg(Ki + col[t]))));
+                    if (need_i) gb = __dadd_rn(gb, __dmul_rn(ci, widen(act ? kvi[k] : __ldg(Ki + col[t]))));
                     if (need_j) gb = __dadd_rn(gb, __dmul_rn(cj, widen(act ? kvj[k] : __ldg(Kj + col[t]))));
                     mGbar[t] = gb;
                 }

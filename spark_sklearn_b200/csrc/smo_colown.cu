@@ -76,7 +76,7 @@ struct RedCo {          // payload of each warp's winner (phase A and phase B)
 };
 
 template <int NT, int KPT, int CL, bool FAST, bool PROF>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, (NT <= 256 ? 3 : 1))
 smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -154,7 +154,7 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
     int par = 0;                                                            // exchange parity
     unsigned xphase = 0;                                                    // bit p: parity the next wait on xbar[p] uses
 
-    double qi[KPT];                                                         // unsigned K_i at the owned elements (widened)
+    float kvi[KPT];                                                         // unsigned K_i at the owned elements (float32 as stored)
 
     auto QDc = [&](int c) -> double {                                       // by dataset row (svm.cpp:1436-1437)
         if constexpr (FAST) return 1.0;
@@ -312,16 +312,29 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
         // ---- phase B: j = argmin -(gd^2)/quad over I_low with gd > 0 (svm.cpp:980-1037) ----
         const double QDi = QDc(col_i);
         const float *__restrict__ Ki = K + (size_t)col_i * ldk;
-        {
-            float kv[KPT];
 #pragma unroll
-            for (int k = 0; k < KPT; k++) kv[k] = pos[k] < active ? __ldg(Ki + colr[k]) : 0.f;    // coalesced: fixed columns
-#pragma unroll
-            for (int k = 0; k < KPT; k++) qi[k] = widen(kv[k]);
-        }
+        for (int k = 0; k < KPT; k++) kvi[k] = pos[k] < active ? __ldg(Ki + colr[k]) : 0.f;    // coalesced: fixed columns
         tick(2);
-        // Approximate gd^2/quad tracked by the HIGH WORD of the (non-negative) double; every near-tie (band of 514 key
-        // units >= 2^-12 relative) is decided by the exact libsvm quotients below, so the choice stays bit-identical.
+        // Approximate gd^2/quad tracked by a 32-bit order-preserving key; every near-tie (keys within BAND units) is decided
+        // by the exact libsvm quotients below, so the choice stays bit-identical (error analysis: smo.cu, same filter).
+        constexpr unsigned BAND = FAST ? 64u : 514u;
+        constexpr unsigned KEY_TINY = 0x0D800000u;                          // float bits of 2^-100
+        auto approx_key = [&](double gd, float kvf, int c) -> unsigned {
+            if constexpr (FAST) {
+                const float gdf = __double2float_rn(gd);
+                const float quadf = __fmaf_rn(-2.f, kvf, 2.f);              // == fl32(2 - 2K): 2K is exact
+                const float g2f = __fmul_rn(gdf, gdf);
+                float r;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(quadf));
+                const float apf = quadf > 0.f ? __fmul_rn(g2f, r) : __fmul_rn(g2f, 1e12f);
+                return __float_as_uint(apf) + 1u;                           // +1: a valid candidate is never 0
+            } else {
+                const double quad = __dsub_rn(__dadd_rn(QDi, QDc(c)), __dmul_rn(2.0, widen(kvf)));
+                const double g2 = __dmul_rn(gd, gd);
+                const double ap = quad > 0 ? g2 * rcp_approx(quad) : g2 * 1e12;
+                return (unsigned)__double2hiint(ap) + 1u;
+            }
+        };
         unsigned b1k = 0u, b2k = 0u;                    // keys of the best and second-best candidate (0 = none)
         int k1 = -1;
 #pragma unroll
@@ -330,11 +343,7 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
                 const int f = fl[k];
                 const double gd = __dsub_rn(gmax, m[k]);
                 if ((f & F_LOW) && gd > 0) {
-                    const double quad = FAST ? __dsub_rn(2.0, __dadd_rn(qi[k], qi[k]))
-                                             : __dsub_rn(__dadd_rn(QDi, QDc(colr[k])), __dmul_rn(2.0, qi[k]));
-                    const double g2 = __dmul_rn(gd, gd);
-                    const double ap = quad > 0 ? g2 * rcp_approx(quad) : g2 * 1e12;
-                    const unsigned key = (unsigned)__double2hiint(ap) + 1u;      // +1: a valid candidate is never 0
+                    const unsigned key = approx_key(gd, kvi[k], colr[k]);
                     const bool gt = key > b1k;
                     b2k = gt ? b1k : max(b2k, key);
                     b1k = gt ? key : b1k;
@@ -346,12 +355,14 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
         int idx1 = -1, c1c = 0;
         if (k1 >= 0) {
             int p1 = pos[0], f1 = fl[0];
-            m1 = m[0]; q1 = qi[0]; c1c = colr[0];
+            float kq = kvi[0];
+            m1 = m[0]; c1c = colr[0];
 #pragma unroll
             for (int k = 1; k < KPT; k++) {
                 const bool s = k == k1;
-                p1 = s ? pos[k] : p1; f1 = s ? fl[k] : f1; m1 = s ? m[k] : m1; q1 = s ? qi[k] : q1; c1c = s ? colr[k] : c1c;
+                p1 = s ? pos[k] : p1; f1 = s ? fl[k] : f1; m1 = s ? m[k] : m1; kq = s ? kvi[k] : kq; c1c = s ? colr[k] : c1c;
             }
+            q1 = widen(kq);
             idx1 = (p1 << IDX_SHIFT) | f1;
         }
         unsigned top1k, top2k;
@@ -394,10 +405,10 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
             mg_j = mk64(r[best][5], r[best][6]); k_ij = mk64(r[best][7], r[best][8]); alpha_j = mk64(r[best][9], r[best][10]);
             col_j = (int)r[best][11];
         }
-        if (top1k - top2k <= 514u) {
+        if (top1k - top2k <= BAND || (FAST && top1k <= KEY_TINY)) {
             // ---- exact tie-break: libsvm's correctly rounded quotients for every element in the band (rare) ----
             __syncthreads();                                 // slower warps may still be reading rc.b_* above
-            const unsigned thrk = top1k > 514u ? top1k - 514u : 1u;
+            const unsigned thrk = (top1k > BAND && !(FAST && top1k <= KEY_TINY)) ? top1k - BAND : 1u;
             double bestn = -CUDART_INF;
             int bidx = -1, bk_ = 0;
 #pragma unroll
@@ -406,10 +417,9 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
                     const int f = fl[k];
                     const double gd = __dsub_rn(gmax, m[k]);
                     if ((f & F_LOW) && gd > 0) {
-                        const double quad = __dsub_rn(__dadd_rn(QDi, QDc(colr[k])), __dmul_rn(2.0, qi[k]));
-                        const double g2 = __dmul_rn(gd, gd);
-                        const double ap = quad > 0 ? g2 * rcp_approx(quad) : g2 * 1e12;
-                        if ((unsigned)__double2hiint(ap) + 1u >= thrk) {
+                        if (approx_key(gd, kvi[k], colr[k]) >= thrk) {
+                            const double quad = __dsub_rn(__dadd_rn(QDi, QDc(colr[k])), __dmul_rn(2.0, widen(kvi[k])));
+                            const double g2 = __dmul_rn(gd, gd);
                             const double nod = quad > 0 ? __ddiv_rn(g2, quad) : __ddiv_rn(g2, TAU);   // == -obj_diff
                             const int cand = (pos[k] << IDX_SHIFT) | f;
                             if (nod > bestn || (nod == bestn && cand > bidx)) { bestn = nod; bidx = cand; bk_ = k; }
@@ -420,11 +430,12 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
             const unsigned long long key = dkey(bestn);
             const KArg w = warp_argmax((unsigned)(key >> 32), (unsigned)key, bidx);
             if (bidx >= 0 && bidx == w.idx) {
-                double mm = m[0], qq = qi[0];
+                double mm = m[0];
+                float qq = kvi[0];
                 int cc = colr[0];
 #pragma unroll
-                for (int k = 1; k < KPT; k++) { const bool s = k == bk_; mm = s ? m[k] : mm; qq = s ? qi[k] : qq; cc = s ? colr[k] : cc; }
-                rc.b_mg[warp] = mm; rc.b_kv[warp] = qq; rc.b_alpha[warp] = alpha[bk_ * NT + tid]; rc.b_col[warp] = cc;
+                for (int k = 1; k < KPT; k++) { const bool s = k == bk_; mm = s ? m[k] : mm; qq = s ? kvi[k] : qq; cc = s ? colr[k] : cc; }
+                rc.b_mg[warp] = mm; rc.b_kv[warp] = widen(qq); rc.b_alpha[warp] = alpha[bk_ * NT + tid]; rc.b_col[warp] = cc;
             }
             if (lane == 0) { red.x_hi[warp] = w.hi; red.x_lo[warp] = w.lo; red.x_idx[warp] = w.idx; }
             __syncthreads();
@@ -632,7 +643,7 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
 #pragma unroll
         for (int k = 0; k < KPT; k++) {
             if (pos[k] < active) {
-                m[k] = __dadd_rn(m[k], __dadd_rn(__dmul_rn(qi[k], a), __dmul_rn(widen(kvj[k]), b)));
+                m[k] = __dadd_rn(m[k], __dadd_rn(__dmul_rn(widen(kvi[k]), a), __dmul_rn(widen(kvj[k]), b)));
                 scan_elem(k);
             }
         }
@@ -651,7 +662,7 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
                 if (pos[k] != NOPOS) {
                     const bool act = pos[k] < active;
                     double gb = mGbar[k * NT + tid];
-                    if (need_i) gb = __dadd_rn(gb, __dmul_rn(ci, act ? qi[k] : widen(__ldg(Ki + colr[k]))));
+                    if (need_i) gb = __dadd_rn(gb, __dmul_rn(ci, widen(act ? kvi[k] : __ldg(Ki + colr[k]))));
                     if (need_j) gb = __dadd_rn(gb, __dmul_rn(cj, widen(act ? kvj[k] : __ldg(Kj + colr[k]))));
                     mGbar[k * NT + tid] = gb;
                 }
@@ -733,7 +744,8 @@ cudaError_t launch_co(const SmoProblem *probs, const int *order, int n_prob, int
     // alpha + mbar per owned element, then 7 bytes per POSITION of cold-path scratch; padded to a whole SM's worth so a
     // cluster CTA never shares its SM (a resident small CTA would keep a full-SM single-CTA solver from being scheduled)
     size_t smem = (size_t)LCAP * 16 + (size_t)lmax * 7 + 64;
-    if (smem < 160 * 1024) smem = 160 * 1024;
+    const char *sh = getenv("B200GS_SMO_CO_SHARE");                         // development switch: let cluster CTAs share an SM
+    if (!(sh && atoi(sh)) && smem < 160 * 1024) smem = 160 * 1024;
     auto kern = smo_colown_kernel<NT, KPT, CL, FAST, PROF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
