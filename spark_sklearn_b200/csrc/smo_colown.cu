@@ -15,14 +15,14 @@
 //   * m = -y*G, the position, the flags and the K_i values of the owned elements live in REGISTERS; alpha and
 //     mbar = -y*G_bar (touched by two elements per iteration / on status flips) in shared memory.
 //
-// Cross-CTA traffic per iteration: two all-gathers of one 64-byte record per CTA (st.async into every peer's shared
-// memory, completion counted on the RECEIVER's mbarrier -- no cluster-wide barrier; ordering argument below), after
-// which all CTAs combine the CL records identically and redundantly run the scalar two-variable update.
-//
-// Ordering argument for the barrier-free exchange (records double-buffered by parity): a CTA can finish exchange n
-// only after every peer SENT record n, and a peer sends record n only after all its warps passed the CTA barrier that
-// precedes the send, i.e. after they finished reading exchange n-1's records.  So a peer's record n+1 (other parity)
-// never overwrites a slot still being read, and record n+2 cannot be sent before this CTA sent n+1.
+// The hot loop has NO barrier of any kind -- neither __syncthreads nor a cluster barrier.  Each of the two arg-reductions
+// of an iteration is a WARP-level all-gather: a warp reduces its own elements (REDUX), its winner lane st.async-writes
+// the warp's 32/48-byte record into every CTA's shared memory (bytes counted on each RECEIVER's mbarrier), and every
+// warp of every CTA waits on its own CTA's mbarrier and reduces the same CL*NW records.  The scalar two-variable update
+// is then computed redundantly by every thread.  Ordering: a warp can finish stage s only after every warp of the
+// cluster SENT its stage-s record, and a warp sends its next record only after it has read all records of the current
+// stage; stages alternate A, B (, X), each with its own slots and mbarrier, so no slot is overwritten while readable.
+// Cold paths keep CTA-level records (double-buffered by parity) behind __syncthreads.
 //
 // Cold paths (every 1000 iterations / at unshrink): do_shrinking builds libsvm's two-pointer partition from a
 // position-indexed mark array (all-gathered through DSMEM), each CTA deriving the identical swap map; the gradient
@@ -70,21 +70,21 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
     }
 }
 
-struct RedCo {          // payload of each warp's winner (phase A and phase B)
-    double a_alpha[32]; int a_col[32], a_fl[32];
-    double b_mg[32], b_kv[32], b_alpha[32]; int b_col[32];
-};
-
 template <int NT, int KPT, int CL, bool FAST, bool PROF>
-__global__ void __launch_bounds__(NT, (NT <= 256 ? 3 : 1))
+__global__ void __launch_bounds__(NT, 1)
 smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ Red red;
-    __shared__ RedCo rc;
     __shared__ Xch<CL> xch;
-    __shared__ __align__(8) unsigned long long xbar[2];                      // one mbarrier per exchange parity
+    __shared__ __align__(8) unsigned long long xbar[2];                      // cold paths: one mbarrier per exchange parity
     constexpr int NW = NT / 32;
+    constexpr int R = CL * NW;                                              // warp records per all-gather
+    constexpr int RPL = (R + 31) / 32;                                      // records per lane
+    __shared__ __align__(16) unsigned wxA[R][8];                            // stage A records: key hi lo | idx | km hi lo | alpha lo hi | col
+    __shared__ __align__(16) unsigned wxB[R][12];                           // stage B: b1 | idx | b2 | col | mg | K_ij | alpha | pad
+    __shared__ __align__(16) unsigned wxX[R][12];                           // exact tie-break: hi | idx | lo | col | mg | K_ij | alpha | pad
+    __shared__ __align__(8) unsigned long long wbar[3];                      // one mbarrier per stage
     constexpr int LCAP = NT * KPT;                                          // elements owned by this CTA
 
     cg::cluster_group cluster = cg::this_cluster();
@@ -133,6 +133,9 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&xbar[0])));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&xbar[1])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&wbar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&wbar[1])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&wbar[2])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     cluster.sync();                                                         // every CTA's barriers exist before any remote signal
@@ -256,60 +259,85 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
     };
 
     // ---------------- select_working_set (svm.cpp:946-1047) ----------------
+    // Warp-level all-gather, no CTA barrier: every warp reduces its own elements, its winner lane writes the warp's record
+    // into slot (rank*NW + warp) of EVERY CTA of the cluster (st.async; bytes counted on each receiver's mbarrier), and
+    // every warp of every CTA then reduces the same R = CL*NW records.  Stage A, stage B and the rare exact tie-break
+    // each own a record array and an mbarrier; a warp sends its stage-(s+1) record only after it has read all stage-s
+    // records, so a slot is never overwritten while any warp can still read it (stages strictly alternate).
+    auto send_record = [&](unsigned slot_base, unsigned bar, int words, const unsigned (&v)[12]) {
+        const unsigned slot = slot_base + (unsigned)((int)rank * NW + warp) * (unsigned)words * 4u;
+#pragma unroll
+        for (int c = 0; c < CL; c++) {
+            const unsigned ra = mapa_u32(slot, (unsigned)c), rb = mapa_u32(bar, (unsigned)c);
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                         ::"r"(ra), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(rb) : "memory");
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                         ::"r"(ra + 16u), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(rb) : "memory");
+            if (words == 12)
+                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                             ::"r"(ra + 32u), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(rb) : "memory");
+        }
+    };
+    unsigned wphase = 0;                                 // bit s: parity the next wait on wbar[s] uses
+    auto stage_wait = [&](int sidx) {
+        mbar_wait(smem_u32(&wbar[sidx]), (wphase >> sidx) & 1u);
+        wphase ^= 1u << sidx;
+    };
+
     int pi = -1, pj = -1, col_i = 0, col_j = 0;          // packed (position << 5 | flags), dataset rows
     double gmax = 0, mg_j = 0, k_ij = 0, alpha_i = 0, alpha_j = 0;
     auto select = [&]() -> bool {
         double gmax2;
-        {   // phase A: i = argmax m over I_up, Gmax2 = max -m over I_low
+        {   // ---- stage A: i = argmax m over I_up, Gmax2 = max -m over I_low ----
             const unsigned long long key = dkey(la);
-            const int la_idx = la_pos >= 0 ? ((la_pos << IDX_SHIFT) | 0) : -1;      // flags are added by the owner below
+            const int la_idx = la_pos >= 0 ? (la_pos << IDX_SHIFT) : -1;             // the sender adds the flags
             const KArg w = warp_argmax((unsigned)(key >> 32), (unsigned)key, la_idx);
             const unsigned long long km = warp_keymax(dkey(-lm));
-            if (la_idx >= 0 && la_idx == w.idx) {                                    // this lane owns the warp's winner
+            if (tid == 0) mbar_expect_tx(smem_u32(&wbar[0]), R * 32);
+            if (w.idx >= 0 ? la_idx == w.idx : lane == 0) {                          // exactly one lane per warp
                 int c = colr[0], f = fl[0];
 #pragma unroll
                 for (int k = 1; k < KPT; k++) { c = k == la_k ? colr[k] : c; f = k == la_k ? fl[k] : f; }
-                rc.a_alpha[warp] = alpha[la_k * NT + tid]; rc.a_col[warp] = c; rc.a_fl[warp] = f;
-            }
-            if (lane == 0) {
-                red.a_hi[warp] = w.hi; red.a_lo[warp] = w.lo; red.a_idx[warp] = w.idx;
-                red.m_hi[warp] = (unsigned)(km >> 32); red.m_lo[warp] = (unsigned)km;
-            }
-            __syncthreads();
-            const bool v = lane < NW;
-            const int myidx = v ? red.a_idx[lane] : -1;
-            const KArg a = warp_argmax(v ? red.a_hi[lane] : 0u, v ? red.a_lo[lane] : 0u, myidx);
-            const unsigned long long km2 =
-                warp_keymax(v ? (((unsigned long long)red.m_hi[lane] << 32) | red.m_lo[lane]) : 0ull);
-            unsigned rec[XW] = {0};
-            rec[0] = a.hi; rec[1] = a.lo; rec[2] = (unsigned)a.idx; rec[3] = (unsigned)(km2 >> 32); rec[4] = (unsigned)km2;
-            if (a.idx >= 0) {
-                const int ww = __ffs(__ballot_sync(0xffffffffu, myidx == a.idx)) - 1;     // the winner's warp
-                const double ai = rc.a_alpha[ww];
-                rec[5] = lo32(ai); rec[6] = hi32(ai); rec[7] = (unsigned)rc.a_col[ww];
-                rec[2] = (unsigned)(a.idx | rc.a_fl[ww]);
+                const double av = alpha[la_k * NT + tid];
+                unsigned v[12];
+                v[0] = w.hi; v[1] = w.lo; v[2] = w.idx >= 0 ? (unsigned)(w.idx | f) : 0xffffffffu;
+                v[3] = (unsigned)(km >> 32); v[4] = (unsigned)km; v[5] = lo32(av); v[6] = hi32(av); v[7] = (unsigned)c;
+                v[8] = v[9] = v[10] = v[11] = 0u;
+                send_record(smem_u32(&wxA[0][0]), smem_u32(&wbar[0]), 8, v);
             }
             tick(0);
-            const unsigned (*r)[XW] = exchange(rec);
-            tick(1);
-            int best = 0;
-            unsigned long long kmax = ((unsigned long long)r[0][3] << 32) | r[0][4];
+            stage_wait(0);
+            // every warp reduces all R records: lane-local best of its RPL records, then REDUX
+            unsigned bh = 0u, bl = 0u; int bi = -1, br = 0;
+            unsigned long long kml = 0ull;
 #pragma unroll
-            for (int c = 1; c < CL; c++) {
-                const unsigned long long kb = ((unsigned long long)r[best][0] << 32) | r[best][1];
-                const unsigned long long kc = ((unsigned long long)r[c][0] << 32) | r[c][1];
-                if (kc > kb || (kc == kb && (int)r[c][2] > (int)r[best][2])) best = c;
-                const unsigned long long k2 = ((unsigned long long)r[c][3] << 32) | r[c][4];
-                kmax = k2 > kmax ? k2 : kmax;
+            for (int q = 0; q < RPL; q++) {
+                const int r = lane + 32 * q;
+                if (r < R) {
+                    const uint4 x = *reinterpret_cast<const uint4 *>(&wxA[r][0]);
+                    const unsigned k4 = wxA[r][4];
+                    const int xi = (int)x.z;
+                    if (xi >= 0 && (x.x > bh || (x.x == bh && (x.y > bl || (x.y == bl && xi > bi))))) { bh = x.x; bl = x.y; bi = xi; br = r; }
+                    const unsigned long long k2 = ((unsigned long long)x.w << 32) | k4;
+                    kml = k2 > kml ? k2 : kml;
+                }
             }
-            pi = (int)r[best][2];
-            gmax = dkey_inv(((unsigned long long)r[best][0] << 32) | r[best][1]);
-            gmax2 = dkey_inv(kmax);
-            alpha_i = mk64(r[best][5], r[best][6]);
-            col_i = (int)r[best][7];
+            const KArg a = warp_argmax(bh, bl, bi);
+            const unsigned long long km2 = warp_keymax(kml);
+            pi = a.idx;
+            if (pi >= 0) {
+                const int wl = __ffs(__ballot_sync(0xffffffffu, bi == a.idx)) - 1;
+                const int rw = __shfl_sync(0xffffffffu, br, wl);
+                const uint4 y = *reinterpret_cast<const uint4 *>(&wxA[rw][4]);           // km lo | alpha lo | alpha hi | col
+                alpha_i = mk64(y.y, y.z);
+                col_i = (int)y.w;
+            }
+            gmax = dkey_inv(((unsigned long long)a.hi << 32) | a.lo);
+            gmax2 = dkey_inv(km2);
+            tick(1);
         }
         if (pi < 0 || __dadd_rn(gmax, gmax2) < eps) return true;              // svm.cpp:1040-1041
-        // ---- phase B: j = argmin -(gd^2)/quad over I_low with gd > 0 (svm.cpp:980-1037) ----
+        // ---- stage B: j = argmin -(gd^2)/quad over I_low with gd > 0 (svm.cpp:980-1037) ----
         const double QDi = QDc(col_i);
         const float *__restrict__ Ki = K + (size_t)col_i * ldk;
 #pragma unroll
@@ -351,18 +379,22 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
                 }
             }
         }
-        double m1 = 0, q1 = 0;
-        int idx1 = -1, c1c = 0;
+        // winner payload of this thread (selected lazily: only the sender lane needs it)
+        auto payload = [&](int kk, unsigned (&v)[12]) {
+            int cc = colr[0];
+            float kq = kvi[0];
+            double mm = m[0];
+#pragma unroll
+            for (int k = 1; k < KPT; k++) { const bool s_ = k == kk; cc = s_ ? colr[k] : cc; kq = s_ ? kvi[k] : kq; mm = s_ ? m[k] : mm; }
+            const double qq = widen(kq), av = alpha[kk * NT + tid];
+            v[3] = (unsigned)cc; v[4] = lo32(mm); v[5] = hi32(mm); v[6] = lo32(qq); v[7] = hi32(qq); v[8] = lo32(av); v[9] = hi32(av);
+            v[10] = v[11] = 0u;
+        };
+        int idx1 = -1;
         if (k1 >= 0) {
             int p1 = pos[0], f1 = fl[0];
-            float kq = kvi[0];
-            m1 = m[0]; c1c = colr[0];
 #pragma unroll
-            for (int k = 1; k < KPT; k++) {
-                const bool s = k == k1;
-                p1 = s ? pos[k] : p1; f1 = s ? fl[k] : f1; m1 = s ? m[k] : m1; kq = s ? kvi[k] : kq; c1c = s ? colr[k] : c1c;
-            }
-            q1 = widen(kq);
+            for (int k = 1; k < KPT; k++) { const bool s_ = k == k1; p1 = s_ ? pos[k] : p1; f1 = s_ ? fl[k] : f1; }
             idx1 = (p1 << IDX_SHIFT) | f1;
         }
         unsigned top1k, top2k;
@@ -370,44 +402,49 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
             const unsigned w1 = __reduce_max_sync(0xffffffffu, b1k);
             const int widx = __reduce_max_sync(0xffffffffu, (b1k == w1) ? idx1 : -1);
             const unsigned w2 = __reduce_max_sync(0xffffffffu, (idx1 == widx) ? b2k : b1k);
-            if (idx1 >= 0 && idx1 == widx) {
-                rc.b_mg[warp] = m1; rc.b_kv[warp] = q1; rc.b_alpha[warp] = alpha[k1 * NT + tid]; rc.b_col[warp] = c1c;
-            }
-            if (lane == 0) { red.b_hi[warp] = w1; red.b_idx[warp] = widx; red.t_hi[warp] = w2; }
-            __syncthreads();
-            const bool v = lane < NW;
-            const unsigned bk = v ? red.b_hi[lane] : 0u;
-            const int bi = v ? red.b_idx[lane] : -1;
-            const unsigned c1 = __reduce_max_sync(0xffffffffu, bk);
-            const int cidx = __reduce_max_sync(0xffffffffu, (bk == c1) ? bi : -1);
-            const unsigned c2 = __reduce_max_sync(0xffffffffu, (v && bi == cidx) ? red.t_hi[lane] : bk);
-            unsigned rec[XW] = {0};
-            rec[0] = c1; rec[2] = (unsigned)cidx; rec[3] = c2;
-            if (cidx >= 0) {
-                const int wj = __ffs(__ballot_sync(0xffffffffu, bi == cidx)) - 1;
-                const double a = rc.b_mg[wj], bb = rc.b_kv[wj], c = rc.b_alpha[wj];
-                rec[5] = lo32(a); rec[6] = hi32(a); rec[7] = lo32(bb); rec[8] = hi32(bb); rec[9] = lo32(c); rec[10] = hi32(c);
-                rec[11] = (unsigned)rc.b_col[wj];
+            if (tid == 0) mbar_expect_tx(smem_u32(&wbar[1]), R * 48);
+            if (widx >= 0 ? idx1 == widx : lane == 0) {
+                unsigned v[12];
+                if (widx >= 0) payload(k1, v);
+                else { v[3] = v[4] = v[5] = v[6] = v[7] = v[8] = v[9] = v[10] = v[11] = 0u; }
+                v[0] = w1; v[1] = (unsigned)widx; v[2] = w2;
+                send_record(smem_u32(&wxB[0][0]), smem_u32(&wbar[1]), 12, v);
             }
             tick(3);
-            const unsigned (*r)[XW] = exchange(rec);
-            tick(4);
-            int best = 0;
+            stage_wait(1);
+            unsigned bk = 0u; int bi = -1, br = 0;
 #pragma unroll
-            for (int c = 1; c < CL; c++)
-                if (r[c][0] > r[best][0] || (r[c][0] == r[best][0] && (int)r[c][2] > (int)r[best][2])) best = c;
-            top2k = 0u;
-#pragma unroll
-            for (int c = 0; c < CL; c++) { const unsigned kc = c == best ? r[c][3] : r[c][0]; top2k = kc > top2k ? kc : top2k; }
-            top1k = r[best][0];
-            pj = (int)r[best][2];
+            for (int q = 0; q < RPL; q++) {
+                const int r = lane + 32 * q;
+                if (r < R) {
+                    const uint2 x = *reinterpret_cast<const uint2 *>(&wxB[r][0]);
+                    const int xi = (int)x.y;
+                    if (xi >= 0 && (x.x > bk || (x.x == bk && xi > bi))) { bk = x.x; bi = xi; br = r; }
+                }
+            }
+            top1k = __reduce_max_sync(0xffffffffu, bk);
+            pj = __reduce_max_sync(0xffffffffu, (bk == top1k) ? bi : -1);
             if (pj < 0) return true;                                               // Gmin_idx == -1
-            mg_j = mk64(r[best][5], r[best][6]); k_ij = mk64(r[best][7], r[best][8]); alpha_j = mk64(r[best][9], r[best][10]);
-            col_j = (int)r[best][11];
+            unsigned sk = 0u;                                                       // runner-up: best b1 of the others, b2 of the winner
+#pragma unroll
+            for (int q = 0; q < RPL; q++) {
+                const int r = lane + 32 * q;
+                if (r < R) {
+                    const unsigned kk = (int)wxB[r][1] == pj ? wxB[r][2] : ((int)wxB[r][1] >= 0 ? wxB[r][0] : 0u);
+                    sk = kk > sk ? kk : sk;
+                }
+            }
+            top2k = __reduce_max_sync(0xffffffffu, sk);
+            const int wl = __ffs(__ballot_sync(0xffffffffu, bi == pj)) - 1;
+            const int rw = __shfl_sync(0xffffffffu, br, wl);
+            const uint4 y = *reinterpret_cast<const uint4 *>(&wxB[rw][4]);             // mg lo hi | kv lo hi
+            const uint2 z = *reinterpret_cast<const uint2 *>(&wxB[rw][8]);             // alpha lo hi
+            col_j = (int)wxB[rw][3];
+            mg_j = mk64(y.x, y.y); k_ij = mk64(y.z, y.w); alpha_j = mk64(z.x, z.y);
+            tick(4);
         }
         if (top1k - top2k <= BAND || (FAST && top1k <= KEY_TINY)) {
             // ---- exact tie-break: libsvm's correctly rounded quotients for every element in the band (rare) ----
-            __syncthreads();                                 // slower warps may still be reading rc.b_* above
             const unsigned thrk = (top1k > BAND && !(FAST && top1k <= KEY_TINY)) ? top1k - BAND : 1u;
             double bestn = -CUDART_INF;
             int bidx = -1, bk_ = 0;
@@ -429,38 +466,33 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
             }
             const unsigned long long key = dkey(bestn);
             const KArg w = warp_argmax((unsigned)(key >> 32), (unsigned)key, bidx);
-            if (bidx >= 0 && bidx == w.idx) {
-                double mm = m[0];
-                float qq = kvi[0];
-                int cc = colr[0];
+            if (tid == 0) mbar_expect_tx(smem_u32(&wbar[2]), R * 48);
+            if (w.idx >= 0 ? bidx == w.idx : lane == 0) {
+                unsigned v[12];
+                if (w.idx >= 0) payload(bk_, v);
+                else { v[3] = v[4] = v[5] = v[6] = v[7] = v[8] = v[9] = v[10] = v[11] = 0u; }
+                v[0] = w.hi; v[1] = (unsigned)w.idx; v[2] = w.lo;
+                send_record(smem_u32(&wxX[0][0]), smem_u32(&wbar[2]), 12, v);
+            }
+            stage_wait(2);
+            unsigned bh = 0u, bl = 0u; int bi = -1, br = 0;
 #pragma unroll
-                for (int k = 1; k < KPT; k++) { const bool s = k == bk_; mm = s ? m[k] : mm; qq = s ? kvi[k] : qq; cc = s ? colr[k] : cc; }
-                rc.b_mg[warp] = mm; rc.b_kv[warp] = widen(qq); rc.b_alpha[warp] = alpha[bk_ * NT + tid]; rc.b_col[warp] = cc;
+            for (int q = 0; q < RPL; q++) {
+                const int r = lane + 32 * q;
+                if (r < R) {
+                    const uint4 x = *reinterpret_cast<const uint4 *>(&wxX[r][0]);       // hi | idx | lo | col
+                    const int xi = (int)x.y;
+                    if (xi >= 0 && (x.x > bh || (x.x == bh && (x.z > bl || (x.z == bl && xi > bi))))) { bh = x.x; bl = x.z; bi = xi; br = r; }
+                }
             }
-            if (lane == 0) { red.x_hi[warp] = w.hi; red.x_lo[warp] = w.lo; red.x_idx[warp] = w.idx; }
-            __syncthreads();
-            const bool v = lane < NW;
-            const int xi = v ? red.x_idx[lane] : -1;
-            const KArg b = warp_argmax(v ? red.x_hi[lane] : 0u, v ? red.x_lo[lane] : 0u, xi);
-            unsigned rec[XW] = {0};
-            rec[0] = b.hi; rec[1] = b.lo; rec[2] = (unsigned)b.idx;
-            if (b.idx >= 0) {
-                const int wj = __ffs(__ballot_sync(0xffffffffu, xi == b.idx)) - 1;
-                const double a = rc.b_mg[wj], bb = rc.b_kv[wj], c = rc.b_alpha[wj];
-                rec[5] = lo32(a); rec[6] = hi32(a); rec[7] = lo32(bb); rec[8] = hi32(bb); rec[9] = lo32(c); rec[10] = hi32(c);
-                rec[11] = (unsigned)rc.b_col[wj];
-            }
-            const unsigned (*r)[XW] = exchange(rec);
-            int best = 0;
-#pragma unroll
-            for (int c = 1; c < CL; c++) {
-                const unsigned long long kb = ((unsigned long long)r[best][0] << 32) | r[best][1];
-                const unsigned long long kc = ((unsigned long long)r[c][0] << 32) | r[c][1];
-                if (kc > kb || (kc == kb && (int)r[c][2] > (int)r[best][2])) best = c;
-            }
-            pj = (int)r[best][2];
-            mg_j = mk64(r[best][5], r[best][6]); k_ij = mk64(r[best][7], r[best][8]); alpha_j = mk64(r[best][9], r[best][10]);
-            col_j = (int)r[best][11];
+            const KArg b = warp_argmax(bh, bl, bi);
+            pj = b.idx;                                                         // >= 0: the approximate winner is in the band
+            const int wl = __ffs(__ballot_sync(0xffffffffu, bi == pj)) - 1;
+            const int rw = __shfl_sync(0xffffffffu, br, wl);
+            const uint4 y = *reinterpret_cast<const uint4 *>(&wxX[rw][4]);
+            const uint2 z = *reinterpret_cast<const uint2 *>(&wxX[rw][8]);
+            col_j = (int)wxX[rw][3];
+            mg_j = mk64(y.x, y.y); k_ij = mk64(y.z, y.w); alpha_j = mk64(z.x, z.y);
         }
         return false;
     };
@@ -577,7 +609,6 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
         if (select()) {
             rebuild_gradient();
             active = l;
-            __syncthreads();                                     // selection scratch is rewritten below
             local_scan();
             if (select()) break;
             counter = 1;
@@ -589,14 +620,16 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
         float kvj[KPT];
 #pragma unroll
         for (int k = 0; k < KPT; k++) kvj[k] = pos[k] < active ? __ldg(Kj + colr[k]) : 0.f;     // in flight during the scalar update
-        if (warp == 0) {                                         // every CTA runs the identical scalar update
+        // analytic two-variable update, computed redundantly (and identically) by every thread: no broadcast, no barrier
+        double a, b, ai = alpha_i, aj = alpha_j;
+        int sti, stj;
+        {
             const double C = Cc;
             const bool yi = (pi & F_YPOS) != 0, yj = (pj & F_YPOS) != 0;
             const double Gi = yi ? -gmax : gmax;                 // G = -y m (exact)
             const double Gj = yj ? -mg_j : mg_j;
             const double QDi = QDc(col_i), QDj = QDc(col_j);
             const double Qij = (yi == yj) ? k_ij : -k_ij;        // signed Q_i[j]
-            double ai = alpha_i, aj = alpha_j;
             if (yi != yj) {                                      // svm.cpp:772-815
                 double quad = __dadd_rn(__dadd_rn(QDi, QDj), __dmul_rn(2.0, Qij));
                 if (quad <= 0) quad = TAU;
@@ -618,25 +651,18 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
                 if (sum > C) { if (aj > C) { aj = C; ai = __dsub_rn(sum, C); } }
                 else         { if (ai < 0) { ai = 0; aj = sum; } }
             }
-            if (lane == 0) {
-                const double dai = __dsub_rn(ai, alpha_i), daj = __dsub_rn(aj, alpha_j);
-                red.bc_d[0] = yi ? -dai : dai;                   // a = -y_i dalpha_i
-                red.bc_d[1] = yj ? -daj : daj;                   // b = -y_j dalpha_j
-                red.bc_d[2] = ai; red.bc_d[3] = aj;
-                red.bc_i[0] = ai >= C ? ST_UPPER : (ai <= 0 ? ST_LOWER : ST_FREE);
-                red.bc_i[1] = aj >= C ? ST_UPPER : (aj <= 0 ? ST_LOWER : ST_FREE);
-            }
+            const double dai = __dsub_rn(ai, alpha_i), daj = __dsub_rn(aj, alpha_j);
+            a = yi ? -dai : dai;                                 // a = -y_i dalpha_i
+            b = yj ? -daj : daj;                                 // b = -y_j dalpha_j
+            sti = ai >= C ? ST_UPPER : (ai <= 0 ? ST_LOWER : ST_FREE);
+            stj = aj >= C ? ST_UPPER : (aj <= 0 ? ST_LOWER : ST_FREE);
         }
         tick(5);
-        __syncthreads();
-        tick(6);
-        const double a = red.bc_d[0], b = red.bc_d[1];
-        const int sti = red.bc_i[0], stj = red.bc_i[1];
         // the owners of i and j take the new alpha and status FIRST: the fused scan below must see the new sets
 #pragma unroll
         for (int k = 0; k < KPT; k++) {
-            if (pos[k] == i) { alpha[k * NT + tid] = red.bc_d[2]; fl[k] = mkflags((pi & F_YPOS) != 0, sti); }
-            if (pos[k] == j) { alpha[k * NT + tid] = red.bc_d[3]; fl[k] = mkflags((pj & F_YPOS) != 0, stj); }
+            if (pos[k] == i) { alpha[k * NT + tid] = ai; fl[k] = mkflags((pi & F_YPOS) != 0, sti); }
+            if (pos[k] == j) { alpha[k * NT + tid] = aj; fl[k] = mkflags((pj & F_YPOS) != 0, stj); }
         }
         // m update over the active set (svm.cpp:866-872), fused with the next iteration's local scan
         la = -CUDART_INF; lm = CUDART_INF; la_pos = -1; la_k = 0;
@@ -670,6 +696,7 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
         }
         tick(8);
     }
+
 
     // ---------------- calculate_rho (svm.cpp:1131-1168): sequential float64 sum in ascending position ----------------
     cluster.sync();
