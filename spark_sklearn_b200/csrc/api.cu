@@ -96,9 +96,6 @@ int gs_create(int device, gs_handle **out)
     {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        if ((e = cudaStreamCreateWithPriority(&h->stream_mid, cudaStreamNonBlocking, hi)) != cudaSuccess) {
-            g_create_error = cudaGetErrorString(e); cudaStreamDestroy(h->stream); delete h; return GS_ERR_CUDA;
-        }
         if ((e = cudaStreamCreateWithPriority(&h->stream_hi, cudaStreamNonBlocking, hi)) != cudaSuccess) {
             g_create_error = cudaGetErrorString(e); cudaStreamDestroy(h->stream); delete h; return GS_ERR_CUDA;
         }
@@ -117,7 +114,6 @@ void gs_destroy(gs_handle *h)
     for (auto &w : h->dWork) w.release();
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream_hi) cudaStreamDestroy(h->stream_hi);
-    if (h->stream_mid) cudaStreamDestroy(h->stream_mid);
     delete h;
 }
 
@@ -289,7 +285,7 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
             }
     }
     sp_off.back() = (int)rows_all.size();
-    if (lmax > smo_max_rows() && lmax > smo_cluster_max_rows(4)) {
+    if (lmax > smo_max_rows() && lmax > smo_colown_max_rows(4)) {
         gs_set_error(h, "gs_svc: sub-problem with " + std::to_string(lmax) + " rows exceeds the resident-state SMO kernel limit of " +
                             std::to_string(smo_max_rows()));
         return GS_ERR_UNSUPPORTED;
@@ -436,63 +432,52 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
         pf.h2d_bytes += (size_t)np * sizeof(SmoProblem) + (size_t)np * 4 + vtasks.size() * sizeof(VoteTask);
         tm.mark(4);
         // -- solve --
-        // The step is bounded by its longest sub-problems.  The predicted-longest share of the problems is solved by
-        // the cluster kernel (one problem over `cl` SMs, high-priority stream, launched first); the rest by the
-        // single-CTA kernel.  Development switches: B200GS_SMO_CLUSTER (0/2/4), B200GS_SMO_CLUSTER_PCT.
+        // Policy (measured on config 2 / config 4, profiles/): a 4-CTA cluster solves one problem at 3.5 us per iteration
+        // against 6.4-7.1 us for the single-CTA kernel, but costs twice the SM-time per iteration.  So clusters are for the
+        // critical path only:
+        //   * fewer problems than SMs: everything on the widest cluster that fits;
+        //   * throughput-bound searches (the predicted-longest problem is shorter than 0.9 x total work / SMs): no clusters;
+        //   * otherwise the group of predicted near-longest problems (cost > 0.8 x the largest), at most half the SMs.
+        //     (config 2: exactly the ten 66-68k-iteration problems; leaving ONE of them on a single SM costs +33 %.)
+        // Cluster launches go first, on the high-priority stream.  Development switches: B200GS_SMO_CLUSTER (0/2/4/8),
+        // B200GS_SMO_CLUSTER_N.
         std::string why;
-        // Policy (measured on config 2, profiles/): a cluster cuts the per-iteration LATENCY of one problem (6.6 us on one
-        // SM, 5.4 us on 2 SMs, 4.2 us on 4, 4.1 us on 8) but costs more SM-time per iteration, so clusters go to the
-        // problems that bound the makespan.  With fewer problems than SMs everything runs on the widest cluster that
-        // fits; otherwise the predicted-longest `pct4` % run on 4-CTA clusters, the next `pct2` % on 2-CTA clusters
-        // (launched first, on high-priority streams) and the rest on the single-CTA kernel.
-        // Development switches: B200GS_SMO_CLUSTER (0/2/4/8), B200GS_SMO_CLUSTER_PCT, B200GS_SMO_CL2_PCT, B200GS_SMO_CO.
-        int cl = 0, pct = 0, pct2 = 0;
+        int cl = 0, n_cl = 0;
         if (lmax > 2048) {
-            if (np * 8 <= h->sm_count) { cl = 8; pct = 100; }
-            else if (np * 4 <= h->sm_count) { cl = 4; pct = 100; }
-            else if (np * 2 <= h->sm_count) { cl = 2; pct = 100; }
-            else { cl = 4; pct = 6; pct2 = 0; }
+            if (np * 8 <= h->sm_count) { cl = 8; n_cl = np; }
+            else if (np * 4 <= h->sm_count) { cl = 4; n_cl = np; }
+            else if (np * 2 <= h->sm_count) { cl = 2; n_cl = np; }
+            else {
+                double total = 0;
+                for (int q = 0; q < np; q++) total += cost[q];
+                const double wmax = cost[order[0]];
+                if (wmax > 0.9 * total / h->sm_count) {
+                    cl = 4;
+                    while (n_cl < np && cost[order[n_cl]] > 0.8 * wmax) ++n_cl;
+                    n_cl = std::min(n_cl, h->sm_count / 8);
+                }
+            }
         }
-        if (const char *e = getenv("B200GS_SMO_CLUSTER")) cl = atoi(e);
-        if (const char *e = getenv("B200GS_SMO_CLUSTER_PCT")) pct = atoi(e);
-        if (const char *e = getenv("B200GS_SMO_CL2_PCT")) pct2 = atoi(e);
-        const char *co_env = getenv("B200GS_SMO_CO");
-        const bool colown = !(co_env && atoi(co_env) == 0);                 // 0 = position-owned cluster kernel (smo_cluster.cu)
-        int n_cl = 0, n_cl2 = 0;
-        if ((cl == 2 || cl == 4 || cl == 8) && lmax <= smo_cluster_max_rows(cl) && lmax > 2048)
-            n_cl = std::min(np, std::max(pct > 0 ? 1 : 0, (int)((int64_t)np * pct / 100)));
-        if (n_cl > 0 && cl != 2 && pct2 > 0 && lmax <= smo_cluster_max_rows(2))
-            n_cl2 = std::min(np - n_cl, (int)((int64_t)np * pct2 / 100));
-        auto launch_tier = [&](int first, int count, int width, cudaStream_t s) -> cudaError_t {
-            return colown ? launch_smo_colown(d_probs, d_order + first, count, lmax, width, fast, s)
-                          : launch_smo_cluster(d_probs, d_order + first, count, lmax, width, fast, (int)ldk, s);
-        };
+        if (const char *e = getenv("B200GS_SMO_CLUSTER")) { cl = atoi(e); if (n_cl == 0) n_cl = std::max(1, np * 6 / 100); }
+        if (const char *e = getenv("B200GS_SMO_CLUSTER_N")) n_cl = std::min(np, atoi(e));
+        if (!(cl == 2 || cl == 4 || cl == 8) || lmax > smo_colown_max_rows(cl) || lmax <= 2048) n_cl = 0;
         if (n_cl > 0) {
-            cudaEvent_t ready, done, done2;
+            cudaEvent_t ready, done;
             cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
             cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
-            cudaEventCreateWithFlags(&done2, cudaEventDisableTiming);
             cudaEventRecord(ready, st);
             cudaStreamWaitEvent(h->stream_hi, ready, 0);
-            cudaError_t ce = launch_tier(0, n_cl, cl, h->stream_hi);
-            if (ce != cudaSuccess) { gs_set_error(h, std::string("launch_smo_cluster: ") + cudaGetErrorString(ce)); return GS_ERR_CUDA; }
+            cudaError_t ce = launch_smo_colown(d_probs, d_order, n_cl, lmax, cl, fast, h->stream_hi);
+            if (ce != cudaSuccess) { gs_set_error(h, std::string("launch_smo_colown: ") + cudaGetErrorString(ce)); return GS_ERR_CUDA; }
             cudaEventRecord(done, h->stream_hi);
             pf.launches++;
-            if (n_cl2 > 0) {
-                cudaStreamWaitEvent(h->stream_mid, ready, 0);
-                ce = launch_tier(n_cl, n_cl2, 2, h->stream_mid);
-                if (ce != cudaSuccess) { gs_set_error(h, std::string("launch_smo_cluster (2): ") + cudaGetErrorString(ce)); return GS_ERR_CUDA; }
-                cudaEventRecord(done2, h->stream_mid);
-                pf.launches++;
-            }
-            if (np - n_cl - n_cl2 > 0) {
-                ce = launch_smo(d_probs, d_order + n_cl + n_cl2, np - n_cl - n_cl2, lmax, fast, (int)ldk, st, &why);
+            if (np - n_cl > 0) {
+                ce = launch_smo(d_probs, d_order + n_cl, np - n_cl, lmax, fast, (int)ldk, st, &why);
                 if (ce != cudaSuccess) { gs_set_error(h, why.empty() ? std::string("launch_smo: ") + cudaGetErrorString(ce) : why); return why.empty() ? GS_ERR_CUDA : GS_ERR_UNSUPPORTED; }
                 pf.launches++;
             }
             cudaStreamWaitEvent(st, done, 0);
-            if (n_cl2 > 0) cudaStreamWaitEvent(st, done2, 0);
-            cudaEventDestroy(ready); cudaEventDestroy(done); cudaEventDestroy(done2);
+            cudaEventDestroy(ready); cudaEventDestroy(done);
         } else {
             cudaError_t ce = launch_smo(d_probs, d_order, np, lmax, fast, (int)ldk, st, &why);
             if (ce != cudaSuccess) { gs_set_error(h, why.empty() ? std::string("launch_smo: ") + cudaGetErrorString(ce) : why); return why.empty() ? GS_ERR_CUDA : GS_ERR_UNSUPPORTED; }

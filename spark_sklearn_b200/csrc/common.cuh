@@ -38,7 +38,6 @@ struct gs_handle {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t stream_hi = nullptr;   // high priority: cluster SMO launches (the critical-path problems)
-    cudaStream_t stream_mid = nullptr;  // high priority: second tier of cluster SMO launches
     std::string err;
     // dataset (rows stored in INTERNAL order: sorted by class, then by original index)
     int64_t n = 0, d = 0;
@@ -89,12 +88,9 @@ struct SmoProblem {
 cudaError_t launch_smo(const SmoProblem *d_probs, const int *d_order, int n_prob, int lmax, bool fast, int rowcap,
                        cudaStream_t st, std::string *why);
 int smo_max_rows();   // largest sub-problem the resident-state kernel supports
-// smo_cluster.cu: the same solver with one sub-problem spread over a thread-block cluster of cl CTAs (DSMEM exchange)
-int smo_cluster_max_rows(int cl);
+// smo_colown.cu: the same solver with one sub-problem spread over a thread-block cluster of cl CTAs (DSMEM exchange)
 int smo_colown_max_rows(int cl);
 cudaError_t launch_smo_colown(const SmoProblem *d_probs, const int *d_order, int n_prob, int lmax, int cl, bool fast, cudaStream_t st);
-cudaError_t launch_smo_cluster(const SmoProblem *d_probs, const int *d_order, int n_prob, int lmax, int cl, bool fast, int rowcap,
-                               cudaStream_t st);
 
 // ---- score.cu ----
 // dec[c][r] = sum_j k64(r, j) * coef[c][j]  (float64 kernel values recomputed from S, not the

@@ -15,13 +15,12 @@
 //   * m = -y*G, the position, the flags and the K_i values of the owned elements live in REGISTERS; alpha and
 //     mbar = -y*G_bar (touched by two elements per iteration / on status flips) in shared memory.
 //
-// The hot loop has NO barrier of any kind -- neither __syncthreads nor a cluster barrier.  Each of the two arg-reductions
-// of an iteration is a WARP-level all-gather: a warp reduces its own elements (REDUX), its winner lane st.async-writes
-// the warp's 32/48-byte record into every CTA's shared memory (bytes counted on each RECEIVER's mbarrier), and every
-// warp of every CTA waits on its own CTA's mbarrier and reduces the same CL*NW records.  The scalar two-variable update
-// is then computed redundantly by every thread.  Ordering: a warp can finish stage s only after every warp of the
-// cluster SENT its stage-s record, and a warp sends its next record only after it has read all records of the current
-// stage; stages alternate A, B (, X), each with its own slots and mbarrier, so no slot is overwritten while readable.
+// The hot loop has no CTA-wide or cluster-wide barrier.  Each of the two arg-reductions
+// of an iteration is two-level: a warp reduces its own elements (REDUX), its winner lane stores the warp's record in
+// local shared memory and the warp arrives on a named barrier; the LEADER warp reduces the NW warp records, st.async-writes
+// the CTA's record into every CTA's shared memory (bytes counted on each RECEIVER's mbarrier), reduces the CL CTA records
+// and publishes the result through shared memory and a named barrier on which the worker warps are parked.  Only the
+// leader executes the combines and the scalar two-variable update, so the workers' issue slots stay free.
 // Cold paths keep CTA-level records (double-buffered by parity) behind __syncthreads.
 //
 // Cold paths (every 1000 iterations / at unshrink): do_shrinking builds libsvm's two-pointer partition from a
@@ -60,11 +59,13 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Default (acquire, CTA scope) wait: shared-memory data delivered by st.async is made visible by the complete_tx that
+// finishes the phase; a .cluster-scope acquire would add an L1 invalidate (CCTL.IVALL) to every wait.
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 {
     unsigned done = 0;
     for (unsigned spin = 0; !done; ++spin) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (spin > (1u << 26)) __trap();                                    // a lost signal must not hang the GPU
     }
@@ -79,12 +80,20 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
     __shared__ Xch<CL> xch;
     __shared__ __align__(8) unsigned long long xbar[2];                      // cold paths: one mbarrier per exchange parity
     constexpr int NW = NT / 32;
-    constexpr int R = CL * NW;                                              // warp records per all-gather
-    constexpr int RPL = (R + 31) / 32;                                      // records per lane
-    __shared__ __align__(16) unsigned wxA[R][8];                            // stage A records: key hi lo | idx | km hi lo | alpha lo hi | col
-    __shared__ __align__(16) unsigned wxB[R][12];                           // stage B: b1 | idx | b2 | col | mg | K_ij | alpha | pad
-    __shared__ __align__(16) unsigned wxX[R][12];                           // exact tie-break: hi | idx | lo | col | mg | K_ij | alpha | pad
-    __shared__ __align__(8) unsigned long long wbar[3];                      // one mbarrier per stage
+    // hot-loop mailboxes: per-warp records (local), per-CTA records (written by every leader), results (leader -> workers)
+    __shared__ struct __align__(16) {
+        unsigned recA[NW][8];        // key hi lo | idx+flags | km hi | km lo | alpha lo hi | col
+        unsigned recB[NW][12];       // b1 | idx | b2 | col | m lo hi | K_i lo hi | alpha lo hi | pad
+        unsigned recX[NW][12];       // hi | idx | lo | col | m | K_i | alpha | pad          (exact tie-break)
+        unsigned xA[CL][8], xB[CL][12], xX[CL][12];
+        unsigned resA[4];            // i (packed; -1 = stop) | col_i | gmax lo hi
+        unsigned resB1[4];           // j (packed) | col_j | mode | band threshold
+        unsigned resB2[12];          // a | b | alpha_i' | alpha_j' | status_i | status_j
+        unsigned resX[4];            // j (packed) | col_j
+    } hot;
+    enum { HB_XA = 0, HB_XB, HB_XX, HB_N };                                  // cross-CTA record arrival (mbarrier, tx bytes): leader only
+    enum { NB_LA = 1, NB_RA, NB_LB, NB_RB1, NB_RB2, NB_LX, NB_RX };          // hardware named barriers (0 is __syncthreads)
+    __shared__ __align__(8) unsigned long long hbar[HB_N];
     constexpr int LCAP = NT * KPT;                                          // elements owned by this CTA
 
     cg::cluster_group cluster = cg::this_cluster();
@@ -133,9 +142,7 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&xbar[0])));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&xbar[1])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&wbar[0])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&wbar[1])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&wbar[2])));
+        for (int q = 0; q < HB_N; q++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&hbar[q])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     cluster.sync();                                                         // every CTA's barriers exist before any remote signal
@@ -197,16 +204,18 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
 
     // ---------------- local scan (normally fused into the update loop) ----------------
     // la: max m over the owned I_up elements, ties -> larger position (libsvm's ascending ">=" scan); lm: min m over I_low
+    // (the winner's column / flags / slot are tracked as VALUES: selecting them later by a run-time k makes the compiler
+    //  index the register arrays dynamically, which demotes them to local memory -- measured: 8 LDL per element loop)
     double la = -CUDART_INF, lm = CUDART_INF;
-    int la_pos = -1, la_k = 0;
+    int la_pos = -1, la_col = 0, la_fl = 0, la_slot = 0;
     auto scan_elem = [&](int k) {
         const int f = fl[k];
         const double mv = m[k];
-        if ((f & F_UP) && (mv > la || (mv == la && pos[k] > la_pos))) { la = mv; la_pos = pos[k]; la_k = k; }
+        if ((f & F_UP) && (mv > la || (mv == la && pos[k] > la_pos))) { la = mv; la_pos = pos[k]; la_col = colr[k]; la_fl = f; la_slot = k * NT + tid; }
         if (f & F_LOW) lm = fmin(lm, mv);
     };
     auto local_scan = [&]() {
-        la = -CUDART_INF; lm = CUDART_INF; la_pos = -1; la_k = 0;
+        la = -CUDART_INF; lm = CUDART_INF; la_pos = -1;
 #pragma unroll
         for (int k = 0; k < KPT; k++)
             if (pos[k] < active) scan_elem(k);
@@ -259,84 +268,92 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
     };
 
     // ---------------- select_working_set (svm.cpp:946-1047) ----------------
-    // Warp-level all-gather, no CTA barrier: every warp reduces its own elements, its winner lane writes the warp's record
-    // into slot (rank*NW + warp) of EVERY CTA of the cluster (st.async; bytes counted on each receiver's mbarrier), and
-    // every warp of every CTA then reduces the same R = CL*NW records.  Stage A, stage B and the rare exact tie-break
-    // each own a record array and an mbarrier; a warp sends its stage-(s+1) record only after it has read all stage-s
-    // records, so a slot is never overwritten while any warp can still read it (stages strictly alternate).
-    auto send_record = [&](unsigned slot_base, unsigned bar, int words, const unsigned (&v)[12]) {
-        const unsigned slot = slot_base + (unsigned)((int)rank * NW + warp) * (unsigned)words * 4u;
-#pragma unroll
-        for (int c = 0; c < CL; c++) {
-            const unsigned ra = mapa_u32(slot, (unsigned)c), rb = mapa_u32(bar, (unsigned)c);
-            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
-                         ::"r"(ra), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(rb) : "memory");
-            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
-                         ::"r"(ra + 16u), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(rb) : "memory");
-            if (words == 12)
-                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
-                             ::"r"(ra + 32u), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(rb) : "memory");
-        }
+    // Two-level arg-reduction without CTA or cluster barriers.  Every warp reduces its own elements (REDUX); its winner
+    // lane stores the warp's record in LOCAL shared memory and the warp arrives on a named barrier.  The leader warp
+    // (warp 0) reduces the NW records, st.async-sends the CTA's record to every CTA of the cluster (bytes counted on each
+    // receiver's mbarrier), reduces the CL CTA records, and publishes the result in shared memory + a named barrier the
+    // workers are parked on.  Only the leader executes the combines and the scalar update: the other warps' issue slots stay free.
+    // Slot reuse is safe without further synchronisation: a warp writes its stage-(n+1) record only after it consumed the
+    // stage-n result, which the leader published after reading all stage-n records; a remote leader can send stage n+1
+    // only after a full B (or X) stage in between, which needs this CTA's leader to have passed stage n.
+    unsigned ph = 0;                                     // phase parity bit per hot mbarrier (index = HB_*)
+    auto hb_wait = [&](int b) {
+        mbar_wait(smem_u32(&hbar[b]), (ph >> b) & 1u);
+        ph ^= 1u << b;
     };
-    unsigned wphase = 0;                                 // bit s: parity the next wait on wbar[s] uses
-    auto stage_wait = [&](int sidx) {
-        mbar_wait(smem_u32(&wbar[sidx]), (wphase >> sidx) & 1u);
-        wphase ^= 1u << sidx;
+    // worker <-> leader hand-offs inside the CTA use HARDWARE named barriers (waiting warps are parked, not polling:
+    // fifteen warps spinning on an mbarrier starve the leader of issue slots -- measured 1.9k cycles per stage vs 0.6k)
+    auto nb_arrive = [&](int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(NT) : "memory"); };
+    auto nb_sync = [&](int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(NT) : "memory"); };
+    // leader: send the CTA record (W words, uniform registers c[]) to slot [rank] of every CTA, then wait for all CL records
+    auto leader_allgather = [&](unsigned slots_base, int W, const unsigned (&c)[12], int xb) {
+        const unsigned bar = smem_u32(&hbar[xb]);
+        const int chunks = W / 4;
+        if (lane == 0) mbar_expect_tx(bar, (unsigned)(CL * W * 4));
+        if (lane < CL * chunks) {
+            const int dst = lane / chunks, ch = lane % chunks;
+            const unsigned a0 = ch == 0 ? c[0] : (ch == 1 ? c[4] : c[8]);
+            const unsigned a1 = ch == 0 ? c[1] : (ch == 1 ? c[5] : c[9]);
+            const unsigned a2 = ch == 0 ? c[2] : (ch == 1 ? c[6] : c[10]);
+            const unsigned a3 = ch == 0 ? c[3] : (ch == 1 ? c[7] : c[11]);
+            const unsigned ra = mapa_u32(slots_base + (unsigned)((int)rank * W + ch * 4) * 4u, (unsigned)dst);
+            const unsigned rb = mapa_u32(bar, (unsigned)dst);
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                         ::"r"(ra), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(rb) : "memory");
+        }
+        hb_wait(xb);
     };
 
     int pi = -1, pj = -1, col_i = 0, col_j = 0;          // packed (position << 5 | flags), dataset rows
-    double gmax = 0, mg_j = 0, k_ij = 0, alpha_i = 0, alpha_j = 0;
+    double gmax = 0, mg_j = 0, k_ij = 0, alpha_i = 0, alpha_j = 0;      // mg_j, k_ij, alpha_*: valid in the leader warp only
     auto select = [&]() -> bool {
-        double gmax2;
         {   // ---- stage A: i = argmax m over I_up, Gmax2 = max -m over I_low ----
             const unsigned long long key = dkey(la);
-            const int la_idx = la_pos >= 0 ? (la_pos << IDX_SHIFT) : -1;             // the sender adds the flags
+            const int la_idx = la_pos >= 0 ? (la_pos << IDX_SHIFT) : -1;             // the winner lane adds the flags
             const KArg w = warp_argmax((unsigned)(key >> 32), (unsigned)key, la_idx);
             const unsigned long long km = warp_keymax(dkey(-lm));
-            if (tid == 0) mbar_expect_tx(smem_u32(&wbar[0]), R * 32);
             if (w.idx >= 0 ? la_idx == w.idx : lane == 0) {                          // exactly one lane per warp
-                int c = colr[0], f = fl[0];
-#pragma unroll
-                for (int k = 1; k < KPT; k++) { c = k == la_k ? colr[k] : c; f = k == la_k ? fl[k] : f; }
-                const double av = alpha[la_k * NT + tid];
-                unsigned v[12];
-                v[0] = w.hi; v[1] = w.lo; v[2] = w.idx >= 0 ? (unsigned)(w.idx | f) : 0xffffffffu;
-                v[3] = (unsigned)(km >> 32); v[4] = (unsigned)km; v[5] = lo32(av); v[6] = hi32(av); v[7] = (unsigned)c;
-                v[8] = v[9] = v[10] = v[11] = 0u;
-                send_record(smem_u32(&wxA[0][0]), smem_u32(&wbar[0]), 8, v);
+                const int c = la_col, f = la_fl;
+                const double av = w.idx >= 0 ? alpha[la_slot] : 0.0;
+                *reinterpret_cast<uint4 *>(&hot.recA[warp][0]) =
+                    make_uint4(w.hi, w.lo, w.idx >= 0 ? (unsigned)(w.idx | f) : 0xffffffffu, (unsigned)(km >> 32));
+                *reinterpret_cast<uint4 *>(&hot.recA[warp][4]) = make_uint4((unsigned)km, lo32(av), hi32(av), (unsigned)c);
             }
+            __syncwarp();
             tick(0);
-            stage_wait(0);
-            // every warp reduces all R records: lane-local best of its RPL records, then REDUX
-            unsigned bh = 0u, bl = 0u; int bi = -1, br = 0;
-            unsigned long long kml = 0ull;
-#pragma unroll
-            for (int q = 0; q < RPL; q++) {
-                const int r = lane + 32 * q;
-                if (r < R) {
-                    const uint4 x = *reinterpret_cast<const uint4 *>(&wxA[r][0]);
-                    const unsigned k4 = wxA[r][4];
-                    const int xi = (int)x.z;
-                    if (xi >= 0 && (x.x > bh || (x.x == bh && (x.y > bl || (x.y == bl && xi > bi))))) { bh = x.x; bl = x.y; bi = xi; br = r; }
-                    const unsigned long long k2 = ((unsigned long long)x.w << 32) | k4;
-                    kml = k2 > kml ? k2 : kml;
-                }
-            }
-            const KArg a = warp_argmax(bh, bl, bi);
-            const unsigned long long km2 = warp_keymax(kml);
-            pi = a.idx;
-            if (pi >= 0) {
-                const int wl = __ffs(__ballot_sync(0xffffffffu, bi == a.idx)) - 1;
-                const int rw = __shfl_sync(0xffffffffu, br, wl);
-                const uint4 y = *reinterpret_cast<const uint4 *>(&wxA[rw][4]);           // km lo | alpha lo | alpha hi | col
-                alpha_i = mk64(y.y, y.z);
-                col_i = (int)y.w;
-            }
-            gmax = dkey_inv(((unsigned long long)a.hi << 32) | a.lo);
-            gmax2 = dkey_inv(km2);
+            if (warp == 0) {
+                nb_sync(NB_LA);
+                const bool v = lane < NW;
+                uint4 x0 = make_uint4(0u, 0u, 0xffffffffu, 0u), x1 = make_uint4(0u, 0u, 0u, 0u);
+                if (v) { x0 = *reinterpret_cast<const uint4 *>(&hot.recA[lane][0]); x1 = *reinterpret_cast<const uint4 *>(&hot.recA[lane][4]); }
+                const KArg a = warp_argmax(x0.x, x0.y, (int)x0.z);
+                const unsigned long long km2 = warp_keymax(((unsigned long long)x0.w << 32) | x1.x);
+                const int wl = a.idx >= 0 ? __ffs(__ballot_sync(0xffffffffu, (int)x0.z == a.idx)) - 1 : 0;
+                unsigned c[12];
+                c[0] = a.hi; c[1] = a.lo; c[2] = (unsigned)a.idx; c[3] = (unsigned)(km2 >> 32); c[4] = (unsigned)km2;
+                c[5] = __shfl_sync(0xffffffffu, x1.y, wl); c[6] = __shfl_sync(0xffffffffu, x1.z, wl); c[7] = __shfl_sync(0xffffffffu, x1.w, wl);
+                c[8] = c[9] = c[10] = c[11] = 0u;
+                leader_allgather(smem_u32(&hot.xA[0][0]), 8, c, HB_XA);
+                const bool vc = lane < CL;
+                uint4 y0 = make_uint4(0u, 0u, 0xffffffffu, 0u), y1 = make_uint4(0u, 0u, 0u, 0u);
+                if (vc) { y0 = *reinterpret_cast<const uint4 *>(&hot.xA[lane][0]); y1 = *reinterpret_cast<const uint4 *>(&hot.xA[lane][4]); }
+                const KArg g = warp_argmax(y0.x, y0.y, (int)y0.z);
+                const unsigned long long kg = warp_keymax(((unsigned long long)y0.w << 32) | y1.x);
+                const int gl = g.idx >= 0 ? __ffs(__ballot_sync(0xffffffffu, (int)y0.z == g.idx)) - 1 : 0;
+                alpha_i = mk64(__shfl_sync(0xffffffffu, y1.y, gl), __shfl_sync(0xffffffffu, y1.z, gl));
+                const int ci = (int)__shfl_sync(0xffffffffu, y1.w, gl);
+                const double gm = dkey_inv(((unsigned long long)g.hi << 32) | g.lo), gm2 = dkey_inv(kg);
+                const bool stop = g.idx < 0 || __dadd_rn(gm, gm2) < eps;              // svm.cpp:1040-1041
+                if (lane == 0)
+                    *reinterpret_cast<uint4 *>(&hot.resA[0]) = make_uint4(stop ? 0xffffffffu : (unsigned)g.idx, (unsigned)ci, lo32(gm), hi32(gm));
+                __syncwarp();
+                nb_arrive(NB_RA);
+            } else { nb_arrive(NB_LA); nb_sync(NB_RA); }
+            const uint4 r = *reinterpret_cast<const uint4 *>(&hot.resA[0]);
+            pi = (int)r.x; col_i = (int)r.y; gmax = mk64(r.z, r.w);
             tick(1);
         }
-        if (pi < 0 || __dadd_rn(gmax, gmax2) < eps) return true;              // svm.cpp:1040-1041
+        if (pi < 0) return true;
         // ---- stage B: j = argmin -(gd^2)/quad over I_low with gd > 0 (svm.cpp:980-1037) ----
         const double QDi = QDc(col_i);
         const float *__restrict__ Ki = K + (size_t)col_i * ldk;
@@ -364,7 +381,9 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
             }
         };
         unsigned b1k = 0u, b2k = 0u;                    // keys of the best and second-best candidate (0 = none)
-        int k1 = -1;
+        int idx1 = -1, c1v = 0, s1v = 0;                // the best candidate's packed index, column, state slot ...
+        float kq1 = 0.f;                                // ... K_i value
+        double m1v = 0.0;                               // ... and m
 #pragma unroll
         for (int k = 0; k < KPT; k++) {
             if (pos[k] < active) {
@@ -375,79 +394,80 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
                     const bool gt = key > b1k;
                     b2k = gt ? b1k : max(b2k, key);
                     b1k = gt ? key : b1k;
-                    k1 = gt ? k : k1;
+                    if (gt) { idx1 = (pos[k] << IDX_SHIFT) | f; c1v = colr[k]; s1v = k * NT + tid; kq1 = kvi[k]; m1v = m[k]; }
                 }
             }
         }
-        // winner payload of this thread (selected lazily: only the sender lane needs it)
-        auto payload = [&](int kk, unsigned (&v)[12]) {
-            int cc = colr[0];
-            float kq = kvi[0];
-            double mm = m[0];
-#pragma unroll
-            for (int k = 1; k < KPT; k++) { const bool s_ = k == kk; cc = s_ ? colr[k] : cc; kq = s_ ? kvi[k] : kq; mm = s_ ? m[k] : mm; }
-            const double qq = widen(kq), av = alpha[kk * NT + tid];
-            v[3] = (unsigned)cc; v[4] = lo32(mm); v[5] = hi32(mm); v[6] = lo32(qq); v[7] = hi32(qq); v[8] = lo32(av); v[9] = hi32(av);
-            v[10] = v[11] = 0u;
+        // record of one candidate element: words 3.. = col | m | K_i (widened) | alpha
+        auto store_record = [&](unsigned (*rec)[12], int cc, int slot, float kq, double mm, unsigned w0, unsigned w1, unsigned w2, bool has) {
+            const double qq = widen(kq), av = has ? alpha[slot] : 0.0;
+            *reinterpret_cast<uint4 *>(&rec[warp][0]) = make_uint4(w0, w1, w2, (unsigned)cc);
+            *reinterpret_cast<uint4 *>(&rec[warp][4]) = make_uint4(lo32(mm), hi32(mm), lo32(qq), hi32(qq));
+            *reinterpret_cast<uint2 *>(&rec[warp][8]) = make_uint2(lo32(av), hi32(av));
         };
-        int idx1 = -1;
-        if (k1 >= 0) {
-            int p1 = pos[0], f1 = fl[0];
-#pragma unroll
-            for (int k = 1; k < KPT; k++) { const bool s_ = k == k1; p1 = s_ ? pos[k] : p1; f1 = s_ ? fl[k] : f1; }
-            idx1 = (p1 << IDX_SHIFT) | f1;
-        }
-        unsigned top1k, top2k;
+        int mode;                                        // 0: j chosen; 1: exact tie-break needed; -1: no j (Gmin_idx == -1)
+        unsigned thrk;
         {
             const unsigned w1 = __reduce_max_sync(0xffffffffu, b1k);
             const int widx = __reduce_max_sync(0xffffffffu, (b1k == w1) ? idx1 : -1);
             const unsigned w2 = __reduce_max_sync(0xffffffffu, (idx1 == widx) ? b2k : b1k);
-            if (tid == 0) mbar_expect_tx(smem_u32(&wbar[1]), R * 48);
             if (widx >= 0 ? idx1 == widx : lane == 0) {
-                unsigned v[12];
-                if (widx >= 0) payload(k1, v);
-                else { v[3] = v[4] = v[5] = v[6] = v[7] = v[8] = v[9] = v[10] = v[11] = 0u; }
-                v[0] = w1; v[1] = (unsigned)widx; v[2] = w2;
-                send_record(smem_u32(&wxB[0][0]), smem_u32(&wbar[1]), 12, v);
+                store_record(hot.recB, c1v, s1v, kq1, m1v, w1, (unsigned)widx, w2, widx >= 0);
             }
+            __syncwarp();
             tick(3);
-            stage_wait(1);
-            unsigned bk = 0u; int bi = -1, br = 0;
-#pragma unroll
-            for (int q = 0; q < RPL; q++) {
-                const int r = lane + 32 * q;
-                if (r < R) {
-                    const uint2 x = *reinterpret_cast<const uint2 *>(&wxB[r][0]);
-                    const int xi = (int)x.y;
-                    if (xi >= 0 && (x.x > bk || (x.x == bk && xi > bi))) { bk = x.x; bi = xi; br = r; }
+            if (warp == 0) {
+                nb_sync(NB_LB);
+                const bool v = lane < NW;
+                uint4 x0 = make_uint4(0u, 0xffffffffu, 0u, 0u), x1 = make_uint4(0u, 0u, 0u, 0u);
+                uint2 x2 = make_uint2(0u, 0u);
+                if (v) {
+                    x0 = *reinterpret_cast<const uint4 *>(&hot.recB[lane][0]); x1 = *reinterpret_cast<const uint4 *>(&hot.recB[lane][4]);
+                    x2 = *reinterpret_cast<const uint2 *>(&hot.recB[lane][8]);
                 }
-            }
-            top1k = __reduce_max_sync(0xffffffffu, bk);
-            pj = __reduce_max_sync(0xffffffffu, (bk == top1k) ? bi : -1);
-            if (pj < 0) return true;                                               // Gmin_idx == -1
-            unsigned sk = 0u;                                                       // runner-up: best b1 of the others, b2 of the winner
-#pragma unroll
-            for (int q = 0; q < RPL; q++) {
-                const int r = lane + 32 * q;
-                if (r < R) {
-                    const unsigned kk = (int)wxB[r][1] == pj ? wxB[r][2] : ((int)wxB[r][1] >= 0 ? wxB[r][0] : 0u);
-                    sk = kk > sk ? kk : sk;
+                const unsigned c1 = __reduce_max_sync(0xffffffffu, (int)x0.y >= 0 ? x0.x : 0u);
+                const int cidx = __reduce_max_sync(0xffffffffu, ((int)x0.y >= 0 && x0.x == c1) ? (int)x0.y : -1);
+                const unsigned c2 = __reduce_max_sync(0xffffffffu, (int)x0.y == cidx ? x0.z : ((int)x0.y >= 0 ? x0.x : 0u));
+                const int wl = cidx >= 0 ? __ffs(__ballot_sync(0xffffffffu, (int)x0.y == cidx)) - 1 : 0;
+                unsigned c[12];
+                c[0] = c1; c[1] = (unsigned)cidx; c[2] = c2; c[3] = __shfl_sync(0xffffffffu, x0.w, wl);
+                c[4] = __shfl_sync(0xffffffffu, x1.x, wl); c[5] = __shfl_sync(0xffffffffu, x1.y, wl);
+                c[6] = __shfl_sync(0xffffffffu, x1.z, wl); c[7] = __shfl_sync(0xffffffffu, x1.w, wl);
+                c[8] = __shfl_sync(0xffffffffu, x2.x, wl); c[9] = __shfl_sync(0xffffffffu, x2.y, wl); c[10] = c[11] = 0u;
+                leader_allgather(smem_u32(&hot.xB[0][0]), 12, c, HB_XB);
+                const bool vc = lane < CL;
+                uint4 y0 = make_uint4(0u, 0xffffffffu, 0u, 0u), y1 = make_uint4(0u, 0u, 0u, 0u);
+                uint2 y2 = make_uint2(0u, 0u);
+                if (vc) {
+                    y0 = *reinterpret_cast<const uint4 *>(&hot.xB[lane][0]); y1 = *reinterpret_cast<const uint4 *>(&hot.xB[lane][4]);
+                    y2 = *reinterpret_cast<const uint2 *>(&hot.xB[lane][8]);
                 }
-            }
-            top2k = __reduce_max_sync(0xffffffffu, sk);
-            const int wl = __ffs(__ballot_sync(0xffffffffu, bi == pj)) - 1;
-            const int rw = __shfl_sync(0xffffffffu, br, wl);
-            const uint4 y = *reinterpret_cast<const uint4 *>(&wxB[rw][4]);             // mg lo hi | kv lo hi
-            const uint2 z = *reinterpret_cast<const uint2 *>(&wxB[rw][8]);             // alpha lo hi
-            col_j = (int)wxB[rw][3];
-            mg_j = mk64(y.x, y.y); k_ij = mk64(y.z, y.w); alpha_j = mk64(z.x, z.y);
+                const unsigned top1k = __reduce_max_sync(0xffffffffu, (int)y0.y >= 0 ? y0.x : 0u);
+                const int gj = __reduce_max_sync(0xffffffffu, ((int)y0.y >= 0 && y0.x == top1k) ? (int)y0.y : -1);
+                const unsigned top2k = __reduce_max_sync(0xffffffffu, (int)y0.y == gj ? y0.z : ((int)y0.y >= 0 ? y0.x : 0u));
+                const int gl = gj >= 0 ? __ffs(__ballot_sync(0xffffffffu, (int)y0.y == gj)) - 1 : 0;
+                const int cj = (int)__shfl_sync(0xffffffffu, y0.w, gl);
+                mg_j = mk64(__shfl_sync(0xffffffffu, y1.x, gl), __shfl_sync(0xffffffffu, y1.y, gl));
+                k_ij = mk64(__shfl_sync(0xffffffffu, y1.z, gl), __shfl_sync(0xffffffffu, y1.w, gl));
+                alpha_j = mk64(__shfl_sync(0xffffffffu, y2.x, gl), __shfl_sync(0xffffffffu, y2.y, gl));
+                const bool tiny = FAST && top1k <= KEY_TINY;
+                const int md = gj < 0 ? -1 : ((top1k - top2k <= BAND || tiny) ? 1 : 0);
+                const unsigned th = (top1k > BAND && !tiny) ? top1k - BAND : 1u;
+                if (lane == 0)
+                    *reinterpret_cast<uint4 *>(&hot.resB1[0]) = make_uint4((unsigned)gj, (unsigned)cj, (unsigned)md, th);
+                __syncwarp();
+                nb_arrive(NB_RB1);
+            } else { nb_arrive(NB_LB); nb_sync(NB_RB1); }
+            const uint4 r = *reinterpret_cast<const uint4 *>(&hot.resB1[0]);
+            pj = (int)r.x; col_j = (int)r.y; mode = (int)r.z; thrk = r.w;
             tick(4);
         }
-        if (top1k - top2k <= BAND || (FAST && top1k <= KEY_TINY)) {
+        if (mode < 0) return true;                                               // Gmin_idx == -1
+        if (mode == 1) {
             // ---- exact tie-break: libsvm's correctly rounded quotients for every element in the band (rare) ----
-            const unsigned thrk = (top1k > BAND && !(FAST && top1k <= KEY_TINY)) ? top1k - BAND : 1u;
-            double bestn = -CUDART_INF;
-            int bidx = -1, bk_ = 0;
+            double bestn = -CUDART_INF, mbv = 0.0;
+            int bidx = -1, cbv = 0, sbv = 0;
+            float kqb = 0.f;
 #pragma unroll
             for (int k = 0; k < KPT; k++) {
                 if (pos[k] < active) {
@@ -459,40 +479,54 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
                             const double g2 = __dmul_rn(gd, gd);
                             const double nod = quad > 0 ? __ddiv_rn(g2, quad) : __ddiv_rn(g2, TAU);   // == -obj_diff
                             const int cand = (pos[k] << IDX_SHIFT) | f;
-                            if (nod > bestn || (nod == bestn && cand > bidx)) { bestn = nod; bidx = cand; bk_ = k; }
+                            if (nod > bestn || (nod == bestn && cand > bidx)) { bestn = nod; bidx = cand; cbv = colr[k]; sbv = k * NT + tid; kqb = kvi[k]; mbv = m[k]; }
                         }
                     }
                 }
             }
             const unsigned long long key = dkey(bestn);
             const KArg w = warp_argmax((unsigned)(key >> 32), (unsigned)key, bidx);
-            if (tid == 0) mbar_expect_tx(smem_u32(&wbar[2]), R * 48);
             if (w.idx >= 0 ? bidx == w.idx : lane == 0) {
-                unsigned v[12];
-                if (w.idx >= 0) payload(bk_, v);
-                else { v[3] = v[4] = v[5] = v[6] = v[7] = v[8] = v[9] = v[10] = v[11] = 0u; }
-                v[0] = w.hi; v[1] = (unsigned)w.idx; v[2] = w.lo;
-                send_record(smem_u32(&wxX[0][0]), smem_u32(&wbar[2]), 12, v);
+                store_record(hot.recX, cbv, sbv, kqb, mbv, w.hi, (unsigned)w.idx, w.lo, w.idx >= 0);
             }
-            stage_wait(2);
-            unsigned bh = 0u, bl = 0u; int bi = -1, br = 0;
-#pragma unroll
-            for (int q = 0; q < RPL; q++) {
-                const int r = lane + 32 * q;
-                if (r < R) {
-                    const uint4 x = *reinterpret_cast<const uint4 *>(&wxX[r][0]);       // hi | idx | lo | col
-                    const int xi = (int)x.y;
-                    if (xi >= 0 && (x.x > bh || (x.x == bh && (x.z > bl || (x.z == bl && xi > bi))))) { bh = x.x; bl = x.z; bi = xi; br = r; }
+            __syncwarp();
+            if (warp == 0) {
+                nb_sync(NB_LX);
+                const bool v = lane < NW;
+                uint4 x0 = make_uint4(0u, 0xffffffffu, 0u, 0u), x1 = make_uint4(0u, 0u, 0u, 0u);
+                uint2 x2 = make_uint2(0u, 0u);
+                if (v) {
+                    x0 = *reinterpret_cast<const uint4 *>(&hot.recX[lane][0]); x1 = *reinterpret_cast<const uint4 *>(&hot.recX[lane][4]);
+                    x2 = *reinterpret_cast<const uint2 *>(&hot.recX[lane][8]);
                 }
-            }
-            const KArg b = warp_argmax(bh, bl, bi);
-            pj = b.idx;                                                         // >= 0: the approximate winner is in the band
-            const int wl = __ffs(__ballot_sync(0xffffffffu, bi == pj)) - 1;
-            const int rw = __shfl_sync(0xffffffffu, br, wl);
-            const uint4 y = *reinterpret_cast<const uint4 *>(&wxX[rw][4]);
-            const uint2 z = *reinterpret_cast<const uint2 *>(&wxX[rw][8]);
-            col_j = (int)wxX[rw][3];
-            mg_j = mk64(y.x, y.y); k_ij = mk64(y.z, y.w); alpha_j = mk64(z.x, z.y);
+                const KArg a = warp_argmax(x0.x, x0.z, (int)x0.y);
+                const int wl = a.idx >= 0 ? __ffs(__ballot_sync(0xffffffffu, (int)x0.y == a.idx)) - 1 : 0;
+                unsigned c[12];
+                c[0] = a.hi; c[1] = (unsigned)a.idx; c[2] = a.lo; c[3] = __shfl_sync(0xffffffffu, x0.w, wl);
+                c[4] = __shfl_sync(0xffffffffu, x1.x, wl); c[5] = __shfl_sync(0xffffffffu, x1.y, wl);
+                c[6] = __shfl_sync(0xffffffffu, x1.z, wl); c[7] = __shfl_sync(0xffffffffu, x1.w, wl);
+                c[8] = __shfl_sync(0xffffffffu, x2.x, wl); c[9] = __shfl_sync(0xffffffffu, x2.y, wl); c[10] = c[11] = 0u;
+                leader_allgather(smem_u32(&hot.xX[0][0]), 12, c, HB_XX);
+                const bool vc = lane < CL;
+                uint4 y0 = make_uint4(0u, 0xffffffffu, 0u, 0u), y1 = make_uint4(0u, 0u, 0u, 0u);
+                uint2 y2 = make_uint2(0u, 0u);
+                if (vc) {
+                    y0 = *reinterpret_cast<const uint4 *>(&hot.xX[lane][0]); y1 = *reinterpret_cast<const uint4 *>(&hot.xX[lane][4]);
+                    y2 = *reinterpret_cast<const uint2 *>(&hot.xX[lane][8]);
+                }
+                const KArg g = warp_argmax(y0.x, y0.z, (int)y0.y);
+                const int gl = g.idx >= 0 ? __ffs(__ballot_sync(0xffffffffu, (int)y0.y == g.idx)) - 1 : 0;   // >= 0: the approximate winner is in the band
+                const int cj = (int)__shfl_sync(0xffffffffu, y0.w, gl);
+                mg_j = mk64(__shfl_sync(0xffffffffu, y1.x, gl), __shfl_sync(0xffffffffu, y1.y, gl));
+                k_ij = mk64(__shfl_sync(0xffffffffu, y1.z, gl), __shfl_sync(0xffffffffu, y1.w, gl));
+                alpha_j = mk64(__shfl_sync(0xffffffffu, y2.x, gl), __shfl_sync(0xffffffffu, y2.y, gl));
+                if (lane == 0)
+                    *reinterpret_cast<uint2 *>(&hot.resX[0]) = make_uint2((unsigned)g.idx, (unsigned)cj);
+                __syncwarp();
+                nb_arrive(NB_RX);
+            } else { nb_arrive(NB_LX); nb_sync(NB_RX); }
+            const uint2 r = *reinterpret_cast<const uint2 *>(&hot.resX[0]);
+            pj = (int)r.x; col_j = (int)r.y;
         }
         return false;
     };
@@ -620,16 +654,14 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
         float kvj[KPT];
 #pragma unroll
         for (int k = 0; k < KPT; k++) kvj[k] = pos[k] < active ? __ldg(Kj + colr[k]) : 0.f;     // in flight during the scalar update
-        // analytic two-variable update, computed redundantly (and identically) by every thread: no broadcast, no barrier
-        double a, b, ai = alpha_i, aj = alpha_j;
-        int sti, stj;
-        {
+        if (warp == 0) {                                         // leader: analytic two-variable update, published to the workers
             const double C = Cc;
             const bool yi = (pi & F_YPOS) != 0, yj = (pj & F_YPOS) != 0;
             const double Gi = yi ? -gmax : gmax;                 // G = -y m (exact)
             const double Gj = yj ? -mg_j : mg_j;
             const double QDi = QDc(col_i), QDj = QDc(col_j);
             const double Qij = (yi == yj) ? k_ij : -k_ij;        // signed Q_i[j]
+            double ai = alpha_i, aj = alpha_j;
             if (yi != yj) {                                      // svm.cpp:772-815
                 double quad = __dadd_rn(__dadd_rn(QDi, QDj), __dmul_rn(2.0, Qij));
                 if (quad <= 0) quad = TAU;
@@ -651,21 +683,32 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
                 if (sum > C) { if (aj > C) { aj = C; ai = __dsub_rn(sum, C); } }
                 else         { if (ai < 0) { ai = 0; aj = sum; } }
             }
-            const double dai = __dsub_rn(ai, alpha_i), daj = __dsub_rn(aj, alpha_j);
-            a = yi ? -dai : dai;                                 // a = -y_i dalpha_i
-            b = yj ? -daj : daj;                                 // b = -y_j dalpha_j
-            sti = ai >= C ? ST_UPPER : (ai <= 0 ? ST_LOWER : ST_FREE);
-            stj = aj >= C ? ST_UPPER : (aj <= 0 ? ST_LOWER : ST_FREE);
-        }
+            if (lane == 0) {
+                const double dai = __dsub_rn(ai, alpha_i), daj = __dsub_rn(aj, alpha_j);
+                const double av = yi ? -dai : dai, bv = yj ? -daj : daj;       // a = -y_i dalpha_i, b = -y_j dalpha_j
+                const int si = ai >= C ? ST_UPPER : (ai <= 0 ? ST_LOWER : ST_FREE), sj = aj >= C ? ST_UPPER : (aj <= 0 ? ST_LOWER : ST_FREE);
+                *reinterpret_cast<uint4 *>(&hot.resB2[0]) = make_uint4(lo32(av), hi32(av), lo32(bv), hi32(bv));
+                *reinterpret_cast<uint4 *>(&hot.resB2[4]) = make_uint4(lo32(ai), hi32(ai), lo32(aj), hi32(aj));
+                *reinterpret_cast<uint2 *>(&hot.resB2[8]) = make_uint2((unsigned)si, (unsigned)sj);
+            }
+            __syncwarp();
+            nb_arrive(NB_RB2);
+        } else nb_sync(NB_RB2);
         tick(5);
+        const uint4 u0 = *reinterpret_cast<const uint4 *>(&hot.resB2[0]);
+        const uint4 u1 = *reinterpret_cast<const uint4 *>(&hot.resB2[4]);
+        const uint2 u2 = *reinterpret_cast<const uint2 *>(&hot.resB2[8]);
+        const double a = mk64(u0.x, u0.y), b = mk64(u0.z, u0.w);
+        const int sti = (int)u2.x, stj = (int)u2.y;
+        tick(6);
         // the owners of i and j take the new alpha and status FIRST: the fused scan below must see the new sets
 #pragma unroll
         for (int k = 0; k < KPT; k++) {
-            if (pos[k] == i) { alpha[k * NT + tid] = ai; fl[k] = mkflags((pi & F_YPOS) != 0, sti); }
-            if (pos[k] == j) { alpha[k * NT + tid] = aj; fl[k] = mkflags((pj & F_YPOS) != 0, stj); }
+            if (pos[k] == i) { alpha[k * NT + tid] = mk64(u1.x, u1.y); fl[k] = mkflags((pi & F_YPOS) != 0, sti); }
+            if (pos[k] == j) { alpha[k * NT + tid] = mk64(u1.z, u1.w); fl[k] = mkflags((pj & F_YPOS) != 0, stj); }
         }
         // m update over the active set (svm.cpp:866-872), fused with the next iteration's local scan
-        la = -CUDART_INF; lm = CUDART_INF; la_pos = -1; la_k = 0;
+        la = -CUDART_INF; lm = CUDART_INF; la_pos = -1;
 #pragma unroll
         for (int k = 0; k < KPT; k++) {
             if (pos[k] < active) {
@@ -810,15 +853,20 @@ cudaError_t launch_smo_colown(const SmoProblem *d_probs, const int *d_order, int
     int nt = 0;
     if (const char *e = getenv("B200GS_SMO_NT")) nt = atoi(e);                  // development switch
     // 512 threads at most: the register-resident state needs more than the 64 registers a 1024-thread CTA leaves a thread
-    if (cl == 2) return launch_co_f<512, 8, 2>(d_probs, d_order, n_prob, lmax, fast, st);
+    if (cl == 2) {
+        if (nt == 1024) return launch_co_f<1024, 4, 2>(d_probs, d_order, n_prob, lmax, fast, st);
+        return launch_co_f<512, 8, 2>(d_probs, d_order, n_prob, lmax, fast, st);
+    }
     if (cl == 4) {
         if (lmax > 8192) return launch_co_f<512, 8, 4>(d_probs, d_order, n_prob, lmax, fast, st);
         if (nt == 256) return launch_co_f<256, 8, 4>(d_probs, d_order, n_prob, lmax, fast, st);
+        if (nt == 1024) return launch_co_f<1024, 2, 4>(d_probs, d_order, n_prob, lmax, fast, st);
         return launch_co_f<512, 4, 4>(d_probs, d_order, n_prob, lmax, fast, st);
     }
     if (cl == 8) {
         if (lmax > 8192) return launch_co_f<512, 4, 8>(d_probs, d_order, n_prob, lmax, fast, st);
         if (nt == 512) return launch_co_f<512, 2, 8>(d_probs, d_order, n_prob, lmax, fast, st);
+        if (nt == 1024) return launch_co_f<1024, 1, 8>(d_probs, d_order, n_prob, lmax, fast, st);
         return launch_co_f<256, 4, 8>(d_probs, d_order, n_prob, lmax, fast, st);
     }
     return cudaErrorInvalidValue;

@@ -1,4 +1,4 @@
-// smo_common.cuh -- helpers shared by the single-CTA (smo.cu) and the cluster (smo_cluster.cu) SMO kernels.
+// smo_common.cuh -- helpers shared by the single-CTA (smo.cu) and the cluster (smo_colown.cu) SMO kernels.
 #pragma once
 #include "common.cuh"
 #include <math_constants.h>

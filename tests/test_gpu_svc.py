@@ -160,15 +160,12 @@ def test_python_api_iris(engine):
     assert clf.estimator.get_params() == clone(svm.SVC(gamma='auto')).get_params()   # the reference's assertion
 
 
-@pytest.mark.parametrize("co", [1, 0])
 @pytest.mark.parametrize("cl", [2, 4, 8])
-def test_cluster_smo_bitexact(engine, monkeypatch, cl, co):
-    """Every sub-problem through a thread-block-cluster solver (one problem over 2 / 4 / 8 SMs, DSMEM exchange) --
-    co=1: static element ownership with register state (smo_colown.cu), co=0: position-owned state (smo_cluster.cu):
-    same trajectory, same scores as scikit-learn."""
-    monkeypatch.setenv("B200GS_SMO_CO", str(co))
+def test_cluster_smo_bitexact(engine, monkeypatch, cl):
+    """Every sub-problem through the thread-block-cluster solver (smo_colown.cu: one problem over 2 / 4 / 8 SMs, static
+    element ownership, DSMEM record exchange): same trajectory, same scores as scikit-learn."""
     monkeypatch.setenv("B200GS_SMO_CLUSTER", str(cl))
-    monkeypatch.setenv("B200GS_SMO_CLUSTER_PCT", "100")
+    monkeypatch.setenv("B200GS_SMO_CLUSTER_N", "100000")
     w, fold_id, ns = _setup(engine, "c2_mid")
     g = golden("c2_mid")
     r = _run(engine, w, W.candidates(w))
