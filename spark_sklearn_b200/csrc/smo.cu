@@ -50,7 +50,7 @@ template <int NT, int KPT, bool SMEM_STATE, bool FAST, bool PROF, bool ROWBUF>
 __global__ void __launch_bounds__(NT, 1)
 smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, int rowcap)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ Red red;
     constexpr int NW = NT / 32;
     constexpr int LCAP = NT * KPT;                                          // compile-time layout: no address math
@@ -73,7 +73,9 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
         col = reinterpret_cast<unsigned short *>(mG + LCAP);
     }
     unsigned char *const fl = reinterpret_cast<unsigned char *>(col + LCAP);
-    float *const rowbuf = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(fl + LCAP) + 127) & ~(uintptr_t)127);
+    // LCAP is a multiple of 128, so the row buffer starts 128-byte aligned; a pointer derived by plain arithmetic keeps
+    // the shared address space (an integer round-up made every gather a generic LD instead of LDS)
+    float *const rowbuf = reinterpret_cast<float *>(fl + LCAP);
     __shared__ unsigned long long rowbar;
     unsigned rowphase = 0;
     const float *__restrict__ const K = Pp->K;
