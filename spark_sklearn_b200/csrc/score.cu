@@ -11,19 +11,26 @@
 
 namespace {
 
-constexpr int TR = 64, TC = 32, TJ = 32;
+constexpr int TR = 64, TJ = 32;
 
+// TC = columns per block (multiple of 8).  The float64 exp of a (row, SV) pair is the expensive part (n^2 of them per
+// block row), so a block takes as many coefficient columns as the group has, up to 96 (static shared memory): the kernel values are computed once
+// per group instead of once per 32 columns.
+template <int TC>
 __global__ void __launch_bounds__(256)
 decision_kernel(const double *__restrict__ S, const double *__restrict__ xsq, int n, int kernel, double gamma,
                 const double *__restrict__ coef, int ncols, double *__restrict__ dec)
 {
+    constexpr int CPT = TC / 8;                       // columns per thread
     __shared__ __align__(16) double E[TJ][TR + 2];
     __shared__ __align__(16) double Cf[TJ][TC + 2];
     const int tid = threadIdx.x;
     const int r0 = blockIdx.x * TR, c0 = blockIdx.y * TC;
-    const int ty = tid >> 3, tx = tid & 7;          // rows ty*2..+1, cols tx*4..+3
+    const int ty = tid >> 3, tx = tid & 7;          // rows ty*2..+1, cols tx + 8*b
     const int lj = tid & 31, lr = tid >> 5;         // loader mapping
-    double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    double acc[2][CPT];
+#pragma unroll
+    for (int b = 0; b < CPT; b++) { acc[0][b] = 0.0; acc[1][b] = 0.0; }
     const double ng = -gamma;
 
     for (int j0 = 0; j0 < n; j0 += TJ) {
@@ -50,15 +57,15 @@ decision_kernel(const double *__restrict__ S, const double *__restrict__ xsq, in
             Cf[lj][lr + 8 * s] = (c < ncols && j < n) ? coef[(size_t)c * n + j] : 0.0;
         }
         __syncthreads();
-#pragma unroll
+#pragma unroll 8
         for (int k = 0; k < TJ; k++) {
             const double2 e = *reinterpret_cast<const double2 *>(&E[k][ty * 2]);
-            const double2 ca = *reinterpret_cast<const double2 *>(&Cf[k][tx * 4]);
-            const double2 cb = *reinterpret_cast<const double2 *>(&Cf[k][tx * 4 + 2]);
-            acc[0][0] = fma(e.x, ca.x, acc[0][0]); acc[0][1] = fma(e.x, ca.y, acc[0][1]);
-            acc[0][2] = fma(e.x, cb.x, acc[0][2]); acc[0][3] = fma(e.x, cb.y, acc[0][3]);
-            acc[1][0] = fma(e.y, ca.x, acc[1][0]); acc[1][1] = fma(e.y, ca.y, acc[1][1]);
-            acc[1][2] = fma(e.y, cb.x, acc[1][2]); acc[1][3] = fma(e.y, cb.y, acc[1][3]);
+#pragma unroll
+            for (int b = 0; b < CPT; b++) {
+                const double cv = Cf[k][tx + 8 * b];
+                acc[0][b] = fma(e.x, cv, acc[0][b]);
+                acc[1][b] = fma(e.y, cv, acc[1][b]);
+            }
         }
         __syncthreads();
     }
@@ -67,8 +74,8 @@ decision_kernel(const double *__restrict__ S, const double *__restrict__ xsq, in
         const int r = r0 + ty * 2 + a;
         if (r >= n) continue;
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
-            const int c = c0 + tx * 4 + b;
+        for (int b = 0; b < CPT; b++) {
+            const int c = c0 + tx + 8 * b;
             if (c < ncols) dec[(size_t)c * n + r] = acc[a][b];
         }
     }
@@ -127,8 +134,11 @@ cudaError_t launch_decision(const double *S, const double *xsq, int n, int kerne
                             const double *coef, int ncols, double *dec, cudaStream_t st)
 {
     if (ncols <= 0) return cudaSuccess;
-    dim3 grid((n + TR - 1) / TR, (ncols + TC - 1) / TC);
-    decision_kernel<<<grid, 256, 0, st>>>(S, xsq, n, kernel, gamma, coef, ncols, dec);
+    const int tc = ncols <= 32 ? 32 : (ncols <= 64 ? 64 : 96);
+    dim3 grid((n + TR - 1) / TR, (ncols + tc - 1) / tc);
+    if (tc == 32) decision_kernel<32><<<grid, 256, 0, st>>>(S, xsq, n, kernel, gamma, coef, ncols, dec);
+    else if (tc == 64) decision_kernel<64><<<grid, 256, 0, st>>>(S, xsq, n, kernel, gamma, coef, ncols, dec);
+    else decision_kernel<96><<<grid, 256, 0, st>>>(S, xsq, n, kernel, gamma, coef, ncols, dec);
     return cudaGetLastError();
 }
 
