@@ -439,7 +439,7 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
         //   * throughput-bound searches (the predicted-longest problem is shorter than 0.9 x total work / SMs): no clusters;
         //   * otherwise the group of predicted near-longest problems (cost > 0.8 x the largest), at most half the SMs.
         //     (config 2: exactly the ten 66-68k-iteration problems; leaving ONE of them on a single SM costs +33 %.)
-        // Cluster launches go first, on the high-priority stream.  Development switches: B200GS_SMO_CLUSTER (0/2/4/8),
+        // Development switches: B200GS_SMO_CLUSTER (0/2/4/8),
         // B200GS_SMO_CLUSTER_N.
         std::string why;
         int cl = 0, n_cl = 0;
@@ -462,21 +462,26 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
         if (const char *e = getenv("B200GS_SMO_CLUSTER_N")) n_cl = std::min(np, atoi(e));
         if (!(cl == 2 || cl == 4 || cl == 8) || lmax > smo_colown_max_rows(cl) || lmax <= 2048) n_cl = 0;
         if (n_cl > 0) {
+            // The cluster launch must get its SMs before the single-CTA launch floods the GPU (a late start of the critical
+            // path costs the makespan that much: measured 292 vs 333 ms when the order of arrival flipped).  So the cluster
+            // kernel goes on the engine stream itself, in order behind the uploads; the single-CTA kernel goes on the second
+            // stream behind the same point plus a 30 us delay kernel, and the engine stream joins it again afterwards.
             cudaEvent_t ready, done;
             cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
             cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
             cudaEventRecord(ready, st);
-            cudaStreamWaitEvent(h->stream_hi, ready, 0);
-            cudaError_t ce = launch_smo_colown(d_probs, d_order, n_cl, lmax, cl, fast, h->stream_hi);
+            cudaError_t ce = launch_smo_colown(d_probs, d_order, n_cl, lmax, cl, fast, st);
             if (ce != cudaSuccess) { gs_set_error(h, std::string("launch_smo_colown: ") + cudaGetErrorString(ce)); return GS_ERR_CUDA; }
-            cudaEventRecord(done, h->stream_hi);
             pf.launches++;
             if (np - n_cl > 0) {
-                ce = launch_smo(d_probs, d_order + n_cl, np - n_cl, lmax, fast, (int)ldk, st, &why);
+                cudaStreamWaitEvent(h->stream_hi, ready, 0);
+                launch_delay(30000, h->stream_hi);
+                ce = launch_smo(d_probs, d_order + n_cl, np - n_cl, lmax, fast, (int)ldk, h->stream_hi, &why);
                 if (ce != cudaSuccess) { gs_set_error(h, why.empty() ? std::string("launch_smo: ") + cudaGetErrorString(ce) : why); return why.empty() ? GS_ERR_CUDA : GS_ERR_UNSUPPORTED; }
-                pf.launches++;
+                pf.launches += 2;
+                cudaEventRecord(done, h->stream_hi);
+                cudaStreamWaitEvent(st, done, 0);
             }
-            cudaStreamWaitEvent(st, done, 0);
             cudaEventDestroy(ready); cudaEventDestroy(done);
         } else {
             cudaError_t ce = launch_smo(d_probs, d_order, np, lmax, fast, (int)ldk, st, &why);

@@ -37,7 +37,7 @@ struct gs_handle {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream_hi = nullptr;   // high priority: cluster SMO launches (the critical-path problems)
+    cudaStream_t stream_hi = nullptr;   // second stream: the single-CTA SMO launch when a cluster launch runs beside it
     std::string err;
     // dataset (rows stored in INTERNAL order: sorted by class, then by original index)
     int64_t n = 0, d = 0;
@@ -90,6 +90,7 @@ cudaError_t launch_smo(const SmoProblem *d_probs, const int *d_order, int n_prob
 int smo_max_rows();   // largest sub-problem the resident-state kernel supports
 // smo_colown.cu: the same solver with one sub-problem spread over a thread-block cluster of cl CTAs (DSMEM exchange)
 int smo_colown_max_rows(int cl);
+void launch_delay(unsigned ns, cudaStream_t st);      // one thread sleeping ns nanoseconds (stream-ordering aid)
 cudaError_t launch_smo_colown(const SmoProblem *d_probs, const int *d_order, int n_prob, int lmax, int cl, bool fast, cudaStream_t st);
 
 // ---- score.cu ----

@@ -842,6 +842,17 @@ cudaError_t launch_co_f(const SmoProblem *p, const int *o, int n, int lmax, bool
 
 }  // namespace
 
+namespace {
+__global__ void delay_kernel(unsigned ns)
+{
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do { __nanosleep(1000); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); } while (t - t0 < ns);
+}
+}  // namespace
+
+void launch_delay(unsigned ns, cudaStream_t st) { delay_kernel<<<1, 1, 0, st>>>(ns); }
+
 // Largest sub-problem a column-owner cluster launch of size cl supports (0: unsupported cluster size)
 int smo_colown_max_rows(int cl) { return cl == 2 ? 8192 : ((cl == 4 || cl == 8) ? 16384 : 0); }
 

@@ -13,18 +13,9 @@ def run(tag, n, setdata):
     ts = []
     for _ in range(n):
         if setdata: eng.set_data(X, fold_id, 5, y_class=y.astype(np.int32))
-        eng.svc(["rbf"] * len(cands), Cs, G); p = eng.profile(); ts.append((round(p["ms_total"], 1), round(p["ms_solve"], 1)))
+        eng.svc(["rbf"] * len(cands), Cs, G); p = eng.profile(); ts.append({k[3:]: round(v, 1) for k, v in p.items() if k.startswith("ms_")})
     print(tag, ts, flush=True)
 eng.set_data(X, fold_id, 5, y_class=y.astype(np.int32))
 run("warm", 2, False)
 run("resident (no set_data)", 4, False)
 run("set_data each step", 4, True)
-proc = subprocess.Popen(["nvidia-smi", "-i", "0", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.DEVNULL)
-time.sleep(0.5)
-run("resident + nvidia-smi -lms 100", 4, False)
-run("set_data + nvidia-smi -lms 100", 3, True)
-proc.terminate()
-proc = subprocess.Popen(["nvidia-smi", "-i", "0", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader,nounits", "-lms", "1000"], stdout=subprocess.DEVNULL)
-time.sleep(0.5)
-run("resident + nvidia-smi -lms 1000", 4, False)
-proc.terminate()
