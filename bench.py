@@ -7,7 +7,7 @@
 A "step" is one pass of the hot path over the whole workload: every (candidate, fold) fit+score task of
 BASELINE config 2 -- GridSearchCV(SVC rbf) on synthetic 10000x512 fp32, C x gamma 8x8, cv=5 = 320 fits per
 GPU.  At N > 1 GPUs every rank holds the dataset and evaluates its own 64 candidates of a grid refined
-on the same ranges (N*64 candidates strided c -> c mod N): weak scaling, no data-path collective, one
+on the same ranges (N*64 candidates dealt to the ranks by predicted cost): weak scaling, no data-path collective, one
 all-gather of the score blocks per step (the counterpart of RDD.collect()).
 
 value  : fits/s with the dataset resident in HBM (gs_set_data done before the timed region); device time
@@ -145,6 +145,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON): libraries that print there (NCCL's version banner, joblib) go to stderr
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -158,7 +168,7 @@ def main():
     cfg = {"workload": "%s: GridSearchCV(%s %s), synthetic %dx%d fp32, %d candidates x cv=%d"
                        % (w["name"], w["estimator"], w["est_params"], w["X"].shape[0], w["X"].shape[1], len(cands), n_splits),
            "n_candidates": len(cands), "n_splits": n_splits, "fits_per_step": len(cands) * n_splits,
-           "parallelism": "candidates strided over %d GPU(s), dataset replicated, one score all-gather" % max(world, 1),
+           "parallelism": "candidates dealt by predicted cost over %d GPU(s), dataset replicated, one score all-gather" % max(world, 1),
            "l2": "inputs larger than L2 (float64 Gram 0.8 GB + float32 kernel matrices 0.4 GB each)", "refit": False}
 
     # ---------------- reference arm: the CPU path on the host cores (rank 0 only) ----------------
@@ -174,7 +184,7 @@ def main():
             tot += dt
             fits += nf
         v = fits / tot
-        print(json.dumps({
+        emit(({
             "impl": "reference", "metric": "candidate-fits/sec", "value": v, "unit": "fits/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": W_, "ms_per_step": 1e3 * tot / max(a.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
@@ -212,11 +222,12 @@ def main():
     splits = list(check_cv(w["cv"], y, classifier=is_classifier(est)).split(X, y))
     fold_id = fold_ids_from_splits(splits, len(y))
     plan = adapter_for(est).plan(est, cands, X, y, fold_id, len(splits))       # gs_set_data happens here
-    my = list(range(rank, len(cands), world))
+    parts = D.assign_candidates(len(cands), world, plan.costs() if world > 1 else None)    # same dealing as GridSearchCV.fit
+    my = parts[rank]
 
     def resident_step():
         local = plan.evaluate(my, return_train=True)
-        out = D.allgather_candidates(local, my, len(cands), len(splits), world)
+        out = D.allgather_candidates(local, my, len(cands), len(splits), world, parts)
         return out, plan.profile()
 
     for _ in range(W_):
@@ -312,7 +323,7 @@ def main():
         result["cpu_baseline"] = {"value": nf / dt, "unit": "fits/s", "cores": cores, "kind": "reference", "sample": desc,
                                   "seconds": dt,
                                   "max_abs_diff_mean_test_score_vs_gpu": float(np.max(np.abs(cpu_mean - gpu_mean)))}
-    print(json.dumps(result))
+    emit(result)
     if dist is not None:
         dist.destroy_process_group()
 

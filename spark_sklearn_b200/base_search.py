@@ -7,7 +7,7 @@ fold-minor task list (:56-61), ``_store`` aggregation with the ``iid`` test-size
 (:100-137), ``rankdata(-mean, 'min')`` (:123-125), masked ``param_*`` arrays (:145-156), refit
 (:165-174) -- except that the Spark fan-out ``parallelize(...).map(fun).collect()`` (:62-98) is ONE
 call into libb200gs.so that evaluates the whole task list on the GPU (``estimators.py``).
-With ``torch.distributed`` initialised (one process per GPU) the candidates are strided over the
+With ``torch.distributed`` initialised (one process per GPU) the candidates are dealt (by predicted cost) over the
 ranks and the per-candidate score blocks are exchanged with a single all-gather -- the
 counterpart of ``collect()``.
 """
@@ -82,10 +82,12 @@ class B200BaseSearchCV(BaseSearchCV):
 
         # ---- the fan-out: every (candidate, fold) task in one engine call per rank ----
         rank, world = _dist.rank_world()
-        my = list(range(rank, n_param_candidates, world))     # candidates strided c -> c mod G
         plan = adapter.plan(clone(estimator), candidate_params, X_arr, y_arr, fold_id, n_splits)
+        # candidates dealt to the GPUs by predicted cost (the reference leaves the placement of its tasks to Spark)
+        parts = _dist.assign_candidates(n_param_candidates, world, plan.costs() if world > 1 else None)
+        my = parts[rank]
         local = plan.evaluate(my, return_train=self.return_train_score, error_score=self.error_score)
-        out = _dist.allgather_candidates(local, my, n_param_candidates, n_splits, world)
+        out = _dist.allgather_candidates(local, my, n_param_candidates, n_splits, world, parts)
         test_scores, train_scores = out["test"], out["train"]
         fit_time, score_time = out["fit_time"], out["score_time"]
         self.device_profile_ = plan.profile()

@@ -1,4 +1,4 @@
-"""Multi-GPU plumbing: one process per GPU (torchrun), candidates strided over ranks, ONE all-gather
+"""Multi-GPU plumbing: one process per GPU (torchrun), candidates dealt to the ranks, ONE all-gather
 of the per-candidate score blocks -- the counterpart of ``RDD.collect()`` (reference
 base_search.py:89).  The data path has no other collective: tasks are independent (reference
 base_search.py:56-62 runs one Spark partition per task) and the dataset is replicated on every
@@ -20,16 +20,36 @@ def rank_world():
     return (td.get_rank(), td.get_world_size()) if td else (0, 1)
 
 
-def allgather_candidates(local, my, n_cand, n_splits, world):
+def assign_candidates(n_cand, world, costs=None):
+    """Candidate indices of every rank (list of ascending lists).  Without costs: strided, c -> c mod world.  With a
+    predicted cost per candidate: sorted by cost and dealt in snake order (0..W-1, W-1..0, ...), so that every rank
+    gets the same share of the expensive candidates -- the makespan of a search is set by its longest fits.
+    Deterministic and identical on every rank; each rank holds ceil or floor of n_cand / world candidates."""
+    if costs is None or world == 1:
+        return [list(range(r, n_cand, world)) for r in range(world)]
+    costs = np.asarray(costs, dtype=np.float64)
+    if costs.shape != (n_cand,) or not np.all(np.isfinite(costs)):
+        return [list(range(r, n_cand, world)) for r in range(world)]
+    order = np.argsort(-costs, kind="stable")
+    parts = [[] for _ in range(world)]
+    for pos, c in enumerate(order):
+        lap, k = divmod(pos, world)
+        parts[k if lap % 2 == 0 else world - 1 - k].append(int(c))
+    return [sorted(p) for p in parts]
+
+
+def allgather_candidates(local, my, n_cand, n_splits, world, parts=None):
     """local: dict of [len(my), n_splits] arrays (test, train|None, fit_time, score_time) for the
     candidates ``my`` of this rank.  Returns the same dict for all n_cand candidates, identical on
-    every rank and independent of the number of ranks."""
+    every rank and independent of the number of ranks.  ``parts`` = assign_candidates(...) (default: strided)."""
     keys = ["test", "train", "fit_time", "score_time"]
     if world == 1:
         return {k: local.get(k) for k in keys}
     import torch
     td = _td()
-    per = (n_cand + world - 1) // world                      # pad to equal counts
+    if parts is None:
+        parts = assign_candidates(n_cand, world)
+    per = max(len(p) for p in parts)                         # pad to equal counts
     buf = np.full((per, n_splits, len(keys)), np.nan)
     for j, k in enumerate(keys):
         if local.get(k) is not None and len(my):
@@ -46,7 +66,7 @@ def allgather_candidates(local, my, n_cand, n_splits, world):
             continue
         full = np.empty((n_cand, n_splits))
         for r in range(world):
-            idx = list(range(r, n_cand, world))
+            idx = parts[r]
             full[idx] = g[r, :len(idx), :, j]
         out[k] = full
     return out

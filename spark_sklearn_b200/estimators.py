@@ -82,6 +82,10 @@ class _Plan:
     def profile(self):
         return dict(self._prof)
 
+    def costs(self):
+        """Predicted relative cost of every candidate (None: all alike) -- used to balance candidates over GPUs."""
+        return None
+
     def close(self):
         pass
 
@@ -154,6 +158,24 @@ class SVCPlan(_Plan):
         if not (isinstance(g, numbers.Real) and g >= 0):
             raise ValueError("gamma must be >= 0 or 'scale'/'auto'; got %r" % (g,))
         return float(g)
+
+    def costs(self):
+        """SMO iterations grow ~linearly with C up to a saturation level ~12.5/(gamma*d) and fall with gamma*d (the model
+        csrc/api.cu orders sub-problems by; measured on config 2)."""
+        d = self.X.shape[1]
+        out = np.ones(len(self.cands))
+        try:
+            for i, cand in enumerate(self.cands):
+                p = self._base_params(cand)
+                C = float(p["C"])
+                if p["kernel"] == "rbf":
+                    gd = self._gamma(p["gamma"], -1) * d
+                    out[i] = min(C, 12.5 / gd) * gd ** -0.35
+                else:
+                    out[i] = C
+        except Exception:
+            return None                                 # invalid candidates are reported by evaluate()
+        return out
 
     def evaluate(self, my, return_train=True, error_score='raise'):
         ns = self.n_splits

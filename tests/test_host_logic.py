@@ -62,6 +62,9 @@ class OraclePlan:
     def profile(self):
         return {}
 
+    def costs(self):
+        return np.array([float(c.get("C", 1.0)) for c in self.cands])      # exercises the cost-balanced dealing
+
     def refit(self, best):
         from oracle import oracle as O
         from sklearn.base import clone
@@ -195,6 +198,24 @@ def test_materialize_svc_binary_equals_sklearn_fit():
     np.testing.assert_array_equal(est.decision_function(w["X"][400:600]), ref.decision_function(w["X"][400:600]))
     import pickle
     np.testing.assert_array_equal(pickle.loads(pickle.dumps(est)).predict(X), ref.predict(X))
+
+
+def test_assign_candidates_is_a_balanced_partition():
+    from spark_sklearn_b200.dist import assign_candidates
+    for n, world in ((64, 1), (64, 8), (6, 4), (7, 3), (512, 8)):
+        strided = assign_candidates(n, world)
+        assert strided == [list(range(r, n, world)) for r in range(world)]
+        rng = np.random.default_rng(n + world)
+        costs = rng.lognormal(size=n)
+        parts = assign_candidates(n, world, costs)
+        assert sorted(sum(parts, [])) == list(range(n))                    # a partition ...
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1           # ... of equal sizes ...
+        load = [costs[p].sum() for p in parts]
+        if n >= 8 * world:
+            assert max(load) <= 1.25 * min(load)                          # ... and similar predicted cost
+        top = np.argsort(-costs)[:world]                                  # the `world` most expensive land on distinct ranks
+        assert len({r for r, p in enumerate(parts) for c in top if c in p}) == world or n < world
+    assert assign_candidates(5, 2, [1, np.nan, 2, 3, 4]) == [[0, 2, 4], [1, 3]]   # unusable costs: strided
 
 
 # ------------------------------------------------------------------ multi-rank (gloo, CPU) --------
