@@ -401,16 +401,22 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
             P.coef = h->dWork[3].as<double>() + (size_t)q * n;
             P.out_rho = d_rho + q; P.out_info = d_info + 4 * (size_t)q; P.out_ns = d_ns + 12 * (size_t)q;
         }
-        // Longest-first launch order.  SMO iteration counts grow with C until the box constraint stops binding, and
-        // that saturation level grows with 1/gamma (config 2: ~C^0.8 up to C_sat ~ 12.5/(gamma*d), measured); the
-        // predicted-longest problems lead the order so that they start first and get the cluster kernel.
+        // Predicted cost = rows x predicted SMO iterations.  For rbf the iteration count of config 2 / config 4 (1600 measured
+        // fits, tests/golden) rises like (C * gamma*d)^0.95 and saturates at a level ~ 1/(gamma*d):
+        //     iterations / 1000 ~= min(4 + 10.3 (C gamma d)^0.95, 9 + 7.3 / (gamma d))      (Spearman 0.985, median error 12 %)
+        // Only the ranking and the ratios are used: the predicted-longest problems lead the launch order and the cluster
+        // policy below works on cost ratios.  (Linear kernel: iterations grow with C; no plateau is modelled.)
         std::vector<double> cost(np);
         for (int q = 0; q < np; q++) {
             const int t = prob_task[q];
             const double Cq = Cv[t / n_splits];
             const auto &grp = groups[task_group[t]];
-            const double sat = grp.first == GS_KERNEL_RBF ? 12.5 / (grp.second * (double)d) : Cq;
-            cost[q] = std::min(Cq, sat) * (double)probs[q].l * (grp.first == GS_KERNEL_RBF ? std::pow(grp.second * d, -0.35) : 1.0);
+            double it = Cq;
+            if (grp.first == GS_KERNEL_RBF) {
+                const double gd = grp.second * (double)d;
+                it = std::min(4.0 + 10.3 * std::pow(Cq * gd, 0.95), 9.0 + 7.3 / gd);
+            }
+            cost[q] = it * (double)probs[q].l;
         }
         std::vector<int> order(np);
         std::iota(order.begin(), order.end(), 0);
@@ -436,9 +442,9 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
         // against 6.4-7.1 us for the single-CTA kernel, but costs twice the SM-time per iteration.  So clusters are for the
         // critical path only:
         //   * fewer problems than SMs: everything on the widest cluster that fits;
-        //   * throughput-bound searches (the predicted-longest problem is shorter than 0.9 x total work / SMs): no clusters;
-        //   * otherwise the group of predicted near-longest problems (cost > 0.8 x the largest), at most half the SMs.
-        //     (config 2: exactly the ten 66-68k-iteration problems; leaving ONE of them on a single SM costs +33 %.)
+        //   * otherwise the number of clustered problems minimises a three-term makespan model (below): none for a
+        //     throughput-bound search (config 4), exactly the ten 66-68k-iteration problems for config 2 (leaving ONE of
+        //     them on a single SM costs +33 %), nineteen for the denser 8-GPU weak-scaling grid.
         // Development switches: B200GS_SMO_CLUSTER (0/2/4/8),
         // B200GS_SMO_CLUSTER_N.
         std::string why;
@@ -448,14 +454,21 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
             else if (np * 4 <= h->sm_count) { cl = 4; n_cl = np; }
             else if (np * 2 <= h->sm_count) { cl = 2; n_cl = np; }
             else {
+                // choose the number n of (predicted-longest) problems on 4-CTA clusters that minimises the predicted makespan
+                //   f(n) = max( throughput bound [sum_rest + 2.0 * sum_clustered] / SMs,   (a cluster iteration costs 2x the SM-time)
+                //               0.9 * cost of the longest problem left on one SM,         (tail of the run: 6.4 vs 7.1 us)
+                //               0.5 * cost of the longest clustered problem )             (3.5 vs 7.1 us per iteration)
+                // in units of (predicted iterations x single-CTA iteration time); only cost RATIOS matter.
                 double total = 0;
                 for (int q = 0; q < np; q++) total += cost[q];
-                const double wmax = cost[order[0]];
-                if (wmax > 0.9 * total / h->sm_count) {
-                    cl = 4;
-                    while (n_cl < np && cost[order[n_cl]] > 0.8 * wmax) ++n_cl;
-                    n_cl = std::min(n_cl, h->sm_count / 8);
+                const int nmax = std::min(np - 1, h->sm_count / 4);
+                double best = 0, clustered = 0;
+                for (int n = 0; n <= nmax; n++) {
+                    const double f = std::max({(total + clustered) / h->sm_count, 0.9 * cost[order[n]], n > 0 ? 0.5 * cost[order[0]] : 0.0});
+                    if (n == 0 || f < 0.99 * best) { best = f; n_cl = n; }
+                    clustered += cost[order[n]];
                 }
+                if (n_cl > 0) cl = 4;
             }
         }
         if (const char *e = getenv("B200GS_SMO_CLUSTER")) { cl = atoi(e); if (n_cl == 0) n_cl = std::max(1, np * 6 / 100); }
@@ -491,12 +504,16 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
         tm.mark(2);
         // -- score (skipped for refit) --
         if (!refit) {
+            int max_cols = 0;
+            for (int g = g0; g < g1; g++) max_cols = std::max(max_cols, group_first[g - g0 + 1] - group_first[g - g0]);
+            const int jch = decision_chunks(n);
+            if (jch > 1) GS_CUDA(h->dWork[8].reserve((size_t)jch * max_cols * n * 8));      // partial sums of the j-chunks
             for (int g = g0; g < g1; g++) {
                 const int c0 = group_first[g - g0], c1 = group_first[g - g0 + 1];
                 GS_CUDA(launch_decision(h->dS.as<double>(), h->dXsq.as<double>(), n, groups[g].first, groups[g].second,
                                         h->dWork[3].as<double>() + (size_t)c0 * n, c1 - c0,
-                                        h->dWork[4].as<double>() + (size_t)c0 * n, st));
-                pf.launches++;
+                                        h->dWork[4].as<double>() + (size_t)c0 * n, jch > 1 ? h->dWork[8].as<double>() : nullptr, st));
+                pf.launches += jch > 1 ? 2 : 1;
             }
             GS_CUDA(launch_vote(h->dWork[4].as<double>(), d_rho, n, nc, h->dY.as<int>(), h->dFold.as<signed char>(),
                                 d_vt, (int)vtasks.size(), d_counts, st));

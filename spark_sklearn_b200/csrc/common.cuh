@@ -52,7 +52,7 @@ struct gs_handle {
     int x_dtype = GS_F32;
     DevBuf dS, dXsq;                  // float64 Gram [n][n], squared norms [n]
     DevBuf dK;                        // float32 kernel matrices (batch)
-    DevBuf dWork[8];                  // per-search scratch
+    DevBuf dWork[9];                  // per-search scratch
     gs_profile prof;
     cudaEvent_t ev[8];
 };
@@ -96,8 +96,9 @@ cudaError_t launch_smo_colown(const SmoProblem *d_probs, const int *d_order, int
 // ---- score.cu ----
 // dec[c][r] = sum_j k64(r, j) * coef[c][j]  (float64 kernel values recomputed from S, not the
 // float32-rounded K: svm.cpp:2821 svm_predict_values uses k_function in double).
+int decision_chunks(int n);
 cudaError_t launch_decision(const double *S, const double *xsq, int n, int kernel, double gamma,
-                            const double *coef, int ncols, double *dec, cudaStream_t st);
+                            const double *coef, int ncols, double *dec, double *part, cudaStream_t st);
 struct VoteTask {          // one (candidate, fold) task
     int first_col;         // first decision column of this task inside its group (n_pairs consecutive)
     int fold;              // test fold id

@@ -160,8 +160,8 @@ class SVCPlan(_Plan):
         return float(g)
 
     def costs(self):
-        """SMO iterations grow ~linearly with C up to a saturation level ~12.5/(gamma*d) and fall with gamma*d (the model
-        csrc/api.cu orders sub-problems by; measured on config 2)."""
+        """Predicted SMO iterations: rise like (C*gamma*d)^0.95, saturate at a level ~1/(gamma*d) (the model csrc/api.cu
+        orders sub-problems by; fitted to the 1600 measured fits of configs 2 and 4)."""
         d = self.X.shape[1]
         out = np.ones(len(self.cands))
         try:
@@ -170,7 +170,7 @@ class SVCPlan(_Plan):
                 C = float(p["C"])
                 if p["kernel"] == "rbf":
                     gd = self._gamma(p["gamma"], -1) * d
-                    out[i] = min(C, 12.5 / gd) * gd ** -0.35
+                    out[i] = min(4.0 + 10.3 * (C * gd) ** 0.95, 9.0 + 7.3 / gd)
                 else:
                     out[i] = C
         except Exception:
