@@ -10,4 +10,5 @@ timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_d
     --log-file gpurun_out/smo_dram_r01.csv python tools/run_workload.py c2 1 > gpurun_out/smo_dram_run.log 2>&1
 B200GS_SMO_CLUSTER=4 B200GS_SMO_CLUSTER_N=100000 timeout 600 ncu --set full --clock-control none --import-source on -k regex:smo_colown -c 1 \
     -o gpurun_out/colown_v3_r01 -f python tools/exp_one.py > gpurun_out/colown_v3_ncu.log 2>&1
+timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 400 gpurun_out/bench_ref.json
 echo done
