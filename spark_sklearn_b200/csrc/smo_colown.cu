@@ -814,8 +814,7 @@ cudaError_t launch_co(const SmoProblem *probs, const int *order, int n_prob, int
     // alpha + mbar per owned element, then 7 bytes per POSITION of cold-path scratch; padded to a whole SM's worth so a
     // cluster CTA never shares its SM (a resident small CTA would keep a full-SM single-CTA solver from being scheduled)
     size_t smem = (size_t)LCAP * 16 + (size_t)lmax * 7 + 64;
-    const char *sh = getenv("B200GS_SMO_CO_SHARE");                         // development switch: let cluster CTAs share an SM
-    if (!(sh && atoi(sh)) && smem < 160 * 1024) smem = 160 * 1024;
+    if (smem < 160 * 1024) smem = 160 * 1024;
     auto kern = smo_colown_kernel<NT, KPT, CL, FAST, PROF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -175,6 +175,29 @@ def test_cluster_smo_bitexact(engine, monkeypatch, cl):
     np.testing.assert_array_equal(r["train"], g["train_scores"])
 
 
+@pytest.mark.parametrize("cl", [0, 2, 4, 8])
+def test_general_kernel_paths_vs_sklearn(engine, monkeypatch, cl):
+    """The non-specialised solver instances (linear kernel: QD != 1; rbf whose kernel matrix underflows to denormals and
+    zeros: no integer-pipe widening, float64 approximate filter), single-CTA (cl=0) and cluster kernels, against
+    scikit-learn fits of the same folds: identical iteration counts and scores."""
+    from sklearn.svm import SVC
+    monkeypatch.setenv("B200GS_SMO_CLUSTER", str(cl))
+    if cl:
+        monkeypatch.setenv("B200GS_SMO_CLUSTER_N", "100000")
+    w, fold_id, ns = _setup(engine, "c2_mid")
+    X, y = w["X"], w["y"]
+    cases = [("linear", 0.01, 0.0), ("rbf", 1.0, 0.35), ("rbf", 3.0, 2.0)]
+    r = engine.svc([c[0] for c in cases], [c[1] for c in cases], np.array([c[2] for c in cases])[:, None], tol=1e-3,
+                   max_iter=-1, shrinking=True, return_train=True)
+    for i, (kern, C, gam) in enumerate(cases):
+        for k in range(ns):
+            tr, te = np.flatnonzero(fold_id != k), np.flatnonzero(fold_id == k)
+            s = SVC(kernel=kern, C=C, gamma=gam if kern == "rbf" else "scale").fit(X[tr], y[tr])
+            assert r["n_iter"][i, k] == s.n_iter_[0], (kern, C, gam, k)
+            assert r["test"][i, k] == s.score(X[te], y[te])
+            assert r["train"][i, k] == s.score(X[tr], y[tr])
+
+
 def test_c2_full_size_vs_golden(engine):
     """BASELINE config 2 at full size (10000x512, 8x8 grid, cv=5 = 320 fits): every split score equals scikit-learn's."""
     w, fold_id, ns = _setup(engine, "c2")
