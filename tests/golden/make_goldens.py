@@ -114,3 +114,20 @@ if __name__ == "__main__":
     a = ap.parse_args()
     for k in a.keys:
         run(k, a.jobs, a.mode)
+
+
+def make_refit_golden():
+    """Full-data fit of one config-2 candidate (the refit path): tests/golden/c2_refit_C10_g1024.npz."""
+    import numpy as np
+    from sklearn.svm import SVC
+    from spark_sklearn_b200 import workloads as W
+    w = W.make_workload("c2")
+    X, y = w["X"], w["y"]
+    s = SVC(kernel="rbf", C=10.0, gamma=1 / 1024).fit(X, y)
+    from oracle import oracle as O                         # the C restatement (Gram formed like the GPU's): bit-level target
+    rows = np.concatenate([np.flatnonzero(y == 0), np.flatnonzero(y == 1)]).astype(np.int32)
+    oc, orho, oit, _ = O.svc_solve(X.astype(np.float64), rows, int((y == 0).sum()), "rbf", 1 / 1024, 10.0)
+    full = np.zeros(len(y)); full[rows] = oc
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "c2_refit_C10_g1024.npz"), n_iter=s.n_iter_,
+                        n_support=s.n_support_, intercept=s.intercept_, support=s.support_.astype(np.int32), dual_coef=s.dual_coef_,
+                        oracle_coef=full, oracle_rho=np.array([orho]))

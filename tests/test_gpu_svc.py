@@ -198,6 +198,26 @@ def test_general_kernel_paths_vs_sklearn(engine, monkeypatch, cl):
             assert r["train"][i, k] == s.score(X[tr], y[tr])
 
 
+def test_full_data_refit_vs_sklearn(engine):
+    """The refit of a candidate on ALL 10000 rows of config 2 (one sub-problem -> an 8-CTA cluster with l = 10000 > 8192).
+    Against scikit-learn's own fit (tests/golden/c2_refit_C10_g1024.npz = SVC(C=10, gamma=1/1024).fit(X, y)): same
+    iteration count and support set, coefficients within 1e-7 (scikit-learn's BLAS dot products round a few float32 Q
+    entries differently; the selection sequence is unaffected here).  Against the C oracle, which forms the Gram the way
+    the GPU does: bit-identical coefficients and intercept."""
+    w = W.make_workload("c2")
+    X, y = w["X"], w["y"]
+    g = golden("c2_refit_C10_g1024")
+    engine.set_data(X, np.full(len(y), -1, np.int8), 1, y_class=y.astype(np.int32))
+    coef, rho, it = engine.svc_refit("rbf", 10.0, 1 / 1024, 2)
+    assert it[0] == int(g["n_iter"][0])
+    sv = np.flatnonzero(coef[0] != 0)
+    order = np.argsort(g["support"], kind="stable")                    # sklearn lists support vectors class by class
+    np.testing.assert_array_equal(sv, g["support"][order])
+    np.testing.assert_allclose(np.abs(coef[0][sv]), np.abs(g["dual_coef"][0][order]), rtol=0, atol=1e-7)
+    np.testing.assert_array_equal(coef[0], g["oracle_coef"])
+    assert rho[0] == float(g["oracle_rho"][0])
+
+
 def test_c2_full_size_vs_golden(engine):
     """BASELINE config 2 at full size (10000x512, 8x8 grid, cv=5 = 320 fits): every split score equals scikit-learn's."""
     w, fold_id, ns = _setup(engine, "c2")
