@@ -124,6 +124,15 @@ int gs_debug_kernel_matrix(gs_handle *h, int32_t kernel, double gamma, float *K_
 /* C[M][N] = sum_k A[M][k]*B[N][k] on the tcgen05 tensor-core path (3xTF32 split), host fp32 row-major in/out. */
 int gs_debug_gemm_nt(gs_handle *h, const float *A, int32_t M, const float *B, int32_t N, int32_t K, float *C);
 
+/* ---- planning helpers (host only, no device work; used by gs_svc itself and by the multi-GPU host driver) -------- */
+/* Predicted SMO iterations (thousands, for ~8000 training rows) of one C-SVC sub-problem: the model that orders the
+ * sub-problems of a search and deals candidates to GPUs.  kernel: GS_KERNEL_*; d = number of features.  Only ratios
+ * between candidates are meaningful. */
+double gs_svc_predicted_iterations(int32_t kernel, double C, double gamma, int32_t d);
+/* Number of sub-problems a search puts on 4-CTA clusters, given the predicted costs sorted in DESCENDING order and
+ * the SM count (the makespan model documented in DESIGN.md section 4). */
+int32_t gs_svc_cluster_count(const double *cost_desc, int32_t n, int32_t sm_count);
+
 /* ---- measurement ----------------------------------------------------------------------- */
 typedef struct gs_profile {
     /* last search call; device times from CUDA events on the engine's stream */

@@ -197,6 +197,41 @@ int gs_set_data(gs_handle *h, const void *X, int32_t x_dtype, int64_t n, int64_t
 // ------------------------------------------------------------------------------------------------
 // SVC: shared implementation of gs_svc (folds) and gs_svc_refit (all rows train).
 // ------------------------------------------------------------------------------------------------
+// ---- planning helpers (also exported: include/b200gs.h) ----
+// Predicted SMO iterations / 1000 of a sub-problem with ~8000 rows.  For rbf the iteration count of config 2 / config 4
+// (1600 measured fits, tests/golden) rises like (C * gamma*d)^0.95 and saturates at a level ~ 1/(gamma*d):
+//     min(4 + 10.3 (C gamma d)^0.95, 9 + 7.3 / (gamma d))      (Spearman 0.985 against the measured counts, median error 12 %)
+// Linear kernel: iterations grow with C; no plateau is modelled.  Only the ranking and the ratios are used.
+extern "C" double gs_svc_predicted_iterations(int32_t kernel, double C, double gamma, int32_t d)
+{
+    if (kernel != GS_KERNEL_RBF) return C;
+    const double gd = gamma * (double)d;
+    if (!(gd > 0)) return C;
+    return std::min(4.0 + 10.3 * std::pow(C * gd, 0.95), 9.0 + 7.3 / gd);
+}
+
+// Number n of (predicted-longest) problems on 4-CTA clusters that minimises the predicted makespan
+//   f(n) = max( throughput bound [sum_rest + 2.0 * sum_clustered] / SMs,   (a cluster iteration costs 2x the SM-time)
+//               0.9 * cost of the longest problem left on one SM,         (tail of the run: 6.4 vs 7.1 us per iteration)
+//               0.5 * cost of the longest clustered problem )             (3.5 vs 7.1 us per iteration)
+// in units of (predicted iterations x single-CTA iteration time); only cost RATIOS matter.  Near-ties go to the smaller n
+// (measured on config 2: 10 clusters 297 ms, 14 clusters 313 ms, 19 clusters 323 ms -- the model is optimistic about clusters).
+extern "C" int32_t gs_svc_cluster_count(const double *cost_desc, int32_t n, int32_t sm_count)
+{
+    if (!cost_desc || n < 2 || sm_count < 4) return 0;
+    double total = 0;
+    for (int q = 0; q < n; q++) total += cost_desc[q];
+    const int nmax = std::min(n - 1, sm_count / 4);
+    double best = 0, clustered = 0;
+    int pick = 0;
+    for (int k = 0; k <= nmax; k++) {
+        const double f = std::max({(total + clustered) / sm_count, 0.9 * cost_desc[k], k > 0 ? 0.5 * cost_desc[0] : 0.0});
+        if (k == 0 || f < 0.97 * best) { best = f; pick = k; }           // more clusters only for a clear (3 %) predicted gain
+        clustered += cost_desc[k];
+    }
+    return pick;
+}
+
 static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double *Cv, const double *gamma,
                    double tol, int max_iter, uint32_t flags, bool refit,
                    double *test_scores, double *train_scores, int32_t *n_iter, int32_t *n_sv,
@@ -401,22 +436,13 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
             P.coef = h->dWork[3].as<double>() + (size_t)q * n;
             P.out_rho = d_rho + q; P.out_info = d_info + 4 * (size_t)q; P.out_ns = d_ns + 12 * (size_t)q;
         }
-        // Predicted cost = rows x predicted SMO iterations.  For rbf the iteration count of config 2 / config 4 (1600 measured
-        // fits, tests/golden) rises like (C * gamma*d)^0.95 and saturates at a level ~ 1/(gamma*d):
-        //     iterations / 1000 ~= min(4 + 10.3 (C gamma d)^0.95, 9 + 7.3 / (gamma d))      (Spearman 0.985, median error 12 %)
-        // Only the ranking and the ratios are used: the predicted-longest problems lead the launch order and the cluster
-        // policy below works on cost ratios.  (Linear kernel: iterations grow with C; no plateau is modelled.)
+        // Predicted cost = rows x predicted SMO iterations (gs_svc_predicted_iterations): the predicted-longest problems lead
+        // the launch order and the cluster policy below works on cost ratios.
         std::vector<double> cost(np);
         for (int q = 0; q < np; q++) {
             const int t = prob_task[q];
-            const double Cq = Cv[t / n_splits];
             const auto &grp = groups[task_group[t]];
-            double it = Cq;
-            if (grp.first == GS_KERNEL_RBF) {
-                const double gd = grp.second * (double)d;
-                it = std::min(4.0 + 10.3 * std::pow(Cq * gd, 0.95), 9.0 + 7.3 / gd);
-            }
-            cost[q] = it * (double)probs[q].l;
+            cost[q] = gs_svc_predicted_iterations(grp.first, Cv[t / n_splits], grp.second, (int32_t)d) * (double)probs[q].l;
         }
         std::vector<int> order(np);
         std::iota(order.begin(), order.end(), 0);
@@ -454,20 +480,9 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
             else if (np * 4 <= h->sm_count) { cl = 4; n_cl = np; }
             else if (np * 2 <= h->sm_count) { cl = 2; n_cl = np; }
             else {
-                // choose the number n of (predicted-longest) problems on 4-CTA clusters that minimises the predicted makespan
-                //   f(n) = max( throughput bound [sum_rest + 2.0 * sum_clustered] / SMs,   (a cluster iteration costs 2x the SM-time)
-                //               0.9 * cost of the longest problem left on one SM,         (tail of the run: 6.4 vs 7.1 us)
-                //               0.5 * cost of the longest clustered problem )             (3.5 vs 7.1 us per iteration)
-                // in units of (predicted iterations x single-CTA iteration time); only cost RATIOS matter.
-                double total = 0;
-                for (int q = 0; q < np; q++) total += cost[q];
-                const int nmax = std::min(np - 1, h->sm_count / 4);
-                double best = 0, clustered = 0;
-                for (int n = 0; n <= nmax; n++) {
-                    const double f = std::max({(total + clustered) / h->sm_count, 0.9 * cost[order[n]], n > 0 ? 0.5 * cost[order[0]] : 0.0});
-                    if (n == 0 || f < 0.99 * best) { best = f; n_cl = n; }
-                    clustered += cost[order[n]];
-                }
+                std::vector<double> sorted_cost(np);
+                for (int q = 0; q < np; q++) sorted_cost[q] = cost[order[q]];
+                n_cl = gs_svc_cluster_count(sorted_cost.data(), np, h->sm_count);
                 if (n_cl > 0) cl = 4;
             }
         }

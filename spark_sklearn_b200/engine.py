@@ -60,6 +60,10 @@ def load_library():
     L.gs_debug_gram.argtypes = [vp, vp, vp]
     L.gs_debug_kernel_matrix.argtypes = [vp, i32, dbl, vp]
     L.gs_debug_gemm_nt.argtypes = [vp, vp, i32, vp, i32, i32, vp]
+    L.gs_svc_predicted_iterations.argtypes = [i32, dbl, dbl, i32]
+    L.gs_svc_predicted_iterations.restype = dbl
+    L.gs_svc_cluster_count.argtypes = [vp, i32, i32]
+    L.gs_svc_cluster_count.restype = i32
     for f in ("gs_create", "gs_set_data", "gs_svc", "gs_svc_refit", "gs_ridge", "gs_ridge_refit", "gs_logreg",
               "gs_logreg_refit", "gs_get_profile", "gs_debug_gram", "gs_debug_kernel_matrix", "gs_debug_gemm_nt"):
         getattr(L, f).restype = c.c_int

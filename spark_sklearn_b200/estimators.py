@@ -160,19 +160,17 @@ class SVCPlan(_Plan):
         return float(g)
 
     def costs(self):
-        """Predicted SMO iterations: rise like (C*gamma*d)^0.95, saturate at a level ~1/(gamma*d) (the model csrc/api.cu
-        orders sub-problems by; fitted to the 1600 measured fits of configs 2 and 4)."""
+        """Predicted SMO iterations per candidate from the library's own model (gs_svc_predicted_iterations: the one
+        gs_svc orders its sub-problems by)."""
+        from .engine import load_library, KERNEL_ID
+        L = load_library()
         d = self.X.shape[1]
         out = np.ones(len(self.cands))
         try:
             for i, cand in enumerate(self.cands):
                 p = self._base_params(cand)
-                C = float(p["C"])
-                if p["kernel"] == "rbf":
-                    gd = self._gamma(p["gamma"], -1) * d
-                    out[i] = min(4.0 + 10.3 * (C * gd) ** 0.95, 9.0 + 7.3 / gd)
-                else:
-                    out[i] = C
+                g = self._gamma(p["gamma"], -1) if p["kernel"] == "rbf" else 0.0
+                out[i] = L.gs_svc_predicted_iterations(KERNEL_ID[p["kernel"]], float(p["C"]), float(g), int(d))
         except Exception:
             return None                                 # invalid candidates are reported by evaluate()
         return out

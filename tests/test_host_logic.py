@@ -29,6 +29,35 @@ def test_cabi_library_exports_every_declared_symbol():
     assert engine.load_library().gs_version() >= 100
 
 
+def _golden_svc(name):
+    g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"), allow_pickle=True)
+    names = [str(x) for x in g["param_names"]]
+    tof = lambda col: np.array([float(re.sub(r"np\.float64\((.*)\)", r"\1", str(x))) for x in col])
+    return tof(g["param_values"][:, names.index("C")]), tof(g["param_values"][:, names.index("gamma")]), g["diag"][:, :, 0]
+
+
+def test_planning_helpers_against_measured_iteration_counts():
+    """gs_svc_predicted_iterations ranks the 1600 measured fits of configs 2 and 4 (scikit-learn's n_iter_) with a Spearman
+    correlation >= 0.97, and gs_svc_cluster_count picks the critical-path group: the ten 66-68k-iteration problems of
+    config 2, nothing for the throughput-bound config 4.  Host-only entry points: callable without a GPU."""
+    from scipy.stats import spearmanr
+    from spark_sklearn_b200 import engine
+    L = engine.load_library()
+    picks = {}
+    for name in ("c2_svc_rbf_8x8", "c4_svc_rbf_16x16"):
+        C, gam, it = _golden_svc(name)
+        pred = np.array([L.gs_svc_predicted_iterations(1, c, g, 512) for c, g in zip(C, gam)])
+        assert spearmanr(np.repeat(pred, it.shape[1]), it.ravel())[0] >= 0.97
+        assert np.median(np.abs(pred * 1000 / it.mean(1) - 1)) <= 0.2          # and is roughly calibrated (thousands)
+        cost = np.sort(np.repeat(pred, it.shape[1]))[::-1].copy()
+        picks[name] = L.gs_svc_cluster_count(cost.ctypes.data, len(cost), 148)
+        true = np.sort(it.ravel().astype(float))[::-1].copy()                     # with the true counts as costs
+        assert L.gs_svc_cluster_count(true.ctypes.data, len(true), 148) == picks[name]
+    assert picks == {"c2_svc_rbf_8x8": 10, "c4_svc_rbf_16x16": 0}
+    assert L.gs_svc_predicted_iterations(0, 3.0, 0.0, 512) == 3.0                  # linear: grows with C
+    assert L.gs_svc_cluster_count(None, 0, 148) == 0
+
+
 def test_no_gpu_fails_loudly():
     import torch
     if torch.cuda.is_available():
