@@ -320,6 +320,25 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
             }
     }
     sp_off.back() = (int)rows_all.size();
+    // column ranges of every sub-problem (see SmoProblem::nseg): maximal runs of its rows, gaps below 64 columns merged,
+    // starts rounded down and ends rounded up to 4 floats (16-byte bulk copies); more than 4 runs -> whole-row copies
+    std::vector<int> sp_nseg((size_t)n_splits * n_pairs, 0), sp_seg((size_t)n_splits * n_pairs * 8, 0);
+    for (size_t s = 0; s + 1 < sp_off.size(); s++) {
+        std::vector<int> rs(rows_all.begin() + sp_off[s], rows_all.begin() + sp_off[s + 1]);
+        std::sort(rs.begin(), rs.end());
+        std::vector<std::pair<int, int>> runs;                               // [start, end)
+        for (int r : rs) {
+            const int a0 = r & ~3, a1 = (r + 4) & ~3;
+            if (!runs.empty() && a0 <= runs.back().second + 64) runs.back().second = std::max(runs.back().second, a1);
+            else runs.emplace_back(a0, a1);
+        }
+        if (runs.empty() || runs.size() > 4) continue;
+        sp_nseg[s] = (int)runs.size();
+        for (size_t e = 0; e < runs.size(); e++) {
+            sp_seg[s * 8 + e] = runs[e].first;
+            sp_seg[s * 8 + 4 + e] = std::min(runs[e].second, (int)ldk) - runs[e].first;
+        }
+    }
     if (lmax > smo_max_rows() && lmax > smo_colown_max_rows(4)) {
         gs_set_error(h, "gs_svc: sub-problem with " + std::to_string(lmax) + " rows exceeds the resident-state SMO kernel limit of " +
                             std::to_string(smo_max_rows()));
@@ -404,6 +423,8 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
                     P.qd = groups[g].first == GS_KERNEL_LINEAR ? h->dXsq.as<double>() : nullptr;
                     P.rows = d_rows + sp_off[s];
                     P.l = sp_off[s + 1] - sp_off[s];
+                    P.nseg = sp_nseg[s];
+                    for (int e = 0; e < 4; e++) { P.seg_start[e] = sp_seg[s * 8 + e]; P.seg_len[e] = sp_seg[s * 8 + 4 + e]; }
                     P.n_pos = sp_npos[s];
                     P.ldk = ldk; P.C = Cv[c]; P.eps = tol; P.max_iter = max_iter;
                     P.shrinking = (flags & GS_NO_SHRINKING) ? 0 : 1;

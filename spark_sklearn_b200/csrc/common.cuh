@@ -83,6 +83,10 @@ struct SmoProblem {
     int64_t ldk;
     double C, eps;
     int l, n_pos, max_iter, shrinking;
+    // up to 4 column ranges (floats, multiples of 4) that cover this sub-problem's dataset rows: the single-CTA kernel
+    // copies only these parts of a K row into shared memory (a fold's training rows are 2-3 contiguous runs of the
+    // class-sorted dataset: 32 KB of a 40 KB row in config 2).  nseg == 0: copy the whole row.
+    int nseg, seg_start[4], seg_len[4];
 };
 // Solve problems order[0..n_prob) (one CTA each); lmax = max l (selects the template instance).
 cudaError_t launch_smo(const SmoProblem *d_probs, const int *d_order, int n_prob, int lmax, bool fast, int rowcap,

@@ -13,7 +13,7 @@ namespace {
 
 constexpr int TR = 64, TJ = 32;
 
-// TC = columns per block (multiple of 8).  The float64 exp of a (row, SV) pair is the expensive part (n^2 of them per
+// TC = columns per block (multiple of 8, the group's column count rounded up to 8 so no lane multiplies padding).  The float64 exp of a (row, SV) pair is the expensive part (n^2 of them per
 // block row), so a block takes as many coefficient columns as the group has, up to 96 (static shared memory): the kernel values are computed once
 // per group instead of once per 32 columns.
 template <int TC>
@@ -153,14 +153,17 @@ cudaError_t launch_decision(const double *S, const double *xsq, int n, int kerne
                             const double *coef, int ncols, double *dec, double *part, cudaStream_t st)
 {
     if (ncols <= 0) return cudaSuccess;
-    const int tc = ncols <= 32 ? 32 : (ncols <= 64 ? 64 : 96);
+    const int tc = std::min(96, (ncols + 7) / 8 * 8);
     const int jchunks = part ? decision_chunks(n) : 1;
     const int jlen = ((n + jchunks - 1) / jchunks + TJ - 1) / TJ * TJ;
     dim3 grid((n + TR - 1) / TR, (ncols + tc - 1) / tc, jchunks);
     double *out = jchunks > 1 ? part : dec;
-    if (tc == 32) decision_kernel<32><<<grid, 256, 0, st>>>(S, xsq, n, kernel, gamma, coef, ncols, out, jlen);
-    else if (tc == 64) decision_kernel<64><<<grid, 256, 0, st>>>(S, xsq, n, kernel, gamma, coef, ncols, out, jlen);
-    else decision_kernel<96><<<grid, 256, 0, st>>>(S, xsq, n, kernel, gamma, coef, ncols, out, jlen);
+#define GS_DEC(T) case T: decision_kernel<T><<<grid, 256, 0, st>>>(S, xsq, n, kernel, gamma, coef, ncols, out, jlen); break;
+    switch (tc) {
+        GS_DEC(8) GS_DEC(16) GS_DEC(24) GS_DEC(32) GS_DEC(40) GS_DEC(48) GS_DEC(56) GS_DEC(64) GS_DEC(72) GS_DEC(80) GS_DEC(88)
+        default: decision_kernel<96><<<grid, 256, 0, st>>>(S, xsq, n, kernel, gamma, coef, ncols, out, jlen); break;
+    }
+#undef GS_DEC
     if (jchunks > 1) {
         const size_t count = (size_t)ncols * n;
         sum_slabs_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(part, count, jchunks, dec);
