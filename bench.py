@@ -293,8 +293,8 @@ def main():
     per_launch_s = solve_ms / max(a.steps, 1) * 1e-3
     achieved = per_launch_bytes / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
     # DRAM traffic of the SMO launches of ONE config-2 step, from ncu (profiles/r01_smo_dram_full_c2.csv):
-    # smo_kernel 283.85 + 1.00 GB, smo_colown_kernel 30.10 + 0.01 GB.  Only valid for the N=1 config-2 workload.
-    traffic = 315.0e9 if (world <= 1 and a.workload == "c2") else None
+    # smo_kernel 257.32 + 0.87 GB, smo_colown_kernel 30.39 + 0.01 GB.  Only valid for the N=1 config-2 workload.
+    traffic = 288.6e9 if (world <= 1 and a.workload == "c2") else None
     roofline = {"kernel": "smo_kernel (one CTA per sub-problem) + smo_colown_kernel (4-CTA cluster per critical-path sub-problem), "
                           "launched concurrently: batched exact-trajectory C-SVC SMO", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
@@ -303,7 +303,7 @@ def main():
                 "note": "algorithmic bytes = sum over sub-problems of n_iter * 2 rows * l * 4 B (SURVEY.md 8d) per step (both SMO "
                         "launches); time = the solve phase of the step from CUDA events on the engine stream.  The solver is bound "
                         "by the dependent chain of an SMO iteration and by issue slots, not by HBM bandwidth "
-                        "(profiles/r01_smo_final_ncu_summary.txt: 58 % / 33 % issue-active, measured DRAM traffic 0.94x algorithmic)"}
+                        "(profiles/r01_smo_final_ncu_summary.txt: 58 % / 33 % issue-active, measured DRAM traffic 0.86x algorithmic)"}
     result = {
         "metric": "candidate-fits/sec", "value": a.steps * fits / (ev_ms * 1e-3), "unit": "fits/s", "n_gpus": max(world, 1),
         "steps": a.steps, "warmup": W_, "ms_per_step": ev_ms / max(a.steps, 1), "higher_is_better": True,
