@@ -222,7 +222,7 @@ def main():
     splits = list(check_cv(w["cv"], y, classifier=is_classifier(est)).split(X, y))
     fold_id = fold_ids_from_splits(splits, len(y))
     plan = adapter_for(est).plan(est, cands, X, y, fold_id, len(splits))       # gs_set_data happens here
-    parts = D.assign_candidates(len(cands), world, plan.costs() if world > 1 else None)    # same dealing as GridSearchCV.fit
+    parts = D.assign_for_plan(plan, len(cands), world)                                     # same dealing as GridSearchCV.fit
     my = parts[rank]
 
     def resident_step():

@@ -84,7 +84,7 @@ class B200BaseSearchCV(BaseSearchCV):
         rank, world = _dist.rank_world()
         plan = adapter.plan(clone(estimator), candidate_params, X_arr, y_arr, fold_id, n_splits)
         # candidates dealt to the GPUs by predicted cost (the reference leaves the placement of its tasks to Spark)
-        parts = _dist.assign_candidates(n_param_candidates, world, plan.costs() if world > 1 else None)
+        parts = _dist.assign_for_plan(plan, n_param_candidates, world)
         my = parts[rank]
         local = plan.evaluate(my, return_train=self.return_train_score, error_score=self.error_score)
         out = _dist.allgather_candidates(local, my, n_param_candidates, n_splits, world, parts)

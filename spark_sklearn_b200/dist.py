@@ -38,6 +38,42 @@ def assign_candidates(n_cand, world, costs=None):
     return [sorted(p) for p in parts]
 
 
+def assign_groups(n_cand, world, costs, keys, max_imbalance=1.08):
+    """Experimental (B200GS_DEAL=groups): deal whole affinity groups (for SVC: all candidates sharing one gamma, which
+    share one kernel matrix and one decision-value pass) instead of single candidates.  Groups are sorted by total
+    predicted cost and dealt in snake order; if there are fewer than 2*world groups or the predicted loads differ by
+    more than ``max_imbalance`` the cost-balanced candidate dealing is used instead."""
+    costs = np.asarray(costs, dtype=np.float64)
+    groups = {}
+    for c, k in enumerate(keys):
+        groups.setdefault(k, []).append(c)
+    if len(groups) < 2 * world:
+        return assign_candidates(n_cand, world, costs)
+    order = sorted(groups, key=lambda k: (-costs[groups[k]].sum(), str(k)))
+    parts = [[] for _ in range(world)]
+    for pos, k in enumerate(order):
+        lap, r = divmod(pos, world)
+        parts[r if lap % 2 == 0 else world - 1 - r].extend(groups[k])
+    load = [costs[p].sum() for p in parts]
+    if min(load) <= 0 or max(load) > max_imbalance * min(load):
+        return assign_candidates(n_cand, world, costs)
+    return [sorted(p) for p in parts]
+
+
+def assign_for_plan(plan, n_cand, world):
+    """The dealing used by the search driver and by bench.py: by predicted cost (default) or, with B200GS_DEAL=groups,
+    by affinity group where that still balances."""
+    import os
+    if world == 1:
+        return assign_candidates(n_cand, 1)
+    costs = plan.costs() if hasattr(plan, "costs") else None
+    if costs is not None and os.environ.get("B200GS_DEAL", "cost") == "groups":
+        keys = plan.affinity() if hasattr(plan, "affinity") else None
+        if keys is not None:
+            return assign_groups(n_cand, world, costs, keys)
+    return assign_candidates(n_cand, world, costs)
+
+
 def allgather_candidates(local, my, n_cand, n_splits, world, parts=None):
     """local: dict of [len(my), n_splits] arrays (test, train|None, fit_time, score_time) for the
     candidates ``my`` of this rank.  Returns the same dict for all n_cand candidates, identical on

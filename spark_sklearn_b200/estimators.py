@@ -86,6 +86,10 @@ class _Plan:
         """Predicted relative cost of every candidate (None: all alike) -- used to balance candidates over GPUs."""
         return None
 
+    def affinity(self):
+        """Per candidate, a hashable key of the device work it shares with others (None: nothing shared)."""
+        return None
+
     def close(self):
         pass
 
@@ -174,6 +178,17 @@ class SVCPlan(_Plan):
         except Exception:
             return None                                 # invalid candidates are reported by evaluate()
         return out
+
+    def affinity(self):
+        """Candidates with the same (kernel, gamma) share a kernel matrix and a decision-value pass."""
+        try:
+            out = []
+            for cand in self.cands:
+                p = self._base_params(cand)
+                out.append((p["kernel"], self._gamma(p["gamma"], -1) if p["kernel"] == "rbf" else 0.0))
+            return out
+        except Exception:
+            return None
 
     def evaluate(self, my, return_train=True, error_score='raise'):
         ns = self.n_splits

@@ -247,6 +247,25 @@ def test_assign_candidates_is_a_balanced_partition():
     assert assign_candidates(5, 2, [1, np.nan, 2, 3, 4]) == [[0, 2, 4], [1, 3]]   # unusable costs: strided
 
 
+def test_assign_groups_keeps_groups_whole_or_falls_back():
+    from spark_sklearn_b200.dist import assign_groups, assign_candidates
+    nc, ng, world = 8, 16, 2                                                # the 2-GPU weak-scaling grid: 8 C x 16 gamma
+    C = np.logspace(-1, 2.5, nc); G = np.geomspace(1 / 4096, 1 / 256, ng)
+    cc, gg = np.meshgrid(C, G, indexing="ij")
+    gd = gg.ravel() * 512
+    cost = np.minimum(4 + 10.3 * (cc.ravel() * gd) ** 0.95, 9 + 7.3 / gd)
+    keys = [("rbf", g) for g in gg.ravel()]
+    parts = assign_groups(len(cost), world, cost, keys)
+    assert sorted(sum(parts, [])) == list(range(len(cost)))
+    assert all(len({keys[c] for c in p}) == ng // world for p in parts)      # 8 whole gamma groups per rank
+    load = [cost[p].sum() for p in parts]
+    assert max(load) <= 1.08 * min(load)
+    # too few groups for the ranks, or loads that cannot balance: candidate dealing
+    assert assign_groups(len(cost), 16, cost, keys) == assign_candidates(len(cost), 16, cost)
+    skew = cost.copy(); skew[np.array([k == keys[0] for k in keys])] *= 100
+    assert assign_groups(len(cost), world, skew, keys) == assign_candidates(len(cost), world, skew)
+
+
 # ------------------------------------------------------------------ multi-rank (gloo, CPU) --------
 def _worker(rank, world, port, q):
     import torch.distributed as dist
