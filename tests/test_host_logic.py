@@ -306,3 +306,37 @@ def test_candidates_strided_over_ranks_allgather_gloo(world, oracle_backend):
     for rank, res in got:
         for k, v in res.items():
             np.testing.assert_array_equal(v, np.asarray(single[k], float), err_msg="rank %d %s" % (rank, k))
+
+
+# ------------------------------------------------------------------ bench.py contract (CPU arm) -----
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the arm the driver times next to ours) on the reduced workload: exactly one stdout
+    line, the contract's keys, the CPU-reference bookkeeping; library chatter goes to stderr."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c2_small",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "impl"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "candidate-fits/sec" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["gpu_launches"] == 0
+
+
+def test_bench_weak_scaling_grids_keep_64_candidates_per_gpu():
+    sys.path.insert(0, ROOT)
+    import bench
+    from spark_sklearn_b200 import workloads as W
+    for n in (1, 2, 4, 8):
+        w = bench.scaled_workload("c2", n)
+        assert len(W.candidates(w)) == 64 * n
+        g = w["param_grid"]
+        assert min(g["gamma"]) == 1 / 4096 and max(g["gamma"]) == 1 / 256 and abs(max(g["C"]) - 10 ** 2.5) < 1e-9
+    idx, desc = bench.cpu_sample(W.candidates(bench.scaled_workload("c2", 1)), 5, 2)
+    assert len(idx) == 2 and "10 fits" in desc
+
