@@ -46,7 +46,7 @@ enum gs_dtype { GS_F32 = 0, GS_F64 = 1 };
 
 enum gs_flags {
     GS_RETURN_TRAIN = 1,     /* also fill train_scores (reference return_train_score=True)   */
-    GS_GRAM_TENSOR = 2,      /* build the Gram on tcgen05 tensor cores (3xBF16 split, fp32-faithful)
+    GS_GRAM_TENSOR = 2,      /* build the Gram on tcgen05 tensor cores (3xTF32 split, fp32-faithful)
                                 instead of the float64 Gram that reproduces libsvm bit for bit */
     GS_NO_SHRINKING = 4      /* SVC(shrinking=False)                                         */
 };

@@ -70,6 +70,10 @@ class B200BaseSearchCV(BaseSearchCV):
         splits = list(cv.split(X, y, groups))
         n_splits = len(splits)
         candidate_params = [dict(p) for p in parameter_iterable]
+        rank, world = _dist.rank_world()
+        if world > 1:                                         # one candidate list and one set of folds for all ranks: rank 0's
+            candidate_params, splits = _dist.broadcast_plan((candidate_params, splits))
+            n_splits = len(splits)
         n_param_candidates = len(candidate_params)
         if self.verbose > 0:                                  # reference base_search.py:48-52
             print("Fitting {0} folds for each of {1} candidates, totalling"
@@ -81,13 +85,12 @@ class B200BaseSearchCV(BaseSearchCV):
         fold_id = _est.fold_ids_from_splits(splits, len(X_arr))
 
         # ---- the fan-out: every (candidate, fold) task in one engine call per rank ----
-        rank, world = _dist.rank_world()
         plan = adapter.plan(clone(estimator), candidate_params, X_arr, y_arr, fold_id, n_splits)
         # candidates dealt to the GPUs by predicted cost (the reference leaves the placement of its tasks to Spark)
         parts = _dist.assign_for_plan(plan, n_param_candidates, world)
         my = parts[rank]
         local = plan.evaluate(my, return_train=self.return_train_score, error_score=self.error_score)
-        out = _dist.allgather_candidates(local, my, n_param_candidates, n_splits, world, parts)
+        out = _dist.allgather_candidates(local, my, n_param_candidates, n_splits, world, parts, device=getattr(getattr(plan, "engine", None), "device", None))
         test_scores, train_scores = out["test"], out["train"]
         fit_time, score_time = out["fit_time"], out["score_time"]
         self.device_profile_ = plan.profile()

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200gs.so")
-SOURCES = ["api.cu", "gram.cu", "smo.cu", "smo_colown.cu", "score.cu", "linear.cu", "logreg.cu", "gemm_tc.cu"]
+SOURCES = ["api.cu", "gram.cu", "smo.cu", "smo_lean.cu", "smo_colown.cu", "score.cu", "linear.cu", "logreg.cu", "gemm_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-cudart", "static"]
 

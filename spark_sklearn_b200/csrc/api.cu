@@ -339,7 +339,7 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
             sp_seg[s * 8 + 4 + e] = std::min(runs[e].second, (int)ldk) - runs[e].first;
         }
     }
-    if (lmax > smo_max_rows() && lmax > smo_colown_max_rows(4)) {
+    if (lmax > smo_max_rows() && lmax > smo_colown_max_rows(4) && lmax >= 16383) {
         gs_set_error(h, "gs_svc: sub-problem with " + std::to_string(lmax) + " rows exceeds the resident-state SMO kernel limit of " +
                             std::to_string(smo_max_rows()));
         return GS_ERR_UNSUPPORTED;
@@ -428,8 +428,11 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
                     P.n_pos = sp_npos[s];
                     P.ldk = ldk; P.C = Cv[c]; P.eps = tol; P.max_iter = max_iter;
                     P.shrinking = (flags & GS_NO_SHRINKING) ? 0 : 1;
-                    P.alpha = (double *)wl; wl += P.l;          // offsets now, pointers below
-                    P.Gbar = (double *)wl; wl += P.l;
+                    P.nslots = 0;
+                    for (int e = 0; e < P.nseg; e++) P.nslots += P.seg_len[e];
+                    const size_t wlen = ((size_t)std::max(P.l, P.nslots) + 3) & ~(size_t)3;   // by position or by slot, 32-byte multiples
+                    P.alpha = (double *)wl; wl += wlen;         // offsets now, pointers below
+                    P.Gbar = (double *)wl; wl += wlen;
                     P.scratch = (int *)ws; ws += 2 * (size_t)P.l + 64;
                     probs.push_back(P);
                     prob_task.push_back(t);
@@ -495,6 +498,17 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
         // Development switches: B200GS_SMO_CLUSTER (0/2/4/8),
         // B200GS_SMO_CLUSTER_N.
         std::string why;
+        // single-CTA launches go to the slot-layout kernel (smo_lean.cu) when every problem of the batch has one
+        int max_slots = 0;
+        bool lean_ok = lmax < 16383 && !(getenv("B200GS_SMO_LEAN") && atoi(getenv("B200GS_SMO_LEAN")) == 0);
+        for (int q = 0; q < np && lean_ok; q++) {
+            lean_ok = probs[q].nseg > 0 && probs[q].nslots <= smo_lean_max_slots();
+            max_slots = std::max(max_slots, probs[q].nslots);
+        }
+        auto launch_single = [&](const int *ord, int cnt, cudaStream_t s_) -> cudaError_t {
+            if (lean_ok) return launch_smo_lean(d_probs, ord, cnt, max_slots, fast, s_);
+            return launch_smo(d_probs, ord, cnt, lmax, fast, (int)ldk, s_, &why);
+        };
         int cl = 0, n_cl = 0;
         if (lmax > 2048) {
             if (np * 8 <= h->sm_count) { cl = 8; n_cl = np; }
@@ -525,7 +539,7 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
             if (np - n_cl > 0) {
                 cudaStreamWaitEvent(h->stream_hi, ready, 0);
                 launch_delay(30000, h->stream_hi);
-                ce = launch_smo(d_probs, d_order + n_cl, np - n_cl, lmax, fast, (int)ldk, h->stream_hi, &why);
+                ce = launch_single(d_order + n_cl, np - n_cl, h->stream_hi);
                 if (ce != cudaSuccess) { gs_set_error(h, why.empty() ? std::string("launch_smo: ") + cudaGetErrorString(ce) : why); return why.empty() ? GS_ERR_CUDA : GS_ERR_UNSUPPORTED; }
                 pf.launches += 2;
                 cudaEventRecord(done, h->stream_hi);
@@ -533,7 +547,7 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
             }
             cudaEventDestroy(ready); cudaEventDestroy(done);
         } else {
-            cudaError_t ce = launch_smo(d_probs, d_order, np, lmax, fast, (int)ldk, st, &why);
+            cudaError_t ce = launch_single(d_order, np, st);
             if (ce != cudaSuccess) { gs_set_error(h, why.empty() ? std::string("launch_smo: ") + cudaGetErrorString(ce) : why); return why.empty() ? GS_ERR_CUDA : GS_ERR_UNSUPPORTED; }
             pf.launches++;
         }

@@ -87,11 +87,16 @@ struct SmoProblem {
     // copies only these parts of a K row into shared memory (a fold's training rows are 2-3 contiguous runs of the
     // class-sorted dataset: 32 KB of a 40 KB row in config 2).  nseg == 0: copy the whole row.
     int nseg, seg_start[4], seg_len[4];
+    int nslots;           // sum of seg_len: size of the slot space of smo_lean.cu (0 when nseg == 0)
 };
 // Solve problems order[0..n_prob) (one CTA each); lmax = max l (selects the template instance).
 cudaError_t launch_smo(const SmoProblem *d_probs, const int *d_order, int n_prob, int lmax, bool fast, int rowcap,
                        cudaStream_t st, std::string *why);
 int smo_max_rows();   // largest sub-problem the resident-state kernel supports
+// smo_lean.cu: the throughput instance (static slots = the problem's column runs, two or more sub-problems per SM).  Every
+// problem of the launch needs a slot layout: nseg > 0, nslots <= smo_lean_max_slots(), l < 16383; alpha and Gbar hold nslots doubles.
+int smo_lean_max_slots();
+cudaError_t launch_smo_lean(const SmoProblem *d_probs, const int *d_order, int n_prob, int max_slots, bool fast, cudaStream_t st);
 // smo_colown.cu: the same solver with one sub-problem spread over a thread-block cluster of cl CTAs (DSMEM exchange)
 int smo_colown_max_rows(int cl);
 void launch_delay(unsigned ns, cudaStream_t st);      // one thread sleeping ns nanoseconds (stream-ordering aid)

@@ -13,6 +13,10 @@
 //      products are one small kernel per iteration.  Converged systems freeze; non-convergence fails loudly.
 //   4. R^2 on the held-out fold and on the training rows from the Gram statistics in float64 (quadratic forms),
 //      no pass over X.
+// With fit_intercept the Grams are formed from SHIFTED data, Z = [X - c | y - c_y | 1] with c the column means over all
+// rows (float64 sums, rounded to float32): the raw-moment subtractions X^T X - n xbar xbar^T and yy - ys^2/n then cancel
+// nothing even when a feature's mean dwarfs its spread (scikit-learn centres before forming products, _ridge.py:964).
+// w and R^2 are invariant under the shift; the intercept gets c_y - c.w added back.
 #include "common.cuh"
 #include <algorithm>
 #include <cmath>
@@ -24,8 +28,25 @@ namespace {
 constexpr int CG_MAX_ITER = 4000;
 constexpr double CG_TOL = 1e-6;          // relative residual; fp32 Cholesky (sklearn) is accurate to ~cond*6e-8
 
-// Zt[j][poff[b] + r] = X[row][j] (j<d) | y[row] (j==d) | 1 (j==d+1); rows of block b are row0[b] .. row0[b]+cnt[b]
-__global__ void build_zt_kernel(const float *__restrict__ X, const float *__restrict__ y, int d, int n_blocks,
+// shift[j] = (float) mean over all rows of column j of [X | y]  (float64 accumulation); block = 32 columns x 32 row stripes
+__global__ void column_means_kernel(const float *__restrict__ X, const float *__restrict__ y, int n, int d, float *__restrict__ shift)
+{
+    __shared__ double acc[32][33];
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    double s = 0;
+    if (j <= d)
+        for (int r = threadIdx.y; r < n; r += 32) s += (double)(j < d ? X[(size_t)r * d + j] : y[r]);
+    acc[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && j <= d) {
+        double t = 0;
+        for (int q = 0; q < 32; q++) t += acc[q][threadIdx.x];
+        shift[j] = (float)(t / (double)n);
+    }
+}
+
+// Zt[j][poff[b] + r] = X[row][j] - shift[j] (j<d) | y[row] - shift[d] (j==d) | 1 (j==d+1); rows of block b are row0[b] .. row0[b]+cnt[b]
+__global__ void build_zt_kernel(const float *__restrict__ X, const float *__restrict__ y, const float *__restrict__ shift, int d, int n_blocks,
                                 const int *__restrict__ row0, const int *__restrict__ cnt, const int *__restrict__ poff,
                                 float *__restrict__ Zt, int64_t ldz)
 {
@@ -39,8 +60,8 @@ __global__ void build_zt_kernel(const float *__restrict__ X, const float *__rest
         float v = 0.f;
         if (r < cnt[b]) {
             const int row = row0[b] + r;
-            if (j < d) v = X[(size_t)row * d + j];
-            else if (j == d) v = y[row];
+            if (j < d) v = X[(size_t)row * d + j] - shift[j];
+            else if (j == d) v = y[row] - shift[d];
             else if (j == d + 1) v = 1.f;
         }
         tile[threadIdx.y][threadIdx.x] = v;
@@ -301,7 +322,7 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     GS_CUDA(bZ.reserve((size_t)Dp * ldz * 4)); GS_CUDA(bZh.reserve((size_t)Dp * ldz * 4)); GS_CUDA(bZl.reserve((size_t)Dp * ldz * 4));
     GS_CUDA(bG.reserve((size_t)(nb + nq) * Dp * Dp * 4));                   // per-block Grams, then the chunk partials
     const size_t tBytes = (size_t)Dp * Dp * 8, meansBytes = (size_t)groups * (dp + 2) * 8;
-    GS_CUDA(bMisc.reserve(tBytes + meansBytes + (size_t)nsys * (8 + 8 + 16) + (size_t)n_cand * 8 + 256));
+    GS_CUDA(bMisc.reserve(tBytes + meansBytes + (size_t)nsys * (8 + 8 + 16) + (size_t)n_cand * 8 + (size_t)(d + 1) * 4 + 256));
     GS_CUDA(bA.reserve((size_t)groups * dp * dp * 4 * 3 + (size_t)groups * dp * 4));
     GS_CUDA(bV.reserve((size_t)nsys * dp * 4 * (6 + (size_t)((dp + TC_KCHUNK - 1) / TC_KCHUNK))));
     const int nkc = (dp + TC_KCHUNK - 1) / TC_KCHUNK;                          // K-chunks of the CG product
@@ -309,6 +330,7 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     double *dT = bMisc.as<double>();
     double *dMeans = dT + (size_t)Dp * Dp;
     double *dRR = dMeans + (size_t)groups * (dp + 2), *dBB = dRR + nsys, *dOut = dBB + nsys, *dAlpha = dOut + 2 * (size_t)nsys;
+    float *dShift = reinterpret_cast<float *>(dAlpha + n_cand);               // [d + 1] column shifts of [X | y]
     float *dA = bA.as<float>(), *dAh = dA + (size_t)groups * dp * dp, *dAl = dAh + (size_t)groups * dp * dp,
           *dRhs = dAl + (size_t)groups * dp * dp;
     float *dX = bV.as<float>(), *dR = dX + (size_t)nsys * dp, *dP = dR + (size_t)nsys * dp, *dPh = dP + (size_t)nsys * dp,
@@ -342,7 +364,10 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     GS_CUDA(cudaMemsetAsync(bZ.p, 0, (size_t)Dp * ldz * 4, st));
     {
         dim3 grid((TC_KCHUNK + 31) / 32, (D + 31) / 32, nq), block(32, 32);
-        build_zt_kernel<<<grid, block, 0, st>>>(h->dX.as<float>(), h->dYt.as<float>(), d, nq, dRow0, dCnt, dPoff, bZ.as<float>(), ldz);
+        if (fit_intercept) column_means_kernel<<<(d + 1 + 31) / 32, dim3(32, 32), 0, st>>>(h->dX.as<float>(), h->dYt.as<float>(), n, d, dShift);
+        else GS_CUDA(cudaMemsetAsync(dShift, 0, (size_t)(d + 1) * 4, st));
+        GS_CUDA(cudaGetLastError());
+        build_zt_kernel<<<grid, block, 0, st>>>(h->dX.as<float>(), h->dYt.as<float>(), dShift, d, nq, dRow0, dCnt, dPoff, bZ.as<float>(), ldz);
         GS_CUDA(cudaGetLastError());
     }
     GS_CUDA(launch_split_tf32(bZ.as<float>(), bZh.as<float>(), bZl.as<float>(), (size_t)Dp * ldz, st));
@@ -352,7 +377,7 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     GS_CUDA(launch_gemm_nt_tf32x3(mzh, mzl, mzh, mzl, dBatchG, nq, D, D, 1.0f, false, st));
     sum_grams_kernel<<<592, 256, 0, st>>>(dGq, dQs, nb, (int64_t)Dp * Dp, bG.as<float>(), dT);
     GS_CUDA(cudaGetLastError());
-    launches += 4;
+    launches += 5;
     cudaEventRecord(ev[1], st);
 
     // ---- 2. per-group centred systems ----
@@ -410,17 +435,18 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
             }
         h->prof.d2h_bytes = (int64_t)out.size() * 8;
     } else {
-        std::vector<float> w(dp);
+        std::vector<float> w(dp), shift(d + 1);
         std::vector<double> means(dp + 2);
         GS_CUDA(cudaMemcpyAsync(w.data(), dX, (size_t)dp * 4, cudaMemcpyDeviceToHost, st));
+        GS_CUDA(cudaMemcpyAsync(shift.data(), dShift, (size_t)(d + 1) * 4, cudaMemcpyDeviceToHost, st));
         GS_CUDA(cudaMemcpyAsync(means.data(), dMeans, (size_t)(dp + 2) * 8, cudaMemcpyDeviceToHost, st));
         cudaEventRecord(ev[3], st);
         GS_CUDA(cudaStreamSynchronize(st));
-        double b0 = means[dp];
+        double b0 = means[dp] + (double)shift[d];                  // intercept in the caller's (unshifted) coordinates
         for (int j = 0; j < d; j++) {
             const int o = j;                                       // feature order is unchanged
             coef_out[o] = (double)w[j];
-            b0 -= means[j] * (double)w[j];
+            b0 -= (means[j] + (double)shift[j]) * (double)w[j];
         }
         coef_out[d] = fit_intercept ? b0 : 0.0;
     }

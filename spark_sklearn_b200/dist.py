@@ -74,7 +74,25 @@ def assign_for_plan(plan, n_cand, world):
     return assign_candidates(n_cand, world, costs)
 
 
-def allgather_candidates(local, my, n_cand, n_splits, world, parts=None):
+def broadcast_plan(obj):
+    """The reference enumerates candidates and CV splits ONCE, on the driver (base_search.py:34-61), and ships them to the
+    executors.  With one process per GPU every rank would otherwise draw its own: RandomizedSearchCV(random_state=None)
+    or a shuffling splitter reseeded per process (base_search.py:39-41) give each rank different candidates / folds,
+    and the all-gather would then merge score blocks of different parameter sets.  Rank 0's objects win."""
+    td = _td()
+    if td is None or td.get_world_size() == 1:
+        return obj
+    box = [obj if td.get_rank() == 0 else None]
+    if td.get_backend() == "nccl":
+        import torch
+        import os
+        td.broadcast_object_list(box, src=0, device=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
+    else:
+        td.broadcast_object_list(box, src=0)
+    return box[0]
+
+
+def allgather_candidates(local, my, n_cand, n_splits, world, parts=None, device=None):
     """local: dict of [len(my), n_splits] arrays (test, train|None, fit_time, score_time) for the
     candidates ``my`` of this rank.  Returns the same dict for all n_cand candidates, identical on
     every rank and independent of the number of ranks.  ``parts`` = assign_candidates(...) (default: strided)."""
@@ -90,7 +108,11 @@ def allgather_candidates(local, my, n_cand, n_splits, world, parts=None):
     for j, k in enumerate(keys):
         if local.get(k) is not None and len(my):
             buf[:len(my), :, j] = local[k]
-    dev = torch.device("cuda", torch.cuda.current_device()) if td.get_backend() == "nccl" else torch.device("cpu")
+    # the gather buffer lives on the engine's GPU (LOCAL_RANK), not on whatever torch's current device happens to be
+    if td.get_backend() == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+    else:
+        dev = torch.device("cpu")
     t = torch.from_numpy(buf).to(dev)
     gathered = torch.empty((world * per,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
     td.all_gather_into_tensor(gathered, t.contiguous())

@@ -290,6 +290,10 @@ class RidgePlan(_Plan):
         y = np.asarray(y)
         if y.ndim != 1:
             raise NotImplementedError("multi-output Ridge is not supported by the CUDA path")
+        if self.X.dtype != np.float32:
+            # scikit-learn solves float64 input in float64; the tensor-core Grams are fp32-faithful (3xTF32 split)
+            warnings.warn("spark_sklearn_b200 Ridge computes in float32: float64 X is rounded to float32 before the "
+                          "search (scores agree with scikit-learn's float64 fit to about 1e-6 relative)", UserWarning)
         self.engine.set_data(self.X.astype(np.float32, copy=False), fold_id, n_splits, y_target=y.astype(np.float32))
 
     def _check(self, p):
@@ -348,14 +352,20 @@ class LogRegPlan(_Plan):
         self.classes, self.y_class = np.unique(np.asarray(y), return_inverse=True)
         if len(self.classes) != 2:
             raise NotImplementedError("LogisticRegression CUDA path is binary only (got %d classes)" % len(self.classes))
+        if self.X.dtype != np.float32:
+            warnings.warn("spark_sklearn_b200 LogisticRegression computes in float32: float64 X is rounded to float32 "
+                          "before the search", UserWarning)
         self.engine.set_data(self.X.astype(np.float32, copy=False), fold_id, n_splits,
                              y_class=self.y_class.astype(np.int32))
 
     def _check(self, p):
         if p.get("solver", "lbfgs") != "lbfgs":
             raise NotImplementedError("LogisticRegression solver=%r has no CUDA path (lbfgs does)" % (p["solver"],))
-        if p.get("penalty", "l2") not in ("l2", "deprecated", None) and p.get("l1_ratio") not in (None, 0, 0.0):
-            raise NotImplementedError("only the L2 penalty has a CUDA path")
+        # scikit-learn 1.9: penalty='deprecated' (the default) or 'l2' with l1_ratio None/0 is the L2 problem the kernel
+        # solves; penalty=None (no regularisation, C ignored), 'l1', 'elasticnet' or any l1_ratio > 0 are other problems
+        if p.get("penalty", "l2") not in ("l2", "deprecated") or p.get("l1_ratio") not in (None, 0, 0.0):
+            raise NotImplementedError("LogisticRegression penalty=%r, l1_ratio=%r has no CUDA path (only the L2 penalty does)"
+                                      % (p.get("penalty"), p.get("l1_ratio")))
         if p.get("class_weight") is not None:
             raise NotImplementedError("LogisticRegression class_weight is not supported by the CUDA path")
         if not (isinstance(p["C"], numbers.Real) and p["C"] > 0):

@@ -308,6 +308,50 @@ def test_candidates_strided_over_ranks_allgather_gloo(world, oracle_backend):
             np.testing.assert_array_equal(v, np.asarray(single[k], float), err_msg="rank %d %s" % (rank, k))
 
 
+def _worker_unseeded(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from scipy.stats import loguniform
+    from sklearn import svm
+    from sklearn.model_selection import StratifiedKFold
+    from spark_sklearn_b200 import RandomizedSearchCV, base_search
+    base_search._est.adapter_for = lambda est: OracleAdapter
+    X, y = _iris()
+    np.random.seed(1000 + rank)                                        # every rank would draw its own candidates ...
+    import random
+    random.seed(2000 + rank)                                           # ... and reseed the splitter differently
+    s = RandomizedSearchCV(None, svm.SVC(gamma='auto'), {"C": loguniform(0.1, 100)}, n_iter=6, random_state=None,
+                           cv=StratifiedKFold(4, shuffle=True, random_state=None), refit=False).fit(X, y)
+    q.put((rank, [p["C"] for p in s.cv_results_["params"]],
+           {k: np.asarray(v, float) for k, v in s.cv_results_.items() if "score" in k}))
+    dist.destroy_process_group()
+
+
+def test_unseeded_search_uses_rank0_candidates_and_folds_gloo(oracle_backend):
+    """RandomizedSearchCV(random_state=None) with a shuffling splitter under 2 ranks: the reference samples candidates and
+    folds once on the driver (base_search.py:34-61); here rank 0's are broadcast, so every rank reports the same parameter
+    sets and the merged scores belong to them (checked by re-scoring rank 0's candidates... on every rank's result)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000 + 17
+    ps = [ctx.Process(target=_worker_unseeded, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = sorted(q.get(timeout=180) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, c0, r0), (_, c1, r1) = got
+    assert c0 == c1 and len(c0) == 6
+    for k in r0:
+        np.testing.assert_array_equal(r0[k], r1[k], err_msg=k)
+    assert np.all(r0["mean_test_score"] > 0.5)
+
+
 # ------------------------------------------------------------------ bench.py contract (CPU arm) -----
 def test_bench_reference_arm_prints_one_json_line():
     """`bench.py --impl reference` (the arm the driver times next to ours) on the reduced workload: exactly one stdout
