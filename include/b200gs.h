@@ -57,6 +57,24 @@ int gs_create(int device, gs_handle **out);
 void gs_destroy(gs_handle *h);
 const char *gs_last_error(const gs_handle *h);      /* h may be NULL: last gs_create failure  */
 int gs_version(void);
+/* Scorer of the following gs_svc / gs_logreg / gs_ridge calls.  Replaces: check_scoring(estimator, scoring) and the scorer
+ * call inside _fit_and_score (reference base_search.py:43,83-87; grid_search.py:212-214 `scoring=`).  The score is
+ * computed on the device from the decision values / Gram statistics already in HBM.  pos_class: class id (index into the
+ * sorted labels) that precision / recall / f1 treat as positive (scikit-learn's pos_label=1). */
+enum {
+    GS_SCORE_DEFAULT = 0,            /* accuracy (classifiers) / r2 (Ridge): estimator.score                */
+    GS_SCORE_BALANCED_ACCURACY = 1,
+    GS_SCORE_F1 = 2, GS_SCORE_PRECISION = 3, GS_SCORE_RECALL = 4,          /* binary, class pos_class      */
+    GS_SCORE_ROC_AUC = 5,            /* binary: rank statistic of the decision values                        */
+    GS_SCORE_F1_MACRO = 6, GS_SCORE_F1_MICRO = 7, GS_SCORE_F1_WEIGHTED = 8,
+    GS_SCORE_NEG_MSE = 16, GS_SCORE_NEG_RMSE = 17                          /* Ridge                         */
+};
+int gs_set_scoring(gs_handle *h, int32_t kind, int32_t pos_class);
+
+/* Number of sm_100 GPUs this process can drive (0: none).  Replaces: the executor count Spark reports to the driver
+ * (reference base_search.py:62 sc.parallelize(..., len(tasks)) leaves placement to Spark); the in-process scheduler of
+ * spark_sklearn_b200/base_search.py opens one handle per device and deals the candidates over them. */
+int gs_device_count(void);
 
 /* ---- data: the "broadcast" (reference base_search.py:63-65) ------------------------------ */
 /*
@@ -132,6 +150,9 @@ double gs_svc_predicted_iterations(int32_t kernel, double C, double gamma, int32
 /* Number of sub-problems a search puts on 4-CTA clusters, given the predicted costs sorted in DESCENDING order and
  * the SM count (the makespan model documented in DESIGN.md section 4). */
 int32_t gs_svc_cluster_count(const double *cost_desc, int32_t n, int32_t sm_count);
+/* Three-tier schedule of the slot-layout solver: of problems sorted by descending predicted cost, *n_cluster go on 4-CTA
+ * clusters, the next *n_exclusive get an SM each, the rest share SMs two by two (makespan model in csrc/api.cu). */
+void gs_svc_schedule(const double *cost_desc, int32_t n, int32_t sm_count, int32_t *n_cluster, int32_t *n_exclusive);
 
 /* ---- measurement ----------------------------------------------------------------------- */
 typedef struct gs_profile {
@@ -149,6 +170,8 @@ typedef struct gs_profile {
     double gram_bytes;         /* algorithmic bytes of the Gram build                           */
     int64_t h2d_bytes;         /* bytes copied host->device by gs_set_data + the search         */
     int64_t d2h_bytes;         /* bytes copied device->host by the search                       */
+    float ms_tensor;           /* CUDA-event time of the tcgen05 contraction launches of the call */
+    double tensor_flops;       /* TF32 tensor-core flops those launches executed (3 MMAs per product) */
 } gs_profile;
 int gs_get_profile(const gs_handle *h, gs_profile *out);
 

@@ -57,10 +57,6 @@ class B200BaseSearchCV(BaseSearchCV):
         if hasattr(cv, 'random_state'):                       # reference base_search.py:39-41
             if not cv.random_state:
                 cv.random_state = randint(1000, 9999)
-        if self.scoring is not None:
-            raise NotImplementedError(
-                "spark_sklearn_b200 fuses the estimator's default score (accuracy / r2) into its CUDA kernels; "
-                "scoring=%r is not implemented and there is no CPU fallback" % (self.scoring,))
         if self.fit_params:
             raise NotImplementedError("fit_params are not supported by the CUDA path (no CPU fallback)")
         self.scorer_ = check_scoring(self.estimator, scoring=self.scoring)
@@ -80,20 +76,53 @@ class B200BaseSearchCV(BaseSearchCV):
                   " {2} fits".format(n_splits, n_param_candidates, n_param_candidates * n_splits))
 
         adapter = _est.adapter_for(estimator)                 # raises for estimators without a CUDA path
+        if self.scoring is not None and (not isinstance(self.scoring, str) or self.scoring not in getattr(adapter, "scorers", {})):
+            raise NotImplementedError(
+                "scoring=%r has no fused CUDA scorer for %s (available: %s); callables and multi-metric scoring would need "
+                "the fitted estimators on the host and there is no CPU fallback"
+                % (self.scoring, type(estimator).__name__, sorted(k for k in getattr(adapter, "scorers", {}) if k)))
         X_arr = np.asarray(X)
         y_arr = None if y is None else np.asarray(y)
         fold_id = _est.fold_ids_from_splits(splits, len(X_arr))
 
-        # ---- the fan-out: every (candidate, fold) task in one engine call per rank ----
-        plan = adapter.plan(clone(estimator), candidate_params, X_arr, y_arr, fold_id, n_splits)
-        # candidates dealt to the GPUs by predicted cost (the reference leaves the placement of its tasks to Spark)
-        parts = _dist.assign_for_plan(plan, n_param_candidates, world)
-        my = parts[rank]
-        local = plan.evaluate(my, return_train=self.return_train_score, error_score=self.error_score)
-        out = _dist.allgather_candidates(local, my, n_param_candidates, n_splits, world, parts, device=getattr(getattr(plan, "engine", None), "device", None))
+        # ---- the fan-out: every (candidate, fold) task in one engine call per GPU ----
+        devices = _dist.local_devices() if (world == 1 and getattr(adapter, "multi_device", False)) else [None]
+        devices = devices[:max(1, n_param_candidates)]
+        if len(devices) > 1:
+            # the in-process scheduler: ONE fit() drives every visible GPU -- a handle and a host thread per device (ctypes
+            # releases the GIL for the whole gs_* call), the dataset uploaded once to each, candidates dealt by predicted cost,
+            # score blocks merged on the host.  The counterpart of sc.parallelize(tasks).map(fun).collect() on one node.
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(len(devices)) as pool:
+                plans = list(pool.map(lambda d: adapter.plan(clone(estimator), candidate_params, X_arr, y_arr, fold_id, n_splits,
+                                                             device=d), devices))
+                for p in plans:
+                    if self.scoring is not None or hasattr(p, "set_scoring"):
+                        p.set_scoring(self.scoring)           # raises for scorers without a fused CUDA path
+                parts = _dist.assign_for_plan(plans[0], n_param_candidates, len(devices))
+                locs = list(pool.map(lambda i: plans[i].evaluate(parts[i], return_train=self.return_train_score,
+                                                                 error_score=self.error_score) if parts[i] else None,
+                                     range(len(devices))))
+            out = _dist.merge_candidates(locs, parts, n_param_candidates, n_splits)
+            plan = plans[0]
+            self.device_profile_ = _dist.merge_profiles([p.profile() for p in plans])
+            self.devices_ = list(devices)
+            for p in plans[1:]:
+                p.close()
+        else:
+            plan = adapter.plan(clone(estimator), candidate_params, X_arr, y_arr, fold_id, n_splits)
+            if self.scoring is not None or hasattr(plan, "set_scoring"):
+                plan.set_scoring(self.scoring)                # raises for scorers without a fused CUDA path
+            # candidates dealt to the GPUs by predicted cost (the reference leaves the placement of its tasks to Spark)
+            parts = _dist.assign_for_plan(plan, n_param_candidates, world)
+            my = parts[rank]
+            local = plan.evaluate(my, return_train=self.return_train_score, error_score=self.error_score)
+            out = _dist.allgather_candidates(local, my, n_param_candidates, n_splits, world, parts,
+                                             device=getattr(getattr(plan, "engine", None), "device", None))
+            self.device_profile_ = plan.profile()
+            self.devices_ = [getattr(getattr(plan, "engine", None), "device", None)]
         test_scores, train_scores = out["test"], out["train"]
         fit_time, score_time = out["fit_time"], out["score_time"]
-        self.device_profile_ = plan.profile()
 
         test_sample_counts = np.array([len(te) for _, te in splits], dtype=int)
         results = dict()

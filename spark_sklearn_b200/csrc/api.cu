@@ -12,6 +12,43 @@
 
 static std::string g_create_error;
 
+// scikit-learn's count-based scores (metrics/_classification.py) from cnt[class][3] = {support, tp, predicted}, float64.
+// Undefined ratios follow zero_division="warn": 0.0.  accuracy_score :187; balanced_accuracy_score :2362 (mean recall over
+// the classes present in y_true); precision_recall_fscore_support :1573 with beta = 1: f = 2 tp / (2 tp + fp + fn).
+double gs_score_from_counts(int kind, int pos_class, int n_classes, const int *cnt)
+{
+    auto sup = [&](int c) { return (double)cnt[c * 3 + 0]; };
+    auto tp = [&](int c) { return (double)cnt[c * 3 + 1]; };
+    auto prd = [&](int c) { return (double)cnt[c * 3 + 2]; };
+    auto f1c = [&](int c) { const double den = sup(c) + prd(c); return den > 0 ? 2.0 * tp(c) / den : 0.0; };   // 2tp + fp + fn = support + predicted
+    double n = 0, correct = 0;
+    for (int c = 0; c < n_classes; c++) { n += sup(c); correct += tp(c); }
+    if (!(n > 0)) return NAN;
+    switch (kind) {
+    case GS_SCORE_DEFAULT: return correct / n;
+    case GS_SCORE_BALANCED_ACCURACY: {
+        double s = 0; int k = 0;
+        for (int c = 0; c < n_classes; c++) if (sup(c) > 0) { s += tp(c) / sup(c); k++; }
+        return k ? s / k : NAN;
+    }
+    case GS_SCORE_F1: return f1c(pos_class);
+    case GS_SCORE_PRECISION: return prd(pos_class) > 0 ? tp(pos_class) / prd(pos_class) : 0.0;
+    case GS_SCORE_RECALL: return sup(pos_class) > 0 ? tp(pos_class) / sup(pos_class) : 0.0;
+    case GS_SCORE_F1_MACRO: {
+        double s = 0;
+        for (int c = 0; c < n_classes; c++) s += f1c(c);
+        return s / n_classes;
+    }
+    case GS_SCORE_F1_MICRO: return correct / n;                         // single-label: micro f1 == accuracy
+    case GS_SCORE_F1_WEIGHTED: {
+        double s = 0;
+        for (int c = 0; c < n_classes; c++) s += f1c(c) * sup(c);
+        return s / n;
+    }
+    default: return NAN;
+    }
+}
+
 void gs_set_error(gs_handle *h, const std::string &msg)
 {
     if (h) h->err = msg; else g_create_error = msg;
@@ -34,15 +71,15 @@ __global__ void gather_rows_kernel(const T *__restrict__ src, const int *__restr
     }
 }
 
-struct EvTimer {       // accumulates elapsed ms between consecutive marks on one stream
+struct EvTimer {       // accumulates elapsed ms between consecutive marks on one stream (events from the handle's pool)
     cudaStream_t st;
+    EventPool &pool;
     std::vector<cudaEvent_t> evs;
     std::vector<int> tag;
-    explicit EvTimer(cudaStream_t s) : st(s) {}
+    EvTimer(cudaStream_t s, EventPool &p) : st(s), pool(p) {}
     void mark(int t)
     {
-        cudaEvent_t e;
-        cudaEventCreate(&e);
+        cudaEvent_t e = pool.get();
         cudaEventRecord(e, st);
         evs.push_back(e); tag.push_back(t);
     }
@@ -54,7 +91,6 @@ struct EvTimer {       // accumulates elapsed ms between consecutive marks on on
             cudaEventElapsedTime(&ms, evs[k - 1], evs[k]);
             if (tag[k] >= 0 && tag[k] < ntags) acc[tag[k]] += ms;
         }
-        for (auto e : evs) cudaEventDestroy(e);
         evs.clear(); tag.clear();
     }
 };
@@ -65,7 +101,27 @@ inline uint64_t dbits(double x) { uint64_t u; memcpy(&u, &x, 8); return u; }
 
 extern "C" {
 
-int gs_version(void) { return 100; }
+int gs_version(void) { return 101; }
+
+int gs_set_scoring(gs_handle *h, int32_t kind, int32_t pos_class)
+{
+    if (!h) return GS_ERR_ARG;
+    const bool known = (kind >= GS_SCORE_DEFAULT && kind <= GS_SCORE_F1_WEIGHTED) || kind == GS_SCORE_NEG_MSE || kind == GS_SCORE_NEG_RMSE;
+    if (!known || pos_class < 0 || pos_class > 31) { gs_set_error(h, "gs_set_scoring: unknown scorer or positive class"); return GS_ERR_ARG; }
+    h->score_kind = kind; h->score_pos = pos_class;
+    return GS_OK;
+}
+
+int gs_device_count(void)
+{
+    int count = 0, usable = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+    for (int d = 0; d < count; d++) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major == 10) usable = d + 1;   // handles index devices 0..n-1
+    }
+    return usable;
+}
 
 const char *gs_last_error(const gs_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -100,6 +156,9 @@ int gs_create(int device, gs_handle **out)
             g_create_error = cudaGetErrorString(e); cudaStreamDestroy(h->stream); delete h; return GS_ERR_CUDA;
         }
     }
+    if ((e = cudaStreamCreateWithFlags(&h->stream_lo, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e); cudaStreamDestroy(h->stream); cudaStreamDestroy(h->stream_hi); delete h; return GS_ERR_CUDA;
+    }
     memset(&h->prof, 0, sizeof h->prof);
     *out = h;
     return GS_OK;
@@ -111,9 +170,11 @@ void gs_destroy(gs_handle *h)
     cudaSetDevice(h->device);
     h->dX.release(); h->dY.release(); h->dFold.release(); h->dYt.release();
     h->dS.release(); h->dXsq.release(); h->dK.release(); h->dX64.release();
+    h->evp.release(); h->dScore.release();
     for (auto &w : h->dWork) w.release();
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream_hi) cudaStreamDestroy(h->stream_hi);
+    if (h->stream_lo) cudaStreamDestroy(h->stream_lo);
     delete h;
 }
 
@@ -158,8 +219,8 @@ int gs_set_data(gs_handle *h, const void *X, int32_t x_dtype, int64_t n, int64_t
     }
     for (int c = 0; c < h->n_classes; c++) h->class_start[c + 1] += h->class_start[c];
 
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    h->evp.reset();
+    cudaEvent_t e0 = h->evp.get(), e1 = h->evp.get();
     cudaEventRecord(e0, h->stream);
     const size_t esz = x_dtype == GS_F64 ? 8 : 4;
     GS_CUDA(h->dX.reserve((size_t)n * d * 4));
@@ -189,7 +250,6 @@ int gs_set_data(gs_handle *h, const void *X, int32_t x_dtype, int64_t n, int64_t
     cudaEventRecord(e1, h->stream);
     GS_CUDA(cudaStreamSynchronize(h->stream));
     cudaEventElapsedTime(&h->prof.ms_h2d, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     h->prof.h2d_bytes = (int64_t)n * d * (int64_t)esz + n * 9;
     return GS_OK;
 }
@@ -232,6 +292,38 @@ extern "C" int32_t gs_svc_cluster_count(const double *cost_desc, int32_t n, int3
     return pick;
 }
 
+// Three-tier schedule of the slot-layout solver (smo_lean.cu): how many of the predicted-longest problems go on 4-CTA
+// clusters (n_cluster) and how many of the next-longest get an SM to themselves (n_exclusive); the rest run two per SM.
+// Measured per-iteration times of an 8000-row sub-problem (profiles/r02_smo_*): 3.55 us on a 4-CTA cluster, 5.8 us alone on
+// an SM, 10.5 us when two share an SM (= 5.25 us of SM time per iteration; a cluster costs 14.2).  Only the RATIOS enter:
+//   T(n_cl, n_ex) = max( 0.34 c[0]                                       longest clustered problem
+//                        0.55 c[n_cl]                                    longest exclusive problem
+//                        0.50 sum(rest) / SMs left, 0.78 c[n_cl + n_ex]  shared SMs: throughput, and the longest shared
+//                                                                        problem (paired for most of its life, alone at the end) )
+// in units of (cost x shared-SM iteration time).  More specialised SMs only for a clear (3 %) predicted gain.
+extern "C" void gs_svc_schedule(const double *cost_desc, int32_t n, int32_t sm_count, int32_t *n_cluster, int32_t *n_exclusive)
+{
+    if (n_cluster) *n_cluster = 0;
+    if (n_exclusive) *n_exclusive = 0;
+    if (!cost_desc || n < 2 || sm_count < 8) return;
+    std::vector<double> suffix(n + 1, 0.0);
+    for (int q = n - 1; q >= 0; q--) suffix[q] = suffix[q + 1] + cost_desc[q];
+    double best = -1;
+    int bc = 0, be = 0;
+    const int max_cl = std::min(n - 1, sm_count / 4);
+    for (int nc = 0; nc <= max_cl; nc++) {
+        for (int ne = 0; nc + ne < n && 4 * nc + ne <= sm_count - 8; ne++) {
+            const int left = sm_count - 4 * nc - ne;
+            double t = std::max(0.50 * suffix[nc + ne] / left, 0.78 * cost_desc[nc + ne]);
+            if (nc > 0) t = std::max(t, 0.34 * cost_desc[0]);
+            if (ne > 0) t = std::max(t, 0.55 * cost_desc[nc]);
+            if (best < 0 || t < 0.97 * best || (t < best && nc + ne <= bc + be)) { best = t; bc = nc; be = ne; }
+        }
+    }
+    if (n_cluster) *n_cluster = bc;
+    if (n_exclusive) *n_exclusive = be;
+}
+
 static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double *Cv, const double *gamma,
                    double tol, int max_iter, uint32_t flags, bool refit,
                    double *test_scores, double *train_scores, int32_t *n_iter, int32_t *n_sv,
@@ -259,9 +351,9 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
     memset(&pf, 0, sizeof pf);
     pf.ms_h2d = keep_h2d; pf.h2d_bytes = keep_h2d_bytes;
     float acc[5] = {0, 0, 0, 0, 0};   // 0 gram, 1 kernel matrix, 2 solve, 3 score, 4 other
-    EvTimer tm(st);
-    cudaEvent_t ev_begin, ev_end;
-    cudaEventCreate(&ev_begin); cudaEventCreate(&ev_end);
+    h->evp.reset(); h->tt.reset();
+    EvTimer tm(st, h->evp);
+    cudaEvent_t ev_begin = h->evp.get(), ev_end = h->evp.get();
     cudaEventRecord(ev_begin, st);
     tm.mark(-1);
 
@@ -286,7 +378,9 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
         GS_CUDA(tc_make_map(&ml, xl, n, dpad, dpad));
         TcBatch hb{0, 0, 0, dpad, bs.as<float>(), ld32};
         GS_CUDA(cudaMemcpyAsync(bb.p, &hb, sizeof hb, cudaMemcpyHostToDevice, st));
+        h->tt.begin(h->evp, st);
         GS_CUDA(launch_gemm_nt_tf32x3(mh, ml, mh, ml, bb.as<TcBatch>(), 1, n, n, 1.0f, false, st));
+        h->tt.end(h->evp, st, 3.0 * 2.0 * n * (double)n * dpad);
         GS_CUDA(launch_widen_gram(bs.as<float>(), n, ld32, h->dS.as<double>(), h->dXsq.as<double>(), st));
         pf.launches += 3;
     } else {
@@ -380,6 +474,17 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
     std::vector<int> task_iter(n_tasks, 0), task_sv(n_tasks, 0);
     std::vector<double> task_fit_ms(n_tasks, 0.0);
     std::vector<int> all_counts((size_t)n_tasks * 4, 0);
+    std::vector<double> task_score((size_t)n_tasks * 2, 0.0);         // non-default scorers: test, train
+    std::vector<int> class_counts;
+    std::vector<unsigned long long> score_raw;
+    if (!refit && h->score_kind != GS_SCORE_DEFAULT) {
+        const int kd = h->score_kind;
+        if (kd == GS_SCORE_NEG_MSE || kd == GS_SCORE_NEG_RMSE) { gs_set_error(h, "gs_svc: regression scorer on a classifier"); return GS_ERR_ARG; }
+        if ((kd == GS_SCORE_ROC_AUC || kd == GS_SCORE_F1 || kd == GS_SCORE_PRECISION || kd == GS_SCORE_RECALL) && nc != 2) {
+            gs_set_error(h, "gs_svc: this scorer is defined for binary problems only"); return GS_ERR_UNSUPPORTED;
+        }
+        if (h->score_pos >= nc) { gs_set_error(h, "gs_svc: positive class out of range"); return GS_ERR_ARG; }
+    }
     int64_t total_iter = 0;
     double solve_bytes = 0;
 
@@ -505,11 +610,17 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
             lean_ok = probs[q].nseg > 0 && probs[q].nslots <= smo_lean_max_slots();
             max_slots = std::max(max_slots, probs[q].nslots);
         }
-        auto launch_single = [&](const int *ord, int cnt, cudaStream_t s_) -> cudaError_t {
-            if (lean_ok) return launch_smo_lean(d_probs, ord, cnt, max_slots, fast, s_);
+        auto launch_single = [&](const int *ord, int cnt, cudaStream_t s_, bool exclusive) -> cudaError_t {
+            if (lean_ok) return launch_smo_lean(d_probs, ord, cnt, max_slots, fast, exclusive, s_);
             return launch_smo(d_probs, ord, cnt, lmax, fast, (int)ldk, s_, &why);
         };
-        int cl = 0, n_cl = 0;
+        // Policy (measured on config 2 / config 4, profiles/): clusters and exclusive SMs buy LATENCY for the critical path at
+        // the price of SM time (gs_svc_schedule above); a throughput-bound search (config 4) uses neither.
+        //   * fewer problems than SMs: everything on the widest cluster that fits;
+        //   * otherwise the three-tier schedule of the slot-layout kernel, or -- when a problem has no slot layout -- the
+        //     two-tier schedule of the position-owned kernel (gs_svc_cluster_count).
+        // Development switches: B200GS_SMO_CLUSTER (0/2/4/8), B200GS_SMO_CLUSTER_N, B200GS_SMO_EXCLUSIVE_N.
+        int cl = 0, n_cl = 0, n_ex = 0;
         if (lmax > 2048) {
             if (np * 8 <= h->sm_count) { cl = 8; n_cl = np; }
             else if (np * 4 <= h->sm_count) { cl = 4; n_cl = np; }
@@ -517,37 +628,53 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
             else {
                 std::vector<double> sorted_cost(np);
                 for (int q = 0; q < np; q++) sorted_cost[q] = cost[order[q]];
-                n_cl = gs_svc_cluster_count(sorted_cost.data(), np, h->sm_count);
+                if (lean_ok) gs_svc_schedule(sorted_cost.data(), np, h->sm_count, &n_cl, &n_ex);
+                else n_cl = gs_svc_cluster_count(sorted_cost.data(), np, h->sm_count);
                 if (n_cl > 0) cl = 4;
             }
         }
         if (const char *e = getenv("B200GS_SMO_CLUSTER")) { cl = atoi(e); if (n_cl == 0) n_cl = std::max(1, np * 6 / 100); }
         if (const char *e = getenv("B200GS_SMO_CLUSTER_N")) n_cl = std::min(np, atoi(e));
         if (!(cl == 2 || cl == 4 || cl == 8) || lmax > smo_colown_max_rows(cl) || lmax <= 2048) n_cl = 0;
-        if (n_cl > 0) {
-            // The cluster launch must get its SMs before the single-CTA launch floods the GPU (a late start of the critical
+        if (const char *e = getenv("B200GS_SMO_EXCLUSIVE_N")) n_ex = atoi(e);
+        if (!lean_ok) n_ex = 0;
+        n_ex = std::max(0, std::min(n_ex, np - n_cl));
+        if (n_cl > 0 || n_ex > 0) {
+            // The latency tiers must get their SMs before the shared-SM launch floods the GPU (a late start of the critical
             // path costs the makespan that much: measured 292 vs 333 ms when the order of arrival flipped).  So the cluster
-            // kernel goes on the engine stream itself, in order behind the uploads; the single-CTA kernel goes on the second
-            // stream behind the same point plus a 30 us delay kernel, and the engine stream joins it again afterwards.
-            cudaEvent_t ready, done;
-            cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
-            cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
+            // kernel goes on the engine stream itself, in order behind the uploads; the exclusive and the shared launches go
+            // on two more streams behind the same point plus a 30 / 60 us delay kernel; the engine stream joins them afterwards.
+            cudaEvent_t ready = h->evp.get();
             cudaEventRecord(ready, st);
-            cudaError_t ce = launch_smo_colown(d_probs, d_order, n_cl, lmax, cl, fast, st);
-            if (ce != cudaSuccess) { gs_set_error(h, std::string("launch_smo_colown: ") + cudaGetErrorString(ce)); return GS_ERR_CUDA; }
-            pf.launches++;
-            if (np - n_cl > 0) {
+            cudaError_t ce = cudaSuccess;
+            if (n_cl > 0) {
+                ce = launch_smo_colown(d_probs, d_order, n_cl, lmax, cl, fast, st);
+                if (ce != cudaSuccess) { gs_set_error(h, std::string("launch_smo_colown: ") + cudaGetErrorString(ce)); return GS_ERR_CUDA; }
+                pf.launches++;
+            }
+            if (n_ex > 0) {
+                cudaEvent_t done = h->evp.get();
                 cudaStreamWaitEvent(h->stream_hi, ready, 0);
                 launch_delay(30000, h->stream_hi);
-                ce = launch_single(d_order + n_cl, np - n_cl, h->stream_hi);
+                ce = launch_single(d_order + n_cl, n_ex, h->stream_hi, true);
                 if (ce != cudaSuccess) { gs_set_error(h, why.empty() ? std::string("launch_smo: ") + cudaGetErrorString(ce) : why); return why.empty() ? GS_ERR_CUDA : GS_ERR_UNSUPPORTED; }
                 pf.launches += 2;
                 cudaEventRecord(done, h->stream_hi);
                 cudaStreamWaitEvent(st, done, 0);
             }
-            cudaEventDestroy(ready); cudaEventDestroy(done);
+            if (np - n_cl - n_ex > 0) {
+                cudaStream_t s2 = n_ex > 0 ? h->stream_lo : h->stream_hi;
+                cudaEvent_t done = h->evp.get();
+                cudaStreamWaitEvent(s2, ready, 0);
+                launch_delay(n_ex > 0 ? 60000 : 30000, s2);
+                ce = launch_single(d_order + n_cl + n_ex, np - n_cl - n_ex, s2, false);
+                if (ce != cudaSuccess) { gs_set_error(h, why.empty() ? std::string("launch_smo: ") + cudaGetErrorString(ce) : why); return why.empty() ? GS_ERR_CUDA : GS_ERR_UNSUPPORTED; }
+                pf.launches += 2;
+                cudaEventRecord(done, s2);
+                cudaStreamWaitEvent(st, done, 0);
+            }
         } else {
-            cudaError_t ce = launch_single(d_order, np, st);
+            cudaError_t ce = launch_single(d_order, np, st, false);
             if (ce != cudaSuccess) { gs_set_error(h, why.empty() ? std::string("launch_smo: ") + cudaGetErrorString(ce) : why); return why.empty() ? GS_ERR_CUDA : GS_ERR_UNSUPPORTED; }
             pf.launches++;
         }
@@ -565,8 +692,31 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
                                         h->dWork[4].as<double>() + (size_t)c0 * n, jch > 1 ? h->dWork[8].as<double>() : nullptr, st));
                 pf.launches += jch > 1 ? 2 : 1;
             }
-            GS_CUDA(launch_vote(h->dWork[4].as<double>(), d_rho, n, nc, h->dY.as<int>(), h->dFold.as<signed char>(),
-                                d_vt, (int)vtasks.size(), d_counts, st));
+            const int kind = h->score_kind, nvt = (int)vtasks.size();
+            if (kind == GS_SCORE_DEFAULT) {
+                GS_CUDA(launch_vote(h->dWork[4].as<double>(), d_rho, n, nc, h->dY.as<int>(), h->dFold.as<signed char>(),
+                                    d_vt, nvt, d_counts, st));
+            } else if (kind == GS_SCORE_ROC_AUC) {
+                // rank statistic of the decision values already in HBM (scikit-learn: roc_auc_score(y, decision_function(X)))
+                std::vector<int> meta((size_t)nvt * 2);
+                for (int v = 0; v < nvt; v++) { meta[v] = vtasks[v].first_col; meta[nvt + v] = vtasks[v].fold; }
+                GS_CUDA(h->dScore.reserve((size_t)nvt * (8 + 32)));
+                unsigned long long *d_auc = h->dScore.as<unsigned long long>();
+                int *d_meta = (int *)(d_auc + (size_t)nvt * 4);
+                GS_CUDA(cudaMemcpyAsync(d_meta, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice, st));
+                GS_CUDA(cudaMemsetAsync(d_auc, 0, (size_t)nvt * 32, st));
+                GS_CUDA(launch_auc_pairs_f64(h->dWork[4].as<double>(), n, n, h->class_start[1], h->dFold.as<signed char>(), d_meta, d_meta + nvt,
+                                             nvt, -1, d_auc, st));
+                score_raw.resize((size_t)nvt * 4);
+                GS_CUDA(cudaMemcpyAsync(score_raw.data(), d_auc, (size_t)nvt * 32, cudaMemcpyDeviceToHost, st));
+            } else {
+                GS_CUDA(h->dScore.reserve((size_t)nvt * 2 * nc * 3 * 4));
+                GS_CUDA(cudaMemsetAsync(h->dScore.p, 0, (size_t)nvt * 2 * nc * 3 * 4, st));
+                GS_CUDA(launch_vote_classes(h->dWork[4].as<double>(), d_rho, n, nc, h->dY.as<int>(), h->dFold.as<signed char>(),
+                                            d_vt, nvt, h->dScore.as<int>(), st));
+                class_counts.resize((size_t)nvt * 2 * nc * 3);
+                GS_CUDA(cudaMemcpyAsync(class_counts.data(), h->dScore.p, class_counts.size() * 4, cudaMemcpyDeviceToHost, st));
+            }
             pf.launches++;
         }
         tm.mark(3);
@@ -610,6 +760,24 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
         }
         for (size_t v = 0; v < vtasks.size(); v++)
             for (int e = 0; e < 4; e++) all_counts[(size_t)vtask_id[v] * 4 + e] = counts[v * 4 + e];
+        if (!refit && h->score_kind == GS_SCORE_ROC_AUC) {
+            for (size_t v = 0; v < vtasks.size(); v++) {
+                const int k = vtasks[v].fold;
+                double na_te = 0, nb_te = 0, na_tr = 0, nb_tr = 0;            // rows of the first / second class inside / outside fold k
+                for (int r = 0; r < n; r++) {
+                    const bool b = r >= h->class_start[1], te = h->fold[r] == k;
+                    (te ? (b ? nb_te : na_te) : (b ? nb_tr : na_tr)) += 1;
+                }
+                const unsigned long long *a = &score_raw[v * 4];
+                task_score[(size_t)vtask_id[v] * 2 + 0] = na_te * nb_te > 0 ? ((double)a[0] + 0.5 * (double)a[1]) / (na_te * nb_te) : NAN;
+                task_score[(size_t)vtask_id[v] * 2 + 1] = na_tr * nb_tr > 0 ? ((double)a[2] + 0.5 * (double)a[3]) / (na_tr * nb_tr) : NAN;
+            }
+        } else if (!refit && h->score_kind != GS_SCORE_DEFAULT) {
+            for (size_t v = 0; v < vtasks.size(); v++)
+                for (int sp = 0; sp < 2; sp++)
+                    task_score[(size_t)vtask_id[v] * 2 + sp] =
+                        gs_score_from_counts(h->score_kind, h->score_pos, nc, &class_counts[(v * 2 + sp) * nc * 3]);
+        }
         if (refit) {
             for (int q = 0; q < np; q++) {
                 if (rho_out) rho_out[q] = rho[q];
@@ -623,7 +791,7 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
     GS_CUDA(cudaStreamSynchronize(st));
     tm.collect(acc, 5);
     cudaEventElapsedTime(&pf.ms_total, ev_begin, ev_end);
-    cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end);
+    pf.ms_tensor = h->tt.collect(); pf.tensor_flops = h->tt.flops;
     pf.ms_gram = acc[0]; pf.ms_kernel_matrix = acc[1]; pf.ms_solve = acc[2]; pf.ms_score = acc[3];
     pf.smo_iterations = total_iter;
     pf.solve_bytes = solve_bytes;
@@ -631,8 +799,13 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
     if (!refit) {
         for (int t = 0; t < n_tasks; t++) {
             const int *cn = &all_counts[(size_t)t * 4];
-            test_scores[t] = cn[1] > 0 ? (double)cn[0] / (double)cn[1] : NAN;
-            if (train_scores) train_scores[t] = cn[3] > 0 ? (double)cn[2] / (double)cn[3] : NAN;
+            if (h->score_kind == GS_SCORE_DEFAULT) {
+                test_scores[t] = cn[1] > 0 ? (double)cn[0] / (double)cn[1] : NAN;
+                if (train_scores) train_scores[t] = cn[3] > 0 ? (double)cn[2] / (double)cn[3] : NAN;
+            } else {
+                test_scores[t] = task_score[(size_t)t * 2];
+                if (train_scores) train_scores[t] = task_score[(size_t)t * 2 + 1];
+            }
             if (n_iter) n_iter[t] = task_iter[t];
             if (n_sv) n_sv[t] = task_sv[t];
             if (fit_ms) fit_ms[t] = (float)task_fit_ms[t];

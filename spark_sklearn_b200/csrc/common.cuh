@@ -33,11 +33,47 @@ struct DevBuf {
     template <class T> T *as() const { return (T *)p; }
 };
 
+// CUDA events owned by the handle: created on first use, reused by every later call, destroyed with the handle
+// (no per-call cudaEventCreate / cudaEventDestroy, nothing to leak on an error return)
+struct EventPool {
+    std::vector<cudaEvent_t> ev;
+    size_t used = 0;
+    cudaEvent_t get()
+    {
+        if (used == ev.size()) { cudaEvent_t e = nullptr; cudaEventCreate(&e); ev.push_back(e); }
+        return ev[used++];
+    }
+    void reset() { used = 0; }
+    void release() { for (auto e : ev) cudaEventDestroy(e); ev.clear(); used = 0; }
+};
+
+// CUDA-event time and executed MMA flops of the tensor-core contraction launches of one call
+struct TensorTimer {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans;
+    double flops = 0;
+    cudaEvent_t open = nullptr;
+    void reset() { spans.clear(); flops = 0; open = nullptr; }
+    void begin(EventPool &p, cudaStream_t st) { open = p.get(); cudaEventRecord(open, st); }
+    void end(EventPool &p, cudaStream_t st, double f)
+    {
+        cudaEvent_t e = p.get();
+        cudaEventRecord(e, st);
+        spans.emplace_back(open, e); flops += f;
+    }
+    float collect()                      // the stream must have been synchronised
+    {
+        float tot = 0;
+        for (auto &s : spans) { float ms = 0; if (cudaEventElapsedTime(&ms, s.first, s.second) == cudaSuccess) tot += ms; }
+        return tot;
+    }
+};
+
 struct gs_handle {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t stream_hi = nullptr;   // second stream: the single-CTA SMO launch when a cluster launch runs beside it
+    cudaStream_t stream_lo = nullptr;   // third stream: the shared-SM launch when cluster and exclusive-SM launches run beside it
     std::string err;
     // dataset (rows stored in INTERNAL order: sorted by class, then by original index)
     int64_t n = 0, d = 0;
@@ -53,8 +89,11 @@ struct gs_handle {
     DevBuf dS, dXsq;                  // float64 Gram [n][n], squared norms [n]
     DevBuf dK;                        // float32 kernel matrices (batch)
     DevBuf dWork[9];                  // per-search scratch
+    DevBuf dScore;                    // class counts / AUC pair counts of the non-default scorers
+    int score_kind = 0, score_pos = 1;   // gs_set_scoring
     gs_profile prof;
-    cudaEvent_t ev[8];
+    EventPool evp;                    // timing events of the current call
+    TensorTimer tt;
 };
 
 void gs_set_error(gs_handle *h, const std::string &msg);
@@ -96,7 +135,8 @@ int smo_max_rows();   // largest sub-problem the resident-state kernel supports
 // smo_lean.cu: the throughput instance (static slots = the problem's column runs, two or more sub-problems per SM).  Every
 // problem of the launch needs a slot layout: nseg > 0, nslots <= smo_lean_max_slots(), l < 16383; alpha and Gbar hold nslots doubles.
 int smo_lean_max_slots();
-cudaError_t launch_smo_lean(const SmoProblem *d_probs, const int *d_order, int n_prob, int max_slots, bool fast, cudaStream_t st);
+// exclusive: one sub-problem per SM (the launch asks for more than half of an SM's shared memory)
+cudaError_t launch_smo_lean(const SmoProblem *d_probs, const int *d_order, int n_prob, int max_slots, bool fast, bool exclusive, cudaStream_t st);
 // smo_colown.cu: the same solver with one sub-problem spread over a thread-block cluster of cl CTAs (DSMEM exchange)
 int smo_colown_max_rows(int cl);
 void launch_delay(unsigned ns, cudaStream_t st);      // one thread sleeping ns nanoseconds (stream-ordering aid)
@@ -116,6 +156,18 @@ struct VoteTask {          // one (candidate, fold) task
 cudaError_t launch_vote(const double *dec, const double *rho, int n, int n_classes, const int *y,
                         const signed char *fold, const VoteTask *tasks, int n_tasks, int *counts,
                         cudaStream_t st);
+
+// per-class counts for the count-based scorers: counts[task][split (0 test, 1 train)][class][3 = support, tp, predicted]
+cudaError_t launch_vote_classes(const double *dec, const double *rho, int n, int n_classes, const int *y,
+                                const signed char *fold, const VoteTask *tasks, int n_tasks, int *counts, cudaStream_t st);
+// ROC-AUC pair counts of binary tasks: out[task][4] = {test wins, test ties, train wins, train ties}; rows are class-sorted
+// (negative class = rows [0, n_a)); score row of task t = score + col_of_task[t] * ld; sign -1 for libsvm decision values
+cudaError_t launch_auc_pairs_f64(const double *score, int64_t ld, int n, int n_a, const signed char *fold, const int *col_of_task,
+                                 const int *fold_of_task, int n_tasks, int sign, unsigned long long *out, cudaStream_t st);
+cudaError_t launch_auc_pairs_f32(const float *score, int64_t ld, int n, int n_a, const signed char *fold, const int *col_of_task,
+                                 const int *fold_of_task, int n_tasks, int sign, unsigned long long *out, cudaStream_t st);
+// score of one (task, split) from the class counts cnt[class][3] (float64, scikit-learn's formulas); NaN when undefined
+double gs_score_from_counts(int kind, int pos_class, int n_classes, const int *cnt);
 
 // ---- gemm_tc.cu: tcgen05 + TMA contraction  C[M][N] = sum_k A[M][k] B[N][k]  (3xTF32 split, fp32 accumulate) ----
 struct alignas(64) TcMap { unsigned char bytes[128]; };            // CUtensorMap

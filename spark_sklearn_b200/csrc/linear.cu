@@ -223,7 +223,7 @@ __global__ void cg_step_kernel(const float *__restrict__ Q, const double *__rest
 // R^2 of system s on its test block and on its training rows, from Gram statistics (float64 quadratic forms)
 __global__ void ridge_r2_kernel(const float *__restrict__ Xs, const double *__restrict__ T, const float *__restrict__ G,
                                 const int *__restrict__ test_block, const double *__restrict__ means, int n_cand, int d, int Dp,
-                                int dp, int fit_intercept, double *__restrict__ out /* [systems][2] */)
+                                int dp, int fit_intercept, int kind, double *__restrict__ out /* [systems][2] */)
 {
     __shared__ double sh[32];
     extern __shared__ double wsh[];                               // w in float64
@@ -260,6 +260,8 @@ __global__ void ridge_r2_kernel(const float *__restrict__ Xs, const double *__re
         auto r2 = [&](double yy, double ys, double nn, double q, double wxy, double ws) {
             const double res = yy - 2 * wxy - 2 * b0 * ys + q + 2 * b0 * ws + nn * b0 * b0;
             const double tot = yy - ys * ys / nn;
+            if (kind == GS_SCORE_NEG_MSE) return -res / nn;              // sklearn.metrics.mean_squared_error, negated by the scorer
+            if (kind == GS_SCORE_NEG_RMSE) return -sqrt(fmax(res, 0.0) / nn);
             return 1.0 - res / tot;
         };
         const double yy_k = Gk[(size_t)d * Dp + d], ys_k = Gk[(size_t)d * Dp + d + 1], n_k = Gk[(size_t)(d + 1) * Dp + d + 1];
@@ -281,6 +283,9 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     if (n_cand <= 0 || !alpha) { gs_set_error(h, "gs_ridge: bad arguments"); return GS_ERR_ARG; }
     for (int c = 0; c < n_cand; c++)
         if (!(alpha[c] >= 0)) { gs_set_error(h, "gs_ridge: alpha must be >= 0"); return GS_ERR_ARG; }
+    if (h->score_kind != GS_SCORE_DEFAULT && h->score_kind != GS_SCORE_NEG_MSE && h->score_kind != GS_SCORE_NEG_RMSE) {
+        gs_set_error(h, "gs_ridge: classification scorer on a regressor"); return GS_ERR_ARG;
+    }
     GS_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     const int n = (int)h->n, d = (int)h->d, ns = h->n_splits;
@@ -312,8 +317,9 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     const int groups = refit ? 1 : ns;
     const int nsys = groups * n_cand;
 
+    h->evp.reset(); h->tt.reset();
     cudaEvent_t ev[5];
-    for (auto &e : ev) cudaEventCreate(&e);
+    for (auto &e : ev) e = h->evp.get();
     cudaEventRecord(ev[0], st);
 
     // ---- buffers ----
@@ -374,7 +380,9 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     TcMap mzh, mzl;
     GS_CUDA(tc_make_map(&mzh, bZh.as<float>(), Dp, ldz, ldz));
     GS_CUDA(tc_make_map(&mzl, bZl.as<float>(), Dp, ldz, ldz));
+    h->tt.begin(h->evp, st);
     GS_CUDA(launch_gemm_nt_tf32x3(mzh, mzl, mzh, mzl, dBatchG, nq, D, D, 1.0f, false, st));
+    h->tt.end(h->evp, st, 3.0 * 2.0 * (double)D * D * (double)ldz);
     sum_grams_kernel<<<592, 256, 0, st>>>(dGq, dQs, nb, (int64_t)Dp * Dp, bG.as<float>(), dT);
     GS_CUDA(cudaGetLastError());
     launches += 5;
@@ -401,7 +409,9 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     int open = 1, it = 0;
     while (open > 0 && it < CG_MAX_ITER) {
         for (int rep = 0; rep < 4; rep++, it++) {
+            h->tt.begin(h->evp, st);
             GS_CUDA(launch_gemm_nt_tf32x3(mph, mpl, mah, mal, dBatchCG, groups * nkc, n_cand, dp, 1.0f, false, st));
+            h->tt.end(h->evp, st, 3.0 * 2.0 * (double)groups * n_cand * (double)dp * dp);
             if (nkc > 1) GS_CUDA(launch_sum_partials(dQp, nkc, (int64_t)nsys * dp, dQ, st));
             GS_CUDA(cudaMemsetAsync(dOpen, 0, 4, st));
             cg_step_kernel<<<nsys, 256, 0, st>>>(nkc > 1 ? dQ : dQp, dAlpha, n_cand, dp, dX, dR, dP, dPh, dPl, dRR, dBB, dDone, dOpen, CG_TOL * CG_TOL);
@@ -420,7 +430,7 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
 
     // ---- 4. scores / coefficients ----
     if (!refit) {
-        ridge_r2_kernel<<<nsys, 256, (size_t)d * 8, st>>>(dX, dT, bG.as<float>(), dTestBlock, dMeans, n_cand, d, Dp, dp, fit_intercept, dOut);
+        ridge_r2_kernel<<<nsys, 256, (size_t)d * 8, st>>>(dX, dT, bG.as<float>(), dTestBlock, dMeans, n_cand, d, Dp, dp, fit_intercept, h->score_kind, dOut);
         GS_CUDA(cudaGetLastError());
         launches++;
         std::vector<double> out((size_t)nsys * 2);
@@ -456,7 +466,6 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     cudaEventElapsedTime(&tmr->solve, ev[1], ev[2]);
     cudaEventElapsedTime(&tmr->score, ev[2], ev[3]);
     cudaEventElapsedTime(&tmr->total, ev[0], ev[4]);
-    for (auto &e : ev) cudaEventDestroy(e);
     gs_profile &pf = h->prof;
     const float keep_h2d = pf.ms_h2d; const int64_t keep_b = pf.h2d_bytes, keep_d2h = pf.d2h_bytes;
     memset(&pf, 0, sizeof pf);
@@ -467,6 +476,7 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     pf.gram_flops = 2.0 * (double)n * D * D;
     pf.gram_bytes = (double)n * D * 4 + (double)nq * D * D * 4;
     pf.solve_bytes = 0;
+    pf.ms_tensor = h->tt.collect(); pf.tensor_flops = h->tt.flops;
     return GS_OK;
 }
 

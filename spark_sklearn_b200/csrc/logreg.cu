@@ -385,6 +385,35 @@ __global__ void logistic_count_kernel(const float *__restrict__ Zt, int64_t ldz,
     }
 }
 
+// per-class counts for the count-based scorers: counts[col][split (0 test, 1 train)][class (0, 1)][3 = support, tp, predicted]
+__global__ void logistic_classes_kernel(const float *__restrict__ Zt, int64_t ldz, int n, const int *__restrict__ y,
+                                        const signed char *__restrict__ fold, const int *__restrict__ fold_of_col, int *__restrict__ counts)
+{
+    __shared__ int sh[12];
+    if (threadIdx.x < 12) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const int c = blockIdx.y, fc = fold_of_col[c];
+    int loc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int pred = Zt[(size_t)c * ldz + i] > 0.f ? 1 : 0, yc = y[i], sp = fold[i] == fc ? 0 : 1;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {                                   // (split, class) = q
+            const int qs = q >> 1, qc = q & 1;
+            loc[q * 3 + 0] += (sp == qs && yc == qc);
+            loc[q * 3 + 1] += (sp == qs && yc == qc && pred == qc);
+            loc[q * 3 + 2] += (sp == qs && pred == qc);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 12; e++) {
+#pragma unroll
+        for (int m = 16; m; m >>= 1) loc[e] += __shfl_xor_sync(0xffffffffu, loc[e], m);
+        if ((threadIdx.x & 31) == 0 && loc[e]) atomicAdd(&sh[e], loc[e]);
+    }
+    __syncthreads();
+    if (threadIdx.x < 12 && sh[threadIdx.x]) atomicAdd(&counts[(size_t)c * 12 + threadIdx.x], sh[threadIdx.x]);
+}
+
 // Xa = [X | 1] padded to [n][nvp] and its transpose [nvp][npad]
 __global__ void build_xa_kernel(const float *__restrict__ X, int n, int d, int fit_intercept, int nvp, int64_t npad,
                                 float *__restrict__ Xa, float *__restrict__ Xat)
@@ -420,8 +449,9 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
     const int64_t npad = ((int64_t)n + 31) & ~31LL;
     const int ncol = n_cand * ns;
 
+    h->evp.reset(); h->tt.reset();
     cudaEvent_t ev[3];
-    for (auto &e : ev) cudaEventCreate(&e);
+    for (auto &e : ev) e = h->evp.get();
     cudaEventRecord(ev[0], st);
 
     // ---- buffers ----
@@ -499,11 +529,15 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
     const int warps_per_block = 4;
     while (open > 0 && rounds < 4000) {
         // f, g at every open column's trial point: Z^T = W Xa^T ; R = residual(Z) ; G = R Xa
+        h->tt.begin(h->evp, st);
         GS_CUDA(launch_gemm_nt_tf32x3(mWh, mWl, mXh, mXl, dBatch, 1, ncol, n, 1.0f, false, st));
+        h->tt.end(h->evp, st, 3.0 * 2.0 * (double)ncol * n * nvp);
         dim3 grid(64, ncol);
         logistic_residual_kernel<<<grid, 256, 0, st>>>(dZ, npad, n, h->dY.as<int>(), h->dFold.as<signed char>(), dFoldOf, dInv, dS, dRh, dRl);
         GS_CUDA(cudaGetLastError());
+        h->tt.begin(h->evp, st);
         GS_CUDA(launch_gemm_nt_tf32x3(mRh, mRl, mXth, mXtl, dBatch + 1, nchunk, ncol, nv, 1.0f, false, st));
+        h->tt.end(h->evp, st, 3.0 * 2.0 * (double)ncol * nv * (double)npad);
         GS_CUDA(launch_sum_partials(dGp, nchunk, (int64_t)ncol * nvp, dG, st));
         GS_CUDA(cudaMemsetAsync(dOpen, 0, 4, st));
         lbfgs_advance_kernel<<<(ncol + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
@@ -522,7 +556,9 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
         // ---- scoring: z at the final iterate for every row, accuracy split by fold ----
         lbfgs_export_kernel<<<ncol, 128, 0, st>>>(dV, ncol, nv, nvp, dWh, dWl, nvp);
         GS_CUDA(cudaGetLastError());
+        h->tt.begin(h->evp, st);
         GS_CUDA(launch_gemm_nt_tf32x3(mWh, mWl, mXh, mXl, dBatch, 1, ncol, n, 1.0f, false, st));
+        h->tt.end(h->evp, st, 3.0 * 2.0 * (double)ncol * n * nvp);
         GS_CUDA(cudaMemsetAsync(dCounts, 0, (size_t)ncol * 16, st));
         dim3 grid(64, ncol);
         logistic_count_kernel<<<grid, 256, 0, st>>>(dZ, npad, n, h->dY.as<int>(), h->dFold.as<signed char>(), dFoldOf, dCounts);
@@ -530,12 +566,52 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
         launches += 3;
         std::vector<int> counts((size_t)ncol * 4);
         GS_CUDA(cudaMemcpyAsync(counts.data(), dCounts, counts.size() * 4, cudaMemcpyDeviceToHost, st));
+        // non-default scorers (gs_set_scoring): class counts or ROC-AUC pair counts from the z values already in HBM
+        const int kind = h->score_kind;
+        std::vector<int> ccounts;
+        std::vector<unsigned long long> araw;
+        if (kind == GS_SCORE_ROC_AUC) {
+            std::vector<int> meta((size_t)ncol * 2);
+            for (int col = 0; col < ncol; col++) { meta[col] = col; meta[ncol + col] = refit ? -100 : col % ns; }
+            GS_CUDA(h->dScore.reserve((size_t)ncol * 40));
+            unsigned long long *d_auc = h->dScore.as<unsigned long long>();
+            int *d_meta = (int *)(d_auc + (size_t)ncol * 4);
+            GS_CUDA(cudaMemcpyAsync(d_meta, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice, st));
+            GS_CUDA(cudaMemsetAsync(d_auc, 0, (size_t)ncol * 32, st));
+            GS_CUDA(launch_auc_pairs_f32(dZ, npad, n, h->class_start[1], h->dFold.as<signed char>(), d_meta, d_meta + ncol, ncol, +1, d_auc, st));
+            araw.resize((size_t)ncol * 4);
+            GS_CUDA(cudaMemcpyAsync(araw.data(), d_auc, (size_t)ncol * 32, cudaMemcpyDeviceToHost, st));
+            launches++;
+        } else if (kind != GS_SCORE_DEFAULT) {
+            GS_CUDA(h->dScore.reserve((size_t)ncol * 48));
+            GS_CUDA(cudaMemsetAsync(h->dScore.p, 0, (size_t)ncol * 48, st));
+            logistic_classes_kernel<<<grid, 256, 0, st>>>(dZ, npad, n, h->dY.as<int>(), h->dFold.as<signed char>(), dFoldOf, h->dScore.as<int>());
+            GS_CUDA(cudaGetLastError());
+            ccounts.resize((size_t)ncol * 12);
+            GS_CUDA(cudaMemcpyAsync(ccounts.data(), h->dScore.p, ccounts.size() * 4, cudaMemcpyDeviceToHost, st));
+            launches++;
+        }
         cudaEventRecord(ev[2], st);
         GS_CUDA(cudaStreamSynchronize(st));
         for (int col = 0; col < ncol; col++) {
             const int *cn = &counts[(size_t)col * 4];
-            test_scores[col] = cn[1] > 0 ? (double)cn[0] / cn[1] : NAN;
-            if (train_scores) train_scores[col] = cn[3] > 0 ? (double)cn[2] / cn[3] : NAN;
+            if (kind == GS_SCORE_DEFAULT) {
+                test_scores[col] = cn[1] > 0 ? (double)cn[0] / cn[1] : NAN;
+                if (train_scores) train_scores[col] = cn[3] > 0 ? (double)cn[2] / cn[3] : NAN;
+            } else if (kind == GS_SCORE_ROC_AUC) {
+                const int k = col % ns;
+                double na_te = 0, nb_te = 0, na_tr = 0, nb_tr = 0;
+                for (int r = 0; r < n; r++) {
+                    const bool b = r >= h->class_start[1], te = h->fold[r] == k;
+                    (te ? (b ? nb_te : na_te) : (b ? nb_tr : na_tr)) += 1;
+                }
+                const unsigned long long *a = &araw[(size_t)col * 4];
+                test_scores[col] = na_te * nb_te > 0 ? ((double)a[0] + 0.5 * (double)a[1]) / (na_te * nb_te) : NAN;
+                if (train_scores) train_scores[col] = na_tr * nb_tr > 0 ? ((double)a[2] + 0.5 * (double)a[3]) / (na_tr * nb_tr) : NAN;
+            } else {
+                test_scores[col] = gs_score_from_counts(kind, h->score_pos, 2, &ccounts[(size_t)col * 12]);
+                if (train_scores) train_scores[col] = gs_score_from_counts(kind, h->score_pos, 2, &ccounts[(size_t)col * 12 + 6]);
+            }
             if (n_iter) n_iter[col] = fin[col].iter;
         }
     } else {
@@ -551,7 +627,6 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
         if (fin[col].task != T_DONE) { gs_set_error(h, "gs_logreg: optimiser did not terminate"); return GS_ERR_NUMERIC; }
     cudaEventElapsedTime(ms_solve, ev[0], ev[1]);
     cudaEventElapsedTime(ms_score, ev[1], ev[2]);
-    for (auto &e : ev) cudaEventDestroy(e);
     gs_profile &pf = h->prof;
     const float keep_h2d = pf.ms_h2d; const int64_t keep_b = pf.h2d_bytes;
     memset(&pf, 0, sizeof pf);
@@ -561,6 +636,7 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
     pf.smo_iterations = rounds;                                 // function-evaluation rounds
     pf.gram_flops = (double)rounds * 2.0 * 2.0 * (double)n * nv * ncol;
     pf.d2h_bytes = (int64_t)ncol * (16 + sizeof(LbScalars));
+    pf.ms_tensor = h->tt.collect(); pf.tensor_flops = h->tt.flops;
     return GS_OK;
 }
 

@@ -8,6 +8,7 @@
 // and for all sub-models c that share one (kernel, gamma): one pass over the float64 Gram per gamma,
 // with the exp fused into the operand load.  coef is zero outside a sub-model's training rows.
 #include "common.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -144,7 +145,136 @@ vote_kernel(const double *__restrict__ dec, const double *__restrict__ rho, int 
     }
 }
 
+// Per-class counts for the count-based scorers (sklearn.metrics accuracy / balanced_accuracy / precision / recall / f1,
+// metrics/_classification.py: everything they need is the multilabel confusion diagonal): for every task, split
+// (0 test, 1 train) and class c:  support (y == c), tp (y == c and predicted c), predicted (predicted c).
+// counts[task][split][class][3]; block-level shared-memory accumulation, one global atomic per non-zero cell.
+__global__ void __launch_bounds__(256)
+vote_classes_kernel(const double *__restrict__ dec, const double *__restrict__ rho, int n, int n_classes,
+                    const int *__restrict__ y, const signed char *__restrict__ fold,
+                    const VoteTask *__restrict__ tasks, int *__restrict__ counts)
+{
+    __shared__ int sh[2 * 32 * 3];
+    for (int i = threadIdx.x; i < 2 * n_classes * 3; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const VoteTask T = tasks[blockIdx.y];
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) {
+        int pred;
+        if (n_classes == 2) {
+            const double dv = dec[(size_t)T.first_col * n + r] - rho[T.first_col];
+            pred = dv > 0 ? 0 : 1;
+        } else {
+            int votes[32];
+            for (int c = 0; c < n_classes; c++) votes[c] = 0;
+            int p = T.first_col;
+            for (int a = 0; a < n_classes; a++)
+                for (int b = a + 1; b < n_classes; b++, p++) {
+                    const double dv = dec[(size_t)p * n + r] - rho[p];
+                    if (dv > 0) ++votes[a]; else ++votes[b];
+                }
+            pred = 0;
+            for (int c = 1; c < n_classes; c++) if (votes[c] > votes[pred]) pred = c;
+        }
+        const int sp = fold[r] == T.fold ? 0 : 1, yc = y[r];
+        atomicAdd(&sh[(sp * n_classes + yc) * 3 + 0], 1);
+        if (pred == yc) atomicAdd(&sh[(sp * n_classes + yc) * 3 + 1], 1);
+        atomicAdd(&sh[(sp * n_classes + pred) * 3 + 2], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * n_classes * 3; i += blockDim.x)
+        if (sh[i]) atomicAdd(&counts[(size_t)blockIdx.y * 2 * n_classes * 3 + i], sh[i]);
+}
+
+// Area under the ROC curve of a binary task (sklearn.metrics.roc_auc_score == the Mann-Whitney statistic with ties counted
+// one half): pairs (p, q) of a row p of the positive class (ids >= n_a in the class-sorted order) and a row q of the
+// negative class whose scores satisfy s_p > s_q (wins) or s_p == s_q (ties), separately for the test rows of the task's
+// fold and for its training rows.  out[task][4] = {test wins, test ties, train wins, train ties} (64-bit).
+// SIGN: +1 when larger values mean the positive class (LogisticRegression z), -1 for libsvm's dec - rho (positive means
+// the FIRST class, svm.cpp:2862; scikit-learn negates it for its binary decision_function).
+template <typename T>
+__global__ void __launch_bounds__(256)
+auc_pairs_kernel(const T *__restrict__ score, int64_t ld, int n, int n_a, const signed char *__restrict__ fold,
+                 const int *__restrict__ col_of_task, const int *__restrict__ fold_of_task, int sign,
+                 unsigned long long *__restrict__ out)
+{
+    __shared__ T s_a[256];
+    __shared__ signed char f_a[256];
+    __shared__ unsigned long long red[4];
+    const int task = blockIdx.y, k = fold_of_task[task];
+    const T *__restrict__ sc = score + (size_t)col_of_task[task] * ld;
+    const int p = n_a + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool has = p < n;
+    const T sp = has ? (sign > 0 ? sc[p] : -sc[p]) : T(0);
+    const bool p_test = has && fold[p] == k;
+    unsigned w_te = 0, t_te = 0, w_tr = 0, t_tr = 0;
+    if (threadIdx.x < 4) red[threadIdx.x] = 0ull;
+    for (int q0 = 0; q0 < n_a; q0 += 256) {
+        __syncthreads();
+        const int q = q0 + threadIdx.x;
+        s_a[threadIdx.x] = q < n_a ? (sign > 0 ? sc[q] : -sc[q]) : T(0);
+        f_a[threadIdx.x] = q < n_a ? (fold[q] == k ? 1 : 0) : (signed char)2;          // 2: no row
+        __syncthreads();
+        if (has) {
+            const int lim = min(256, n_a - q0);
+            for (int j = 0; j < lim; j++) {
+                const bool q_test = f_a[j] == 1;
+                if (q_test == p_test) {                                                  // both test rows or both training rows
+                    const unsigned win = sp > s_a[j], tie = sp == s_a[j];
+                    if (p_test) { w_te += win; t_te += tie; } else { w_tr += win; t_tr += tie; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    unsigned v[4] = {w_te, t_te, w_tr, t_tr};
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+#pragma unroll
+        for (int m = 16; m; m >>= 1) v[e] += __shfl_xor_sync(0xffffffffu, v[e], m);
+        if ((threadIdx.x & 31) == 0 && v[e]) atomicAdd(&red[e], (unsigned long long)v[e]);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 && red[threadIdx.x]) atomicAdd(&out[(size_t)task * 4 + threadIdx.x], red[threadIdx.x]);
+}
+
 }  // namespace
+
+cudaError_t launch_vote_classes(const double *dec, const double *rho, int n, int n_classes, const int *y,
+                                const signed char *fold, const VoteTask *tasks, int n_tasks, int *counts, cudaStream_t st)
+{
+    if (n_tasks <= 0) return cudaSuccess;
+    for (int t0 = 0; t0 < n_tasks; t0 += 32768) {                     // gridDim.y <= 65535
+        const int nt = std::min(32768, n_tasks - t0);
+        dim3 grid((n + 255) / 256, nt);
+        vote_classes_kernel<<<grid, 256, 0, st>>>(dec, rho, n, n_classes, y, fold, tasks + t0, counts + (size_t)t0 * 2 * n_classes * 3);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_auc_pairs_f64(const double *score, int64_t ld, int n, int n_a, const signed char *fold, const int *col_of_task,
+                                 const int *fold_of_task, int n_tasks, int sign, unsigned long long *out, cudaStream_t st)
+{
+    if (n_tasks <= 0 || n - n_a <= 0) return cudaSuccess;
+    for (int t0 = 0; t0 < n_tasks; t0 += 32768) {
+        const int nt = std::min(32768, n_tasks - t0);
+        dim3 grid((n - n_a + 255) / 256, nt);
+        auc_pairs_kernel<double><<<grid, 256, 0, st>>>(score, ld, n, n_a, fold, col_of_task + t0, fold_of_task + t0, sign, out + (size_t)t0 * 4);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_auc_pairs_f32(const float *score, int64_t ld, int n, int n_a, const signed char *fold, const int *col_of_task,
+                                 const int *fold_of_task, int n_tasks, int sign, unsigned long long *out, cudaStream_t st)
+{
+    if (n_tasks <= 0 || n - n_a <= 0) return cudaSuccess;
+    for (int t0 = 0; t0 < n_tasks; t0 += 32768) {
+        const int nt = std::min(32768, n_tasks - t0);
+        dim3 grid((n - n_a + 255) / 256, nt);
+        auc_pairs_kernel<float><<<grid, 256, 0, st>>>(score, ld, n, n_a, fold, col_of_task + t0, fold_of_task + t0, sign, out + (size_t)t0 * 4);
+    }
+    return cudaGetLastError();
+}
 
 // part: workspace of at least jchunks * ncols * n doubles when jchunks > 1 (see decision_chunks)
 int decision_chunks(int n) { return n >= 4096 ? 4 : 1; }
@@ -176,7 +306,10 @@ cudaError_t launch_vote(const double *dec, const double *rho, int n, int n_class
                         cudaStream_t st)
 {
     if (n_tasks <= 0) return cudaSuccess;
-    dim3 grid((n + 255) / 256, n_tasks);
-    vote_kernel<<<grid, 256, 0, st>>>(dec, rho, n, n_classes, y, fold, tasks, counts);
+    for (int t0 = 0; t0 < n_tasks; t0 += 32768) {                     // gridDim.y <= 65535
+        const int nt = std::min(32768, n_tasks - t0);
+        dim3 grid((n + 255) / 256, nt);
+        vote_kernel<<<grid, 256, 0, st>>>(dec, rho, n, n_classes, y, fold, tasks + t0, counts + (size_t)t0 * 4);
+    }
     return cudaGetLastError();
 }

@@ -16,10 +16,15 @@
 //     compare (value, word); the winner's word carries its slot.  Elements outside the active set have I_up/I_low
 //     cleared, so the hot loops need no active-set test; their m is updated along with the rest and overwritten by
 //     reconstruct_gradient exactly as libsvm overwrites G (svm.cpp:633-636).
-//   * Resident state per sub-problem: m (8 B) and the word (4 B) per slot in shared memory = 96 KB for 8192 slots, read
-//     and written with 16-byte accesses; alpha and G_bar (touched by two elements per iteration / on status flips) in
-//     global memory.  512 threads x 64 registers: two sub-problems per SM, so one's row latency and barriers overlap the
-//     other's arithmetic.
+//   * Resident state per sub-problem: m (8 B) and the word (4 B) per slot in shared memory = 96 KB for 8192 slots; alpha
+//     and G_bar (touched by two elements per iteration / on status flips) in global memory.  512 threads x 64 registers:
+//     two sub-problems per SM, so one's row latency and barriers overlap the other's arithmetic.
+//     m is stored in two planes (elements 0-1 and 2-3 of every group) so that a warp's 16-byte accesses are consecutive:
+//     no bank conflicts (a plain [slot] array of doubles makes every LDS.128 / STS.128 a 2-way conflict, measured as the
+//     limiter of both element loops).  The I_up / I_low bits of a thread's own slots are mirrored in ONE register
+//     (2 bits per slot); the hot loops read no slot words -- only the winner's word is fetched after the loop.
+//   * alpha_j and Q_ij travel with the warp records: each warp's phase-B winner lane loads its alpha before the barrier
+//     (the latency hides in the barrier skew), so the two-variable update waits for no memory.
 //   * The stopping test Gmax + Gmax2 < eps (svm.cpp:1040) is evaluated as "no I_low element has fl(Gmax - m_t) >= eps"
 //     (rounding is monotone, so this is the same predicate) inside the j-selection loop and reduced by the barrier itself
 //     (__syncthreads_or): the update loop carries one running arg-max instead of an arg-max and a min.
@@ -29,7 +34,9 @@
 //     full (value, position) order.  After the first iteration exact ties in m do not occur in practice.
 //   * float32 -> float64 widening of a positive normal K entry is ONE integer multiply-add (u * 2^29 + 0x38 << 56).
 #include "smo_common.cuh"
+#include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 namespace {
 
@@ -47,6 +54,13 @@ __device__ __forceinline__ unsigned lean_flags(bool ypos, int st)
     return (unsigned)st | (up ? LF_UP : 0u) | (low ? LF_LOW : 0u);
 }
 
+// compile-time unrolled loop: f(std::integral_constant<int, 0>) ... f(std::integral_constant<int, N - 1>)
+template <int N, int I = 0, class F>
+__device__ __forceinline__ void lean_loop(F &&f)
+{
+    if constexpr (I < N) { f(std::integral_constant<int, I>{}); lean_loop<N, I + 1>(f); }
+}
+
 struct UArg { unsigned hi, lo, idx; };
 // warp arg-max over (64-bit key, word): largest key, ties -> largest word; word 0 = none.  3 REDUX.
 __device__ __forceinline__ UArg warp_argmax_u(unsigned hi, unsigned lo, unsigned idx)
@@ -58,11 +72,79 @@ __device__ __forceinline__ UArg warp_argmax_u(unsigned hi, unsigned lo, unsigned
     return r;
 }
 
+// ---- per-slot bodies of the two hot loops, FAST instance (rbf, positive normal K), as straight PTX: the compiler's own
+//      lowering of the same C++ kept the predicates in general registers and spilled (measured 20 instructions per slot and
+//      loop); this is 17 and 13.  Rounding: every f64 operation carries .rn, which also forbids contraction.
+// phase B: gd = Gmax - m; candidate iff I_low bit set and gd > 0; key = bits(fl32(gd)^2 * rcp(max(fl32(2 - 2K), 1e-12)))
+template <int K>
+__device__ __forceinline__ void lean_phase_b_slot(double gmax, double m, unsigned fm, float kv, unsigned &b1k, unsigned &b2k,
+                                                  int &k1, float &kq1, float &gmxf)
+{
+    asm volatile("{\n\t"
+                 ".reg .pred pc, pg;\n\t"
+                 ".reg .f64 gd;\n\t"
+                 ".reg .f32 gdf, qf, g2, r, ap;\n\t"
+                 ".reg .b32 key, t;\n\t"
+                 "sub.rn.f64 gd, %5, %6;\n\t"
+                 "and.b32 t, %7, %8;\n\t"
+                 "setp.ne.u32 pc, t, 0;\n\t"
+                 "setp.gt.and.f64 pc, gd, 0d0000000000000000, pc;\n\t"
+                 "cvt.rn.f32.f64 gdf, gd;\n\t"
+                 "selp.f32 gdf, gdf, 0f00000000, pc;\n\t"
+                 "max.f32 %4, %4, gdf;\n\t"
+                 "fma.rn.f32 qf, %9, 0fC0000000, 0f40000000;\n\t"
+                 "max.f32 qf, qf, 0f2B8CBCCC;\n\t"
+                 "mul.rn.f32 g2, gdf, gdf;\n\t"
+                 "rcp.approx.ftz.f32 r, qf;\n\t"
+                 "mul.rn.f32 ap, g2, r;\n\t"
+                 "mov.b32 key, ap;\n\t"
+                 "setp.gt.u32 pg, key, %0;\n\t"
+                 "min.u32 t, %0, key;\n\t"
+                 "max.u32 %1, %1, t;\n\t"
+                 "max.u32 %0, %0, key;\n\t"
+                 "selp.b32 %2, %10, %2, pg;\n\t"
+                 "selp.f32 %3, %9, %3, pg;\n\t"
+                 "}"
+                 : "+r"(b1k), "+r"(b2k), "+r"(k1), "+f"(kq1), "+f"(gmxf)
+                 : "d"(gmax), "d"(m), "r"(fm), "n"(2u << (2 * K)), "f"(kv), "n"(K));
+}
+// update: m += fl(fl(K_i a) + fl(K_j b)); running arg-max over I_up with a strict compare, equal values raise `tie`
+template <int K>
+__device__ __forceinline__ void lean_update_slot(double &m, float kvi, float kvj, double a, double b, unsigned fm, double &la,
+                                                 int &la_k, unsigned &tie)
+{
+    asm volatile("{\n\t"
+                 ".reg .pred pu, pb, pe;\n\t"
+                 ".reg .b64 wi, wj;\n\t"
+                 ".reg .f64 fi, fj;\n\t"
+                 ".reg .b32 t;\n\t"
+                 "mad.wide.u32 wi, %4, 0x20000000, 0x3800000000000000;\n\t"
+                 "mad.wide.u32 wj, %5, 0x20000000, 0x3800000000000000;\n\t"
+                 "mov.b64 fi, wi;\n\t"
+                 "mov.b64 fj, wj;\n\t"
+                 "mul.rn.f64 fi, fi, %6;\n\t"
+                 "mul.rn.f64 fj, fj, %7;\n\t"
+                 "add.rn.f64 fi, fi, fj;\n\t"
+                 "add.rn.f64 %0, %0, fi;\n\t"
+                 "and.b32 t, %8, %9;\n\t"
+                 "setp.ne.u32 pu, t, 0;\n\t"
+                 "setp.gt.and.f64 pb, %0, %1, pu;\n\t"
+                 "setp.eq.and.f64 pe, %0, %1, pu;\n\t"
+                 "selp.f64 %1, %0, %1, pb;\n\t"
+                 "selp.b32 %2, %10, %2, pb;\n\t"
+                 "selp.b32 %3, 1, %3, pe;\n\t"
+                 "}"
+                 : "+d"(m), "+d"(la), "+r"(la_k), "+r"(tie)
+                 : "r"(__float_as_uint(kvi)), "r"(__float_as_uint(kvj)), "d"(a), "d"(b), "r"(fm), "n"(1u << (2 * K)), "n"(K));
+}
+
 struct LeanRed {                                      // static shared scratch; NW <= 32 warps
     unsigned a_hi[32], a_lo[32], a_pf[32];            // phase A warp records (arg-max m over I_up)
     unsigned b_k1[32], b_pf[32], b_k2[32], b_fl[32];  // phase B warp records (approximate arg-max, stop-test bits)
+    float b_kq[32]; double b_al[32], b_mg[32];        // ... the warp winner's K_i value, alpha and m
+    double al_i;                                      // alpha_i (published by warp 0 before barrier 2)
     unsigned x_hi[32], x_lo[32], x_pf[32];            // exact tie-break records (rare path)
-    double bc_d[2]; int bc_i[2];                      // scalars broadcast by warp 0
+    float x_kq[32]; double x_al[32], x_mg[32];
     double dm[32], dm2[32]; int cnt[32];              // cold-path reductions
     int seg_slot[5], seg_col[4];                      // slot -> column map
     int ysplit;                                       // first slot of the -1 class
@@ -120,6 +202,21 @@ smo_lean_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ or
         gcol[g] = s4 < nslots ? slot_col(s4) : 0;                            // groups past the last slot read column 0 (valid memory)
     }
 
+    // m of slot s lives at plane (s & 2), group s >> 2, element s & 1: a thread's group is two 16-byte pieces LCAP/2 doubles apart
+    auto m_at = [&](int slot) -> double & { return mG[((slot >> 1) & 1) * (LCAP / 2) + (slot >> 2) * 2 + (slot & 1)]; };
+    auto load_m4 = [&](int s4, double (&mv)[4]) {
+        const double2 a = *reinterpret_cast<const double2 *>(mG + (s4 >> 1)), b = *reinterpret_cast<const double2 *>(mG + LCAP / 2 + (s4 >> 1));
+        mv[0] = a.x; mv[1] = a.y; mv[2] = b.x; mv[3] = b.y;
+    };
+    auto store_m4 = [&](int s4, const double (&mv)[4]) {
+        *reinterpret_cast<double2 *>(mG + (s4 >> 1)) = make_double2(mv[0], mv[1]);
+        *reinterpret_cast<double2 *>(mG + LCAP / 2 + (s4 >> 1)) = make_double2(mv[2], mv[3]);
+    };
+    auto load_pf4 = [&](int s4, unsigned (&pv)[4]) {
+        const uint4 p = *reinterpret_cast<const uint4 *>(pfS + s4);
+        pv[0] = p.x; pv[1] = p.y; pv[2] = p.z; pv[3] = p.w;
+    };
+
     // ---- initial point: alpha = 0, G = p = -1  =>  m = y (svm.cpp:1611-1626, :716-736) ----
     {
         const int n_pos = Pp->n_pos;
@@ -145,7 +242,7 @@ smo_lean_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ or
                     alpha_g[s] = 0.0;
                     if (use_gbar) gbar_g[s] = 0.0;
                 }
-                mG[s] = mv; pfS[s] = w;
+                m_at(s) = mv; pfS[s] = w;
             }
         }
         if (ysp != 0x7fffffff) red.ysplit = ysp;                             // exactly one slot holds position n_pos
@@ -189,34 +286,21 @@ smo_lean_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ or
             kv[g * 4 + 0] = v.x; kv[g * 4 + 1] = v.y; kv[g * 4 + 2] = v.z; kv[g * 4 + 3] = v.w;
         }
     };
-    auto load_m4 = [&](int s4, double (&mv)[4]) {
-        const double2 a = *reinterpret_cast<const double2 *>(mG + s4), b = *reinterpret_cast<const double2 *>(mG + s4 + 2);
-        mv[0] = a.x; mv[1] = a.y; mv[2] = b.x; mv[3] = b.y;
-    };
-    auto load_pf4 = [&](int s4, unsigned (&pv)[4]) {
-        const uint4 p = *reinterpret_cast<const uint4 *>(pfS + s4);
-        pv[0] = p.x; pv[1] = p.y; pv[2] = p.z; pv[3] = p.w;
-    };
 
     // ---------------- local scan (normally fused into the update loop) ----------------
     // la / la_pf: arg-max of m over the owned I_up slots, ties -> larger position (libsvm's ascending ">=" scan)
     double la = -CUDART_INF;
     unsigned la_pf = 0u;
-    bool la_tie = false;
+    unsigned fm = 0u;                   // I_up (bit 2k) and I_low (bit 2k+1) of the owned slot k = g*4 + q
+    static_assert(G <= 4, "the flag mask holds 16 slots");
+    auto slot_of = [&](int k) -> int { return ((k >> 2) * NT + tid) * 4 + (k & 3); };
     auto scan_exact = [&](double mv, unsigned w) {
         const bool better = ((w & LF_UP) != 0u) & ((mv > la) | ((mv == la) & (w > la_pf)));
         la = better ? mv : la;
         la_pf = better ? w : la_pf;
     };
-    auto scan_fast = [&](double mv, unsigned w) {                            // strict compare; equal values raise the tie flag
-        const bool up = (w & LF_UP) != 0u;
-        const bool better = up & (mv > la);
-        la_tie = la_tie | (up & (mv == la));
-        la = better ? mv : la;
-        la_pf = better ? w : la_pf;
-    };
     auto local_scan = [&]() {
-        la = -CUDART_INF; la_pf = 0u; la_tie = false;
+        la = -CUDART_INF; la_pf = 0u;
 #pragma unroll
         for (int g = 0; g < G; g++) {
             const int s4 = (g * NT + tid) * 4;
@@ -229,6 +313,7 @@ smo_lean_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ or
     // I_up / I_low bits follow the active set: cleared for positions >= active, recomputed from status and label below it
     auto refresh_flags = [&]() {
         const unsigned act_lim = (unsigned)active << POS_SHIFT;
+        fm = 0u;
 #pragma unroll
         for (int g = 0; g < G; g++) {
             const int s4 = (g * NT + tid) * 4;
@@ -241,6 +326,7 @@ smo_lean_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ or
                     const unsigned base = w & ~(LF_UP | LF_LOW);
                     pv[q] = w < act_lim ? (base & ~3u) | lean_flags(s4 + q < ysplit, (int)(w & 3u)) : base;
                 }
+                fm |= ((pv[q] >> 2) & 3u) << (2 * (g * 4 + q));
             }
             *reinterpret_cast<uint4 *>(pfS + s4) = make_uint4(pv[0], pv[1], pv[2], pv[3]);
         }
@@ -303,7 +389,7 @@ smo_lean_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ or
             }
 #pragma unroll
             for (int q = 0; q < 4; q++)
-                if (in[q]) mG[s4 + q] = gacc[q];
+                if (in[q]) m_at(s4 + q) = gacc[q];
         }
         __syncthreads();
     };
@@ -311,7 +397,7 @@ smo_lean_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ or
     // ---------------- select_working_set (svm.cpp:946-1047) ----------------
     unsigned pi = 0u, pj = 0u;           // slot words of i and j
     int col_i = 0, col_j = 0;
-    double gmax = 0, mg_j = 0, k_ij = 0, alpha_i = 0, alpha_j = 0;      // alpha_*: valid in warp 0 only
+    double gmax = 0, mg_j = 0, k_ij = 0, alpha_i = 0, alpha_j = 0;
     float kvi[KPT];                      // K_i row at the owned slots (float32 as stored), alive until the update loop
     auto select = [&]() -> bool {
         // ---- phase A: i = argmax m_t over I_up (from the local scan) ----
@@ -331,7 +417,7 @@ smo_lean_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ or
         const int slot_i = (int)((pi >> SLOT_SHIFT) & SLOT_MASK);
         col_i = slot_col(slot_i);
         load_row(col_i, kvi);
-        if (warp == 0) alpha_i = __ldcg(alpha_g + slot_i);
+        if (tid == 0) red.al_i = __ldcg(alpha_g + slot_i);                         // read by every warp after barrier 2
         const double QDi = QDc(col_i);
         // ---- phase B: j = argmin -(gd^2)/quad over I_low with gd > 0 (svm.cpp:980-1037); error analysis of the approximate
         //      key and of BAND: smo.cu.  A slot that is no candidate gets gd := 0 and with it key 0 (FAST) / is masked.
@@ -352,32 +438,50 @@ smo_lean_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ or
                 return (unsigned)__double2hiint(ap);
             }
         };
-        unsigned b1k = 0u, b2k = 0u, idx1 = 0u;         // best / second-best key, the best candidate's word
+        unsigned b1k = 0u, b2k = 0u;                    // best / second-best key
+        int k1 = 0;                                     // the best candidate's local slot number ...
+        float kq1 = 0.f;                                // ... and its K_i value
         float gmxf = 0.f;                               // max over the candidates of fl32(Gmax - m_t)
+        double mvb[4];
+        if constexpr (FAST) {
+            lean_loop<G * 4>([&](auto kc) {
+                constexpr int k = decltype(kc)::value, g = k >> 2, q = k & 3;
+                if constexpr (q == 0) load_m4((g * NT + tid) * 4, mvb);
+                lean_phase_b_slot<k>(gmax, mvb[q], fm, kvi[k], b1k, b2k, k1, kq1, gmxf);
+            });
+        } else {
 #pragma unroll
-        for (int g = 0; g < G; g++) {
-            const int s4 = (g * NT + tid) * 4;
-            double mv[4]; unsigned pv[4];
-            load_m4(s4, mv); load_pf4(s4, pv);
+            for (int g = 0; g < G; g++) {
+                const int s4 = (g * NT + tid) * 4;
+                double mv[4];
+                load_m4(s4, mv);
 #pragma unroll
-            for (int q = 0; q < 4; q++) {                                    // branch-free: every slot evaluates a key
-                const double gd = __dsub_rn(gmax, mv[q]);
-                const bool cand = ((pv[q] & LF_LOW) != 0u) & (gd > 0);
-                const float gdf = cand ? __double2float_rn(gd) : 0.f;
-                gmxf = fmaxf(gmxf, gdf);
-                unsigned key = approx_key(gd, gdf, kvi[g * 4 + q], gcol[g] + q);
-                if constexpr (!FAST) key = cand ? key : 0u;
-                const bool gt = key > b1k;
-                b2k = max(b2k, min(b1k, key));
-                b1k = max(b1k, key);
-                idx1 = gt ? pv[q] : idx1;
+                for (int q = 0; q < 4; q++) {                                // branch-free: every slot evaluates a key
+                    const int k = g * 4 + q;
+                    const double gd = __dsub_rn(gmax, mv[q]);
+                    const bool cand = ((fm & (2u << (2 * k))) != 0u) & (gd > 0);
+                    const float gdf = cand ? __double2float_rn(gd) : 0.f;
+                    gmxf = fmaxf(gmxf, gdf);
+                    const unsigned key = cand ? approx_key(gd, gdf, kvi[k], gcol[g] + q) : 0u;
+                    const bool gt = key > b1k;
+                    b2k = max(b2k, min(b1k, key));
+                    b1k = max(b1k, key);
+                    k1 = gt ? k : k1;
+                    kq1 = gt ? kvi[k] : kq1;
+                }
             }
         }
+        const unsigned idx1 = b1k ? pfS[slot_of(k1)] : 0u;                   // the best candidate's word
         unsigned top1k, top2k;
         {
             const unsigned w1 = __reduce_max_sync(0xffffffffu, b1k);
             const unsigned widx = __reduce_max_sync(0xffffffffu, (b1k == w1) ? idx1 : 0u);
             const unsigned w2 = __reduce_max_sync(0xffffffffu, (idx1 == widx) ? b2k : b1k);
+            if (idx1 == widx && widx != 0u) {                                         // this lane owns the warp's winner
+                red.b_kq[warp] = kq1;
+                red.b_al[warp] = __ldcg(alpha_g + slot_of(k1));
+                red.b_mg[warp] = m_at(slot_of(k1));
+            }
             // stop-test bits: 1 = some candidate certainly has Gmax - m_t >= eps, 2 = undecided in float32, 4 = a candidate exists
             const unsigned fb = __reduce_or_sync(0xffffffffu, (gmxf > epsf ? 1u : 0u) | (gmxf == epsf ? 2u : 0u) | (gmxf > 0.f ? 4u : 0u));
             if (lane == 0) { red.b_k1[warp] = w1; red.b_pf[warp] = widx; red.b_k2[warp] = w2; red.b_fl[warp] = fb; }
@@ -391,6 +495,10 @@ smo_lean_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ or
             top1k = __reduce_max_sync(0xffffffffu, bk);
             pj = __reduce_max_sync(0xffffffffu, (bk == top1k) ? bi : 0u);
             top2k = __reduce_max_sync(0xffffffffu, (v && bi == pj) ? red.b_k2[lane] : bk);
+            {
+                const int wl = __ffs(__ballot_sync(0xffffffffu, v && bi == pj && pj != 0u)) - 1;
+                if (wl >= 0) { k_ij = widen(red.b_kq[wl]); alpha_j = red.b_al[wl]; mg_j = red.b_mg[wl]; }
+            }
             if (!(fl & 4u)) return true;                                              // no candidate: Gmin_idx == -1 (and Gmax + Gmax2 <= 0)
             if (!(fl & 1u)) {
                 if (!(fl & 2u)) return true;                                          // every Gmax - m_t < eps: svm.cpp:1040-1041
@@ -398,19 +506,21 @@ smo_lean_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ or
 #pragma unroll
                 for (int g = 0; g < G; g++) {
                     const int s4 = (g * NT + tid) * 4;
-                    double mv[4]; unsigned pv[4];
-                    load_m4(s4, mv); load_pf4(s4, pv);
+                    double mv[4];
+                    load_m4(s4, mv);
 #pragma unroll
-                    for (int q = 0; q < 4; q++) viol = viol | (((pv[q] & LF_LOW) != 0u) & (__dsub_rn(gmax, mv[q]) >= eps));
+                    for (int q = 0; q < 4; q++) viol = viol | (((fm & (2u << (2 * (g * 4 + q)))) != 0u) & (__dsub_rn(gmax, mv[q]) >= eps));
                 }
                 if (!__syncthreads_or(viol ? 1 : 0)) return true;
             }
         }
         if (top1k - top2k <= BAND || top1k <= KEY_TINY) {
             // ---- exact tie-break: libsvm's correctly rounded quotients for every element in the band (rare) ----
+            if constexpr (PROF) prof[7] += 1;                                     // how often: reported as slot 7
             const unsigned thrk = (top1k > BAND && top1k > KEY_TINY) ? top1k - BAND : 0u;
             double bestn = -CUDART_INF;
             unsigned bidx = 0u;
+            float kqb = 0.f;
 #pragma unroll
             for (int g = 0; g < G; g++) {
                 const int s4 = (g * NT + tid) * 4;
@@ -424,22 +534,30 @@ smo_lean_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ or
                             const double quad = __dsub_rn(__dadd_rn(QDi, QDc(gcol[g] + q)), __dmul_rn(2.0, widen(kvi[g * 4 + q])));
                             const double g2 = __dmul_rn(gd, gd);
                             const double nod = quad > 0 ? __ddiv_rn(g2, quad) : __ddiv_rn(g2, TAU);   // == -obj_diff
-                            if (nod > bestn || (nod == bestn && pv[q] > bidx)) { bestn = nod; bidx = pv[q]; }
+                            if (nod > bestn || (nod == bestn && pv[q] > bidx)) { bestn = nod; bidx = pv[q]; kqb = kvi[g * 4 + q]; }
                         }
                     }
                 }
             }
             const unsigned long long key = dkey(bestn);
             const UArg w = warp_argmax_u((unsigned)(key >> 32), (unsigned)key, bidx);
+            if (bidx == w.idx && w.idx != 0u) {
+                red.x_kq[warp] = kqb;
+                red.x_al[warp] = __ldcg(alpha_g + (int)((bidx >> SLOT_SHIFT) & SLOT_MASK));
+                red.x_mg[warp] = m_at((int)((bidx >> SLOT_SHIFT) & SLOT_MASK));
+            }
             if (lane == 0) { red.x_hi[warp] = w.hi; red.x_lo[warp] = w.lo; red.x_pf[warp] = w.idx; }
             __syncthreads();                                                      // rare barrier
             const bool v = lane < NW;
-            const UArg b = warp_argmax_u(v ? red.x_hi[lane] : 0u, v ? red.x_lo[lane] : 0u, v ? red.x_pf[lane] : 0u);
+            const unsigned xi = v ? red.x_pf[lane] : 0u;
+            const UArg b = warp_argmax_u(v ? red.x_hi[lane] : 0u, v ? red.x_lo[lane] : 0u, xi);
             pj = b.idx;                                                           // != 0: every candidate with a key >= thrk took part
+            const int wl = __ffs(__ballot_sync(0xffffffffu, v && xi == pj)) - 1;
+            k_ij = widen(red.x_kq[wl]); alpha_j = red.x_al[wl]; mg_j = red.x_mg[wl];
         }
         const int slot_j = (int)((pj >> SLOT_SHIFT) & SLOT_MASK);
         col_j = slot_col(slot_j);
-        mg_j = mG[slot_j];
+        alpha_i = red.al_i;
         return false;
     };
 
@@ -558,6 +676,7 @@ smo_lean_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ or
     };
 
     // ---------------- main loop (svm.cpp:742-907) ----------------
+    refresh_flags();                                             // builds the register mirror of the I_up / I_low bits
     bool scan_valid = false, second = false;                     // second: the retry of svm.cpp:756-764 after un-shrinking
     for (;;) {
         if (!second) {
@@ -585,9 +704,12 @@ smo_lean_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ or
         const int slot_i = (int)((pi >> SLOT_SHIFT) & SLOT_MASK), slot_j = (int)((pj >> SLOT_SHIFT) & SLOT_MASK);
         float kvj[KPT];
         load_row(col_j, kvj);                                    // in flight during the scalar update
-        if (warp == 0) {                                         // analytic 2-variable update, once per CTA
-            alpha_j = __ldcg(alpha_g + slot_j);
-            k_ij = widen(__ldg(K + (size_t)col_i * ldk + col_j));            // Q_i[j]: one more (L2-resident) load beside alpha_j
+        // analytic two-variable update, evaluated by EVERY warp (uniform): its ~250 dependent instructions run under the
+        // row-j fetch that each warp waits for anyway, and the CTA needs no third barrier per iteration (a single warp
+        // computing it kept the other fifteen parked for ~0.9 us, measured)
+        double a, b;
+        int sti, stj;
+        {
             const double C = Cc;
             const bool yi = slot_i < ysplit, yj = slot_j < ysplit;
             const double Gi = yi ? -gmax : gmax;                 // G = -y m (exact)
@@ -616,64 +738,87 @@ smo_lean_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ or
                 if (sum > C) { if (aj > C) { aj = C; ai = __dsub_rn(sum, C); } }
                 else         { if (ai < 0) { ai = 0; aj = sum; } }
             }
-            if (lane == 0) {
-                const double dai = __dsub_rn(ai, alpha_i), daj = __dsub_rn(aj, alpha_j);
-                const int sti = ai >= C ? ST_UPPER : (ai <= 0 ? ST_LOWER : ST_FREE);
-                const int stj = aj >= C ? ST_UPPER : (aj <= 0 ? ST_LOWER : ST_FREE);
-                red.bc_d[0] = yi ? -dai : dai;                   // a = -y_i dalpha_i
-                red.bc_d[1] = yj ? -daj : daj;                   // b = -y_j dalpha_j
-                red.bc_i[0] = sti; red.bc_i[1] = stj;
-                alpha_g[slot_i] = ai; alpha_g[slot_j] = aj;
-                // new status and set membership of i and j: the fused scan below must see them
-                pfS[slot_i] = (pi & ~15u) | lean_flags(yi, sti);
-                pfS[slot_j] = (pj & ~15u) | lean_flags(yj, stj);
-            }
+            const double dai = __dsub_rn(ai, alpha_i), daj = __dsub_rn(aj, alpha_j);
+            sti = ai >= C ? ST_UPPER : (ai <= 0 ? ST_LOWER : ST_FREE);
+            stj = aj >= C ? ST_UPPER : (aj <= 0 ? ST_LOWER : ST_FREE);
+            a = yi ? -dai : dai;                                 // a = -y_i dalpha_i
+            b = yj ? -daj : daj;                                 // b = -y_j dalpha_j
+            // the OWNERS of i and j store alpha and the slot word (new status and set membership) and patch their flag mask;
+            // nobody else reads these before the next barrier
+            auto own = [&](int s, unsigned w, bool y, int st, double av) {
+                const int grp = s >> 2;
+                if ((grp & (NT - 1)) == tid) {
+                    const unsigned fl = lean_flags(y, st);
+                    const int k = (grp / NT) * 4 + (s & 3);
+                    alpha_g[s] = av;
+                    pfS[s] = (w & ~15u) | fl;
+                    fm = (fm & ~(3u << (2 * k))) | ((fl >> 2) << (2 * k));
+                }
+            };
+            own(slot_i, pi, yi, sti, ai);
+            own(slot_j, pj, yj, stj, aj);
         }
         tick(4);
-        __syncthreads();                                                          // barrier 3
         tick(5);
-        const double a = red.bc_d[0], b = red.bc_d[1];
-        const int sti = red.bc_i[0], stj = red.bc_i[1];
 
-        // m update (svm.cpp:866-872) over every slot, fused with the next iteration's local scan
-        la = -CUDART_INF; la_pf = 0u; la_tie = false;
+        // m update (svm.cpp:866-872) over every slot, fused with the next iteration's local scan: strict compare and a tie
+        // flag here; a thread that met equal values redoes its scan with the full (value, position) order
+        la = -CUDART_INF;
+        int la_k = -1;
+        unsigned la_tie = 0u;
+        if constexpr (FAST) {
+            double mvu[4];
+            lean_loop<G * 4>([&](auto kc) {
+                constexpr int k = decltype(kc)::value, g = k >> 2, q = k & 3;
+                if constexpr (q == 0) load_m4((g * NT + tid) * 4, mvu);
+                lean_update_slot<k>(mvu[q], kvi[k], kvj[k], a, b, fm, la, la_k, la_tie);
+                if constexpr (q == 3) store_m4((g * NT + tid) * 4, mvu);
+            });
+        } else {
 #pragma unroll
-        for (int g = 0; g < G; g++) {
-            const int s4 = (g * NT + tid) * 4;
-            double mv[4]; unsigned pv[4];
-            load_m4(s4, mv); load_pf4(s4, pv);
+            for (int g = 0; g < G; g++) {
+                const int s4 = (g * NT + tid) * 4;
+                double mv[4];
+                load_m4(s4, mv);
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                mv[q] = __dadd_rn(mv[q], __dadd_rn(__dmul_rn(widen(kvi[g * 4 + q]), a), __dmul_rn(widen(kvj[g * 4 + q]), b)));
-                scan_fast(mv[q], pv[q]);
+                for (int q = 0; q < 4; q++) {
+                    const int k = g * 4 + q;
+                    mv[q] = __dadd_rn(mv[q], __dadd_rn(__dmul_rn(widen(kvi[k]), a), __dmul_rn(widen(kvj[k]), b)));
+                    const bool up = (fm & (1u << (2 * k))) != 0u;
+                    const bool better = up & (mv[q] > la);
+                    la_tie |= (up & (mv[q] == la)) ? 1u : 0u;
+                    la = better ? mv[q] : la;
+                    la_k = better ? k : la_k;
+                }
+                store_m4(s4, mv);
             }
-            *reinterpret_cast<double2 *>(mG + s4) = make_double2(mv[0], mv[1]);
-            *reinterpret_cast<double2 *>(mG + s4 + 2) = make_double2(mv[2], mv[3]);
         }
-        if (la_tie) local_scan();                                // equal values met: redo this thread's scan with the full order
+        la_pf = la_k >= 0 ? pfS[slot_of(la_k)] : 0u;
+        if (la_tie) local_scan();
         scan_valid = true;
-        // G_bar over all l when a bound status flips (svm.cpp:876-905): i first, then j.  The rows are read again (L2) so
-        // that nothing of this path stays live across the hot loop.
+        // G_bar over all l when a bound status flips (svm.cpp:876-905): i first, then j; K_i and K_j are still in registers
         const bool need_i = use_gbar && (((pi & 3u) == ST_UPPER) != (sti == ST_UPPER));
         const bool need_j = use_gbar && (((pj & 3u) == ST_UPPER) != (stj == ST_UPPER));
         if (need_i || need_j) {
             // Gbar -= C Q_i (was upper) / += C Q_i (became upper)  <=>  mbar += fl(c K_i), c = +/- y_i C
             const double ci = (((pi & 3u) == ST_UPPER) == (slot_i < ysplit)) ? Cc : -Cc;
             const double cj = (((pj & 3u) == ST_UPPER) == (slot_j < ysplit)) ? Cc : -Cc;
-            const float *__restrict__ Kri = K + (size_t)col_i * ldk, *__restrict__ Krj = K + (size_t)col_j * ldk;
-#pragma unroll 1
+            // one group of 4 slots at a time, the next group's G_bar already in flight (all of it at once spills)
+            double2 nx0 = make_double2(0, 0), nx1 = nx0;
+            if (tid * 4 < nslots) { nx0 = *reinterpret_cast<const double2 *>(gbar_g + tid * 4); nx1 = *reinterpret_cast<const double2 *>(gbar_g + tid * 4 + 2); }
+#pragma unroll
             for (int g = 0; g < G; g++) {
                 const int s4 = (g * NT + tid) * 4;
+                double gb[4] = {nx0.x, nx0.y, nx1.x, nx1.y};
+                if (g + 1 < G) {
+                    const int n4 = ((g + 1) * NT + tid) * 4;
+                    if (n4 < nslots) { nx0 = *reinterpret_cast<const double2 *>(gbar_g + n4); nx1 = *reinterpret_cast<const double2 *>(gbar_g + n4 + 2); }
+                }
                 if (s4 < nslots) {
-                    const float4 vi = __ldg(reinterpret_cast<const float4 *>(Kri + gcol[g]));
-                    const float4 vj = __ldg(reinterpret_cast<const float4 *>(Krj + gcol[g]));
-                    const float ki4[4] = {vi.x, vi.y, vi.z, vi.w}, kj4[4] = {vj.x, vj.y, vj.z, vj.w};
-                    const double2 g01 = *reinterpret_cast<const double2 *>(gbar_g + s4), g23 = *reinterpret_cast<const double2 *>(gbar_g + s4 + 2);
-                    double gb[4] = {g01.x, g01.y, g23.x, g23.y};
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        if (need_i) gb[q] = __dadd_rn(gb[q], __dmul_rn(ci, widen(ki4[q])));
-                        if (need_j) gb[q] = __dadd_rn(gb[q], __dmul_rn(cj, widen(kj4[q])));
+                        if (need_i) gb[q] = __dadd_rn(gb[q], __dmul_rn(ci, widen(kvi[g * 4 + q])));
+                        if (need_j) gb[q] = __dadd_rn(gb[q], __dmul_rn(cj, widen(kvj[g * 4 + q])));
                     }
                     *reinterpret_cast<double2 *>(gbar_g + s4) = make_double2(gb[0], gb[1]);
                     *reinterpret_cast<double2 *>(gbar_g + s4 + 2) = make_double2(gb[2], gb[3]);
@@ -762,10 +907,11 @@ smo_lean_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ or
 }
 
 template <int NT, int G, bool FAST, bool PROF>
-cudaError_t launch_lean_one(const SmoProblem *probs, const int *order, int n_prob, cudaStream_t st)
+cudaError_t launch_lean_one(const SmoProblem *probs, const int *order, int n_prob, bool exclusive, cudaStream_t st)
 {
     constexpr int LCAP = NT * G * 4;
-    const size_t smem = (size_t)LCAP * 12;
+    // exclusive: ask for more than half of the SM's 227 KB so that no second CTA (of this or of the shared launch) fits
+    const size_t smem = exclusive ? std::max<size_t>((size_t)LCAP * 12, 132 * 1024) : (size_t)LCAP * 12;
     auto kern = smo_lean_kernel<NT, G, FAST, PROF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -776,10 +922,10 @@ cudaError_t launch_lean_one(const SmoProblem *probs, const int *order, int n_pro
 }
 
 template <int NT, int G>
-cudaError_t launch_lean_cfg(const SmoProblem *probs, const int *order, int n_prob, bool fast, bool prof, cudaStream_t st)
+cudaError_t launch_lean_cfg(const SmoProblem *probs, const int *order, int n_prob, bool fast, bool prof, bool excl, cudaStream_t st)
 {
-    if (prof) return fast ? launch_lean_one<NT, G, true, true>(probs, order, n_prob, st) : launch_lean_one<NT, G, false, true>(probs, order, n_prob, st);
-    return fast ? launch_lean_one<NT, G, true, false>(probs, order, n_prob, st) : launch_lean_one<NT, G, false, false>(probs, order, n_prob, st);
+    if (prof) return fast ? launch_lean_one<NT, G, true, true>(probs, order, n_prob, excl, st) : launch_lean_one<NT, G, false, true>(probs, order, n_prob, excl, st);
+    return fast ? launch_lean_one<NT, G, true, false>(probs, order, n_prob, excl, st) : launch_lean_one<NT, G, false, false>(probs, order, n_prob, excl, st);
 }
 
 int env_int(const char *name, int dflt)
@@ -793,24 +939,16 @@ int env_int(const char *name, int dflt)
 int smo_lean_max_slots() { return 16384; }
 
 // Every problem of the launch must have a slot layout (nseg > 0, nslots <= max_slots <= 16384, l < 16383).
-// Shapes: (threads) x (4-slot groups per thread).  8 groups = 32 slots per thread at 128 registers, 4 groups = 16 slots at 64
-// registers; both keep two 8192-slot sub-problems per SM.  B200GS_LEAN_G (4 | 8) is a development switch.
-cudaError_t launch_smo_lean(const SmoProblem *d_probs, const int *d_order, int n_prob, int max_slots, bool fast, cudaStream_t st)
+// Shapes: (threads) x 4 groups of 4 slots per thread = 16 slots per thread at 64 registers: two 8192-slot sub-problems per SM
+// (32 slots per thread at 128 registers measured no faster and does not fit the one-register flag mask).
+cudaError_t launch_smo_lean(const SmoProblem *d_probs, const int *d_order, int n_prob, int max_slots, bool fast, bool exclusive, cudaStream_t st)
 {
     if (n_prob <= 0) return cudaSuccess;
     const bool prof = env_int("B200GS_SMO_PROF", 0) != 0;                    // development switch: per-phase cycle counters
     if (env_int("B200GS_SMO_NOFAST", 0)) fast = false;
-    const int G = env_int("B200GS_LEAN_G", 4);
-    if (G == 8) {
-        if (max_slots <= 2048) return launch_lean_cfg<64, 8>(d_probs, d_order, n_prob, fast, prof, st);
-        if (max_slots <= 4096) return launch_lean_cfg<128, 8>(d_probs, d_order, n_prob, fast, prof, st);
-        if (max_slots <= 8192) return launch_lean_cfg<256, 8>(d_probs, d_order, n_prob, fast, prof, st);
-        if (max_slots <= 16384) return launch_lean_cfg<512, 8>(d_probs, d_order, n_prob, fast, prof, st);
-        return cudaErrorInvalidValue;
-    }
-    if (max_slots <= 2048) return launch_lean_cfg<128, 4>(d_probs, d_order, n_prob, fast, prof, st);
-    if (max_slots <= 4096) return launch_lean_cfg<256, 4>(d_probs, d_order, n_prob, fast, prof, st);
-    if (max_slots <= 8192) return launch_lean_cfg<512, 4>(d_probs, d_order, n_prob, fast, prof, st);
-    if (max_slots <= 16384) return launch_lean_cfg<1024, 4>(d_probs, d_order, n_prob, fast, prof, st);
+    if (max_slots <= 2048) return launch_lean_cfg<128, 4>(d_probs, d_order, n_prob, fast, prof, exclusive, st);
+    if (max_slots <= 4096) return launch_lean_cfg<256, 4>(d_probs, d_order, n_prob, fast, prof, exclusive, st);
+    if (max_slots <= 8192) return launch_lean_cfg<512, 4>(d_probs, d_order, n_prob, fast, prof, exclusive, st);
+    if (max_slots <= 16384) return launch_lean_cfg<1024, 4>(d_probs, d_order, n_prob, fast, prof, exclusive, st);
     return cudaErrorInvalidValue;
 }

@@ -20,6 +20,24 @@ def rank_world():
     return (td.get_rank(), td.get_world_size()) if td else (0, 1)
 
 
+def local_devices():
+    """GPUs one plain ``fit()`` drives when torch.distributed is NOT initialised: every visible sm_100 device by default
+    (B200GS_DEVICES = "all" | a count | a comma-separated list of indices; "1" keeps the search on one GPU)."""
+    import os
+    from .engine import device_count
+    spec = os.environ.get("B200GS_DEVICES", "all").strip().lower()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:      # a torchrun rank whose process group is not up: its own GPU only
+        return [int(os.environ.get("LOCAL_RANK", "0"))]
+    n = device_count()
+    if n <= 0:
+        return [0]                                      # Engine(0) then fails loudly: there is no CPU fallback
+    if spec in ("", "all"):
+        return list(range(n))
+    if "," in spec:
+        return [int(x) for x in spec.split(",") if x.strip() != ""]
+    return list(range(max(1, min(n, int(spec)))))
+
+
 def assign_candidates(n_cand, world, costs=None):
     """Candidate indices of every rank (list of ascending lists).  Without costs: strided, c -> c mod world.  With a
     predicted cost per candidate: sorted by cost and dealt in snake order (0..W-1, W-1..0, ...), so that every rank
@@ -72,6 +90,34 @@ def assign_for_plan(plan, n_cand, world):
         if keys is not None:
             return assign_groups(n_cand, world, costs, keys)
     return assign_candidates(n_cand, world, costs)
+
+
+def merge_candidates(locs, parts, n_cand, n_splits):
+    """Host-side merge of per-device score blocks (in-process multi-GPU path): same result layout as allgather_candidates."""
+    keys = ["test", "train", "fit_time", "score_time"]
+    out = {}
+    for k in keys:
+        if all(l is None or l.get(k) is None for l in locs):
+            out[k] = None
+            continue
+        full = np.full((n_cand, n_splits), np.nan)
+        for l, idx in zip(locs, parts):
+            if l is not None and len(idx):
+                full[idx] = l[k]
+        out[k] = full
+    return out
+
+
+def merge_profiles(profs):
+    """Device profiles of concurrent per-GPU calls: times are the slowest device's, counters add up."""
+    out = {}
+    for p in profs:
+        for k, v in p.items():
+            if k.startswith("ms_"):
+                out[k] = max(out.get(k, 0.0), v)
+            else:
+                out[k] = out.get(k, 0) + v
+    return out
 
 
 def broadcast_plan(obj):

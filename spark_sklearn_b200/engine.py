@@ -22,7 +22,8 @@ class GsProfile(ctypes.Structure):
                 ("ms_kernel_matrix", ctypes.c_float), ("ms_solve", ctypes.c_float), ("ms_score", ctypes.c_float),
                 ("launches", ctypes.c_int64), ("smo_iterations", ctypes.c_int64),
                 ("solve_bytes", ctypes.c_double), ("gram_flops", ctypes.c_double), ("gram_bytes", ctypes.c_double),
-                ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64)]
+                ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64),
+                ("ms_tensor", ctypes.c_float), ("tensor_flops", ctypes.c_double)]
 
 
 class EngineError(RuntimeError):
@@ -44,6 +45,9 @@ def load_library():
     c = ctypes
     vp, i32, i64, u32, dbl = c.c_void_p, c.c_int32, c.c_int64, c.c_uint32, c.c_double
     L.gs_version.restype = c.c_int
+    L.gs_device_count.restype = c.c_int
+    L.gs_set_scoring.argtypes = [vp, i32, i32]
+    L.gs_set_scoring.restype = c.c_int
     L.gs_create.argtypes = [c.c_int, c.POINTER(vp)]
     L.gs_destroy.argtypes = [vp]
     L.gs_destroy.restype = None
@@ -64,6 +68,8 @@ def load_library():
     L.gs_svc_predicted_iterations.restype = dbl
     L.gs_svc_cluster_count.argtypes = [vp, i32, i32]
     L.gs_svc_cluster_count.restype = i32
+    L.gs_svc_schedule.argtypes = [vp, i32, i32, vp, vp]
+    L.gs_svc_schedule.restype = None
     for f in ("gs_create", "gs_set_data", "gs_svc", "gs_svc_refit", "gs_ridge", "gs_ridge_refit", "gs_logreg",
               "gs_logreg_refit", "gs_get_profile", "gs_debug_gram", "gs_debug_kernel_matrix", "gs_debug_gemm_nt"):
         getattr(L, f).restype = c.c_int
@@ -73,6 +79,11 @@ def load_library():
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def device_count():
+    """sm_100 GPUs visible to this process (0 without a GPU or without the library's CUDA runtime)."""
+    return int(load_library().gs_device_count())
 
 
 class Engine:
@@ -100,6 +111,10 @@ class Engine:
     def _check(self, st):
         if st != 0:
             raise EngineError(st, (self._L.gs_last_error(self._h) or b"").decode())
+
+    def set_scoring(self, kind=0, pos_class=1):
+        """Scorer of the following search calls (include/b200gs.h GS_SCORE_*): reference base_search.py:43 check_scoring."""
+        self._check(self._L.gs_set_scoring(self._h, int(kind), int(pos_class)))
 
     # -- the "broadcast" (reference base_search.py:63-65) --
     def set_data(self, X, fold_id, n_splits, y_class=None, y_target=None):

@@ -72,15 +72,43 @@ def _pad_scores(arr_list, my):
     return None if not my else np.concatenate(arr_list, 0)
 
 
+# scoring= names with a fused CUDA scorer (include/b200gs.h GS_SCORE_*); None = the estimator's own score
+CLASSIFICATION_SCORERS = {None: 0, "accuracy": 0, "balanced_accuracy": 1, "f1": 2, "precision": 3, "recall": 4, "roc_auc": 5,
+                          "f1_macro": 6, "f1_micro": 7, "f1_weighted": 8}
+REGRESSION_SCORERS = {None: 0, "r2": 0, "neg_mean_squared_error": 16, "neg_root_mean_squared_error": 17}
+
+
 class _Plan:
-    def __init__(self, estimator, cands, X, y, fold_id, n_splits):
+    def __init__(self, estimator, cands, X, y, fold_id, n_splits, device=None):
         self.estimator, self.cands = estimator, cands
         self.X, self.y, self.fold_id, self.n_splits = _as_matrix(X), y, fold_id, n_splits
-        self.engine = get_engine()
+        self.engine = get_engine(device)
         self._prof = {}
+        self.score_kind, self.score_pos = 0, 1
 
     def profile(self):
         return dict(self._prof)
+
+    scorers = {None: 0}
+
+    def set_scoring(self, scoring):
+        """reference base_search.py:43: check_scoring(estimator, scoring).  Only scorers with a fused CUDA path are accepted
+        (strings; callables and multi-metric dicts would need the fitted estimator on the host: no CPU fallback)."""
+        if scoring is not None and not isinstance(scoring, str):
+            raise NotImplementedError("scoring must be None or a scorer name; callables / multi-metric scoring have no CUDA path")
+        if scoring not in self.scorers:
+            raise NotImplementedError("scoring=%r has no CUDA path for %s (available: %s)" % (
+                scoring, type(self.estimator).__name__, sorted(k for k in self.scorers if k)))
+        self.score_kind, self.score_pos = self.scorers[scoring], 1
+        if self.score_kind in (2, 3, 4):                      # precision / recall / f1: scikit-learn's pos_label=1
+            classes = list(getattr(self, "classes", []))
+            if len(classes) != 2:
+                raise ValueError("Target is multiclass but average='binary'. Please choose another average setting")
+            if 1 not in classes:
+                raise ValueError("pos_label=1 is not a valid label. It should be one of %s" % classes)
+            self.score_pos = classes.index(1)
+        elif self.score_kind == 5 and len(getattr(self, "classes", [])) != 2:
+            raise NotImplementedError("scoring='roc_auc' has a CUDA path for binary problems only")
 
     def costs(self):
         """Predicted relative cost of every candidate (None: all alike) -- used to balance candidates over GPUs."""
@@ -117,16 +145,20 @@ class _Plan:
 
 # ------------------------------------------------------------------ SVC -----------------------
 class SVCAdapter:
+    multi_device = True        # plan(..., device=d): one plan per GPU of the in-process scheduler
+    scorers = CLASSIFICATION_SCORERS
+
     @staticmethod
-    def plan(estimator, cands, X, y, fold_id, n_splits):
-        return SVCPlan(estimator, cands, X, y, fold_id, n_splits)
+    def plan(estimator, cands, X, y, fold_id, n_splits, device=None):
+        return SVCPlan(estimator, cands, X, y, fold_id, n_splits, device)
 
 
 class SVCPlan(_Plan):
     """sklearn.svm.SVC (C-SVC).  Scalars per candidate: kernel, C, gamma (resolved per fold)."""
+    scorers = CLASSIFICATION_SCORERS
 
-    def __init__(self, estimator, cands, X, y, fold_id, n_splits):
-        super().__init__(estimator, cands, X, y, fold_id, n_splits)
+    def __init__(self, estimator, cands, X, y, fold_id, n_splits, device=None):
+        super().__init__(estimator, cands, X, y, fold_id, n_splits, device)
         if y is None:
             raise ValueError("SVC needs y")
         self.classes, self.y_class = np.unique(np.asarray(y), return_inverse=True)
@@ -211,6 +243,7 @@ class SVCPlan(_Plan):
             # B200GS_GRAM=tensor: opt-in tcgen05 Gram (fp32-faithful; scores match to solver tolerance, not bit for bit)
             import os
             flags = 2 if os.environ.get("B200GS_GRAM", "exact") == "tensor" else 0
+            self.engine.set_scoring(self.score_kind, self.score_pos)
             r = self.engine.svc(kern, C, gam, tol=tol, max_iter=max_iter, shrinking=shrinking,
                                 return_train=return_train, flags=flags)
             for key in ("test", "fit_ms", "score_ms", "n_iter"):
@@ -279,14 +312,19 @@ def materialize_svc(est, X, y_class, classes, pair_coef, rho, n_iter, gamma):
 
 # ------------------------------------------------------------------ Ridge ---------------------
 class RidgeAdapter:
+    multi_device = True        # plan(..., device=d): one plan per GPU of the in-process scheduler
+    scorers = REGRESSION_SCORERS
+
     @staticmethod
-    def plan(estimator, cands, X, y, fold_id, n_splits):
-        return RidgePlan(estimator, cands, X, y, fold_id, n_splits)
+    def plan(estimator, cands, X, y, fold_id, n_splits, device=None):
+        return RidgePlan(estimator, cands, X, y, fold_id, n_splits, device)
 
 
 class RidgePlan(_Plan):
-    def __init__(self, estimator, cands, X, y, fold_id, n_splits):
-        super().__init__(estimator, cands, X, y, fold_id, n_splits)
+    scorers = REGRESSION_SCORERS
+
+    def __init__(self, estimator, cands, X, y, fold_id, n_splits, device=None):
+        super().__init__(estimator, cands, X, y, fold_id, n_splits, device)
         y = np.asarray(y)
         if y.ndim != 1:
             raise NotImplementedError("multi-output Ridge is not supported by the CUDA path")
@@ -315,6 +353,7 @@ class RidgePlan(_Plan):
         prof = {}
         for fi, items in groups.items():
             idx = [j for j, _ in items]
+            self.engine.set_scoring(self.score_kind, self.score_pos)
             r = self.engine.ridge([a for _, a in items], fit_intercept=fi, return_train=return_train)
             for key in ("test", "fit_ms", "score_ms"):
                 res[key][idx] = r[key]
@@ -341,14 +380,19 @@ class RidgePlan(_Plan):
 
 # ------------------------------------------------------------------ LogisticRegression --------
 class LogRegAdapter:
+    multi_device = True        # plan(..., device=d): one plan per GPU of the in-process scheduler
+    scorers = CLASSIFICATION_SCORERS
+
     @staticmethod
-    def plan(estimator, cands, X, y, fold_id, n_splits):
-        return LogRegPlan(estimator, cands, X, y, fold_id, n_splits)
+    def plan(estimator, cands, X, y, fold_id, n_splits, device=None):
+        return LogRegPlan(estimator, cands, X, y, fold_id, n_splits, device)
 
 
 class LogRegPlan(_Plan):
-    def __init__(self, estimator, cands, X, y, fold_id, n_splits):
-        super().__init__(estimator, cands, X, y, fold_id, n_splits)
+    scorers = CLASSIFICATION_SCORERS
+
+    def __init__(self, estimator, cands, X, y, fold_id, n_splits, device=None):
+        super().__init__(estimator, cands, X, y, fold_id, n_splits, device)
         self.classes, self.y_class = np.unique(np.asarray(y), return_inverse=True)
         if len(self.classes) != 2:
             raise NotImplementedError("LogisticRegression CUDA path is binary only (got %d classes)" % len(self.classes))
@@ -382,6 +426,7 @@ class LogRegPlan(_Plan):
         prof = {}
         for (tol, mi, fi), items in groups.items():
             idx = [j for j, _ in items]
+            self.engine.set_scoring(self.score_kind, self.score_pos)
             r = self.engine.logreg([c for _, c in items], tol=tol, max_iter=mi, fit_intercept=fi,
                                    return_train=return_train)
             for key in ("test", "fit_ms", "score_ms"):

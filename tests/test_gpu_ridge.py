@@ -68,3 +68,31 @@ def test_ridge_c5_full_size_vs_golden(engine):
     r = engine.ridge([c["alpha"] for c in W.candidates(w)])
     assert np.abs(r["test"].mean(1) - g["test_scores"].mean(1)).max() <= 5e-5
     assert np.abs(r["train"].mean(1) - g["train_scores"].mean(1)).max() <= 5e-5
+
+
+def test_ridge_large_offsets_match_sklearn_float64(engine):
+    """Features and targets whose mean dwarfs their spread (a year column near 2000, targets offset by 1e4): the Grams
+    are formed from mean-shifted data, so the centring subtractions cancel nothing.  Checked against scikit-learn on
+    float64 copies of the same float32 values (the well-conditioned answer), through the public API incl. the refit."""
+    import warnings
+    from sklearn.linear_model import Ridge
+    from sklearn.model_selection import GridSearchCV as SkGrid
+    from spark_sklearn_b200 import GridSearchCV
+    rng = np.random.RandomState(7)
+    n, d = 3000, 40
+    X = rng.randn(n, d).astype(np.float32)
+    y = (X @ rng.randn(d) + 0.3 * rng.randn(n)).astype(np.float32)
+    X = (X + 1000.0).astype(np.float32)
+    X[:, 0] = (2000.0 + rng.randint(0, 20, n)).astype(np.float32)
+    y = (y + 1e4).astype(np.float32)
+    grid = {"alpha": [1e-2, 1.0, 100.0]}
+    a = GridSearchCV(None, Ridge(), grid, cv=5).fit(X, y)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        b = SkGrid(Ridge(), grid, cv=5, return_train_score=True).fit(X.astype(np.float64), y.astype(np.float64))
+    assert np.abs(a.cv_results_["mean_test_score"] - b.cv_results_["mean_test_score"]).max() <= 1e-4
+    assert np.abs(a.cv_results_["mean_train_score"] - b.cv_results_["mean_train_score"]).max() <= 1e-4
+    assert a.best_index_ == b.best_index_
+    res = y - a.predict(X)
+    assert np.abs(res).max() < 3.0 and abs(res.mean()) < 0.05          # the intercept carries the offsets back
+    assert np.abs(a.best_estimator_.coef_ - b.best_estimator_.coef_).max() <= 2e-3 * np.abs(b.best_estimator_.coef_).max()

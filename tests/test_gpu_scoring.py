@@ -1,0 +1,74 @@
+"""GPU parity tests for `scoring=` (reference grid_search.py:212-214, base_search.py:43,83-87): every fused CUDA scorer
+against scikit-learn's GridSearchCV with the same scorer on the same folds.  Count-based scorers are exact rational
+functions of integer counts (bit-equal up to the last float64 ulp of a different evaluation order); roc_auc is the
+Mann-Whitney statistic of the decision values (SVC: float64, identical ranking; LogisticRegression: float32 z)."""
+import warnings
+
+import numpy as np
+import pytest
+
+from spark_sklearn_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+def _both(est, grid, X, y, scoring, cv=5):
+    from sklearn.model_selection import GridSearchCV as SkGrid
+    from spark_sklearn_b200 import GridSearchCV
+    a = GridSearchCV(None, est, grid, cv=cv, scoring=scoring, refit=False).fit(X, y)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        b = SkGrid(est, grid, cv=cv, scoring=scoring, return_train_score=True, refit=False).fit(X, y)
+    return a.cv_results_, b.cv_results_
+
+
+@pytest.mark.parametrize("scoring", ["accuracy", "balanced_accuracy", "f1", "precision", "recall", "roc_auc", "f1_macro", "f1_weighted", "f1_micro"])
+def test_svc_binary_scorers(engine, scoring):
+    from sklearn.svm import SVC
+    w = W.make_workload("c2_small")
+    grid = {"C": [0.1, 10.0], "gamma": [1 / 512, 1 / 64]}
+    a, b = _both(SVC(kernel="rbf"), grid, w["X"], w["y"], scoring)
+    for k in range(5):
+        for part in ("test", "train"):
+            key = "split%d_%s_score" % (k, part)
+            np.testing.assert_allclose(a[key], b[key], rtol=0, atol=1e-12, err_msg="%s %s" % (scoring, key))
+    np.testing.assert_array_equal(a["rank_test_score"], b["rank_test_score"])
+
+
+@pytest.mark.parametrize("scoring", ["balanced_accuracy", "f1_macro", "f1_weighted"])
+def test_svc_multiclass_scorers_iris(engine, scoring):
+    from sklearn import svm
+    w = W.make_workload("c1")
+    a, b = _both(svm.SVC(gamma="auto"), {"kernel": ("linear", "rbf"), "C": [1, 10]}, w["X"], w["y"], scoring)
+    np.testing.assert_allclose(a["mean_test_score"], b["mean_test_score"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(a["mean_train_score"], b["mean_train_score"], rtol=0, atol=1e-12)
+
+
+def test_binary_only_scorers_raise_on_multiclass(engine):
+    from sklearn import svm
+    from spark_sklearn_b200 import GridSearchCV
+    w = W.make_workload("c1")
+    for scoring in ("f1", "roc_auc"):
+        with pytest.raises((ValueError, NotImplementedError)):
+            GridSearchCV(None, svm.SVC(gamma="auto"), {"C": [1, 10]}, cv=3, scoring=scoring).fit(w["X"], w["y"])
+
+
+@pytest.mark.parametrize("scoring", ["f1", "roc_auc", "balanced_accuracy"])
+def test_logreg_scorers(engine, scoring):
+    from sklearn.linear_model import LogisticRegression
+    w = W.make_workload("c3_small")
+    a, b = _both(LogisticRegression(), {"C": [1e-3, 1e-1, 50.0]}, w["X"], w["y"], scoring)
+    # <= 2 borderline rows of 4000 flip (test_gpu_logreg.py); AUC moves by a few pairs in 4e5
+    assert np.abs(a["mean_test_score"] - b["mean_test_score"]).max() <= 1e-3
+    assert np.abs(a["mean_train_score"] - b["mean_train_score"]).max() <= 1e-3
+
+
+@pytest.mark.parametrize("scoring", ["r2", "neg_mean_squared_error", "neg_root_mean_squared_error"])
+def test_ridge_scorers(engine, scoring):
+    from sklearn.linear_model import Ridge
+    w = W.make_workload("c5_small")
+    a, b = _both(Ridge(), {"alpha": np.logspace(-2, 3, 6)}, w["X"], w["y"], scoring)
+    scale = np.abs(b["mean_test_score"]).max()
+    assert np.abs(a["mean_test_score"] - b["mean_test_score"]).max() <= 1e-4 * max(scale, 1.0)
+    assert np.abs(a["mean_train_score"] - b["mean_train_score"]).max() <= 1e-4 * max(scale, 1.0)
+    np.testing.assert_array_equal(a["rank_test_score"], b["rank_test_score"])

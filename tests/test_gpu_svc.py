@@ -266,3 +266,22 @@ def test_tensor_core_gram_mode(engine):
     assert np.abs(r["test"].mean(1) - g["test_scores"].mean(1)).max() <= 3e-3
     rel = np.abs(r["n_iter"] - g["diag"][:, :, 0]) / g["diag"][:, :, 0]
     assert np.median(rel) < 0.05
+
+
+def test_in_process_multi_gpu_equals_single_gpu(monkeypatch):
+    """One plain fit() on a node with several GPUs drives all of them (a handle and a host thread per device, no
+    torch.distributed): identical cv_results_ to the one-GPU search; skipped on a one-GPU box."""
+    from sklearn.svm import SVC
+    from spark_sklearn_b200 import GridSearchCV
+    from spark_sklearn_b200.engine import device_count
+    if device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    w = W.make_workload("c2_mid")
+    monkeypatch.setenv("B200GS_DEVICES", "1")
+    one = GridSearchCV(None, SVC(kernel="rbf"), w["param_grid"], cv=w["cv"], refit=False).fit(w["X"], w["y"])
+    monkeypatch.setenv("B200GS_DEVICES", "all")
+    many = GridSearchCV(None, SVC(kernel="rbf"), w["param_grid"], cv=w["cv"], refit=False).fit(w["X"], w["y"])
+    assert len(many.devices_) == min(device_count(), 16) and len(one.devices_) == 1
+    for k in one.cv_results_:
+        if "score" in k:
+            np.testing.assert_array_equal(np.asarray(one.cv_results_[k], float), np.asarray(many.cv_results_[k], float), err_msg=k)

@@ -193,7 +193,10 @@ def test_unsupported_configurations_raise_instead_of_falling_back():
     with pytest.raises(NotImplementedError):
         GridSearchCV(None, DecisionTreeClassifier(), {"max_depth": [1, 2]}, cv=3).fit(X, y)
     with pytest.raises(NotImplementedError):
-        GridSearchCV(None, svm.SVC(), {"C": [1.0]}, scoring="f1_macro", cv=3).fit(X, y)
+        GridSearchCV(None, svm.SVC(), {"C": [1.0]}, scoring="neg_log_loss", cv=3).fit(X, y)      # no fused scorer
+    with pytest.raises(NotImplementedError):
+        from sklearn.metrics import make_scorer, accuracy_score
+        GridSearchCV(None, svm.SVC(), {"C": [1.0]}, scoring=make_scorer(accuracy_score), cv=3).fit(X, y)
     with pytest.raises(ValueError):
         GridSearchCV(None, svm.SVC(), {"C": 1.0})          # _check_param_grid (grid_search.py:226)
 
@@ -264,6 +267,40 @@ def test_assign_groups_keeps_groups_whole_or_falls_back():
     assert assign_groups(len(cost), 16, cost, keys) == assign_candidates(len(cost), 16, cost)
     skew = cost.copy(); skew[np.array([k == keys[0] for k in keys])] *= 100
     assert assign_groups(len(cost), world, skew, keys) == assign_candidates(len(cost), world, skew)
+
+
+def test_in_process_scheduler_deals_candidates_over_devices_and_merges(monkeypatch):
+    """One fit() over several devices without torch.distributed (north_star: "a single in-process scheduler"): a plan and a
+    host thread per device, candidates dealt by predicted cost, host-side merge -- cv_results_ identical to the
+    one-device search, whatever the device count (incl. more devices than candidates)."""
+    from sklearn import svm
+    from spark_sklearn_b200 import GridSearchCV, base_search
+    seen = []
+
+    class MultiAdapter:
+        multi_device = True
+
+        @staticmethod
+        def plan(est, cands, X, y, fold_id, n_splits, device=None):
+            seen.append(device)
+            return OraclePlan(est, cands, X, y, fold_id, n_splits)
+
+    monkeypatch.setattr(base_search._est, "adapter_for", lambda est: MultiAdapter)
+    X, y = _iris()
+    grid = {'kernel': ('linear', 'rbf'), 'C': [1, 10, 100]}
+    monkeypatch.setattr(base_search._dist, "local_devices", lambda: [0])
+    single = GridSearchCV(None, svm.SVC(gamma='auto'), grid, cv=5).fit(X, y)
+    assert single.devices_ == [None] or len(single.devices_) == 1
+    for nd in (2, 3, 8):
+        del seen[:]
+        monkeypatch.setattr(base_search._dist, "local_devices", lambda nd=nd: list(range(nd)))
+        multi = GridSearchCV(None, svm.SVC(gamma='auto'), grid, cv=5).fit(X, y)
+        assert sorted(seen) == list(range(min(nd, 6))) and multi.devices_ == list(range(min(nd, 6)))
+        for k, v in single.cv_results_.items():
+            if "score" in k:
+                np.testing.assert_array_equal(np.asarray(v, float), np.asarray(multi.cv_results_[k], float), err_msg=k)
+        assert multi.best_params_ == single.best_params_
+        np.testing.assert_array_equal(multi.predict(X), single.predict(X))
 
 
 # ------------------------------------------------------------------ multi-rank (gloo, CPU) --------
@@ -381,6 +418,12 @@ def test_bench_weak_scaling_grids_keep_64_candidates_per_gpu():
         assert len(W.candidates(w)) == 64 * n
         g = w["param_grid"]
         assert min(g["gamma"]) == 1 / 4096 and max(g["gamma"]) == 1 / 256 and abs(max(g["C"]) - 10 ** 2.5) < 1e-9
-    idx, desc = bench.cpu_sample(W.candidates(bench.scaled_workload("c2", 1)), 5, 2)
-    assert len(idx) == 2 and "10 fits" in desc
+    # the CPU arm: one (candidate, fold) task per host core, candidates of about the grid's mean predicted cost
+    w = bench.scaled_workload("c2", 1)
+    cands = W.candidates(w)
+    for cores in (6, 16, 96):
+        idx, rel = bench.cpu_sample(w, cands, cores)
+        assert len(idx) == min(cores, 64) and len(set(idx)) == len(idx)
+        assert 0.7 <= rel <= 1.3 or cores >= 64                          # sample mean cost ~ grid mean cost
+    assert bench.scaled_workload("c2", 4)["golden"] == "c4_svc_rbf_16x16"    # the N=4 weak grid is config 4: parity asserted in-run
 

@@ -1,0 +1,21 @@
+"""Where does a GridSearchCV.fit() on config 2 spend its time?  (e2e vs resident gap)"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("B200GS_DEVICES", "1")
+import numpy as np
+from spark_sklearn_b200 import GridSearchCV, workloads as W
+from spark_sklearn_b200.estimators import get_engine
+w = W.make_workload("c2")
+est = W.make_estimator(w)
+for rep in range(4):
+    t0 = time.perf_counter()
+    s = GridSearchCV(None, est, w["param_grid"], cv=w["cv"], refit=False).fit(w["X"], w["y"])
+    dt = time.perf_counter() - t0
+    p = s.device_profile_
+    print("fit %d: wall %.1f ms | device total %.1f solve %.1f gram %.1f kmat %.1f score %.1f h2d %.1f" % (
+        rep, dt * 1e3, p["ms_total"], p["ms_solve"], p["ms_gram"], p["ms_kernel_matrix"], p["ms_score"], p["ms_h2d"]), flush=True)
+import cProfile, pstats
+pr = cProfile.Profile(); pr.enable()
+GridSearchCV(None, est, w["param_grid"], cv=w["cv"], refit=False).fit(w["X"], w["y"])
+pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
