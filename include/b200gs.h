@@ -57,6 +57,13 @@ int gs_create(int device, gs_handle **out);
 void gs_destroy(gs_handle *h);
 const char *gs_last_error(const gs_handle *h);      /* h may be NULL: last gs_create failure  */
 int gs_version(void);
+/* General CV splits.  Replaces: the per-task (train, test) index arrays of the reference (base_search.py:81-82,
+ * islice(cv.split(X, y, groups))) for splitters whose test sets overlap or whose training set is not the complement of the
+ * test set (ShuffleSplit, RepeatedKFold, PredefinedSplit with -1).  Call after gs_set_data (whose fold ids may all be -1).
+ * test_mask / train_mask: [n][2] uint64, bit k of word k/64 = row belongs to the test / training set of split k; a row may be
+ * in neither.  gs_svc and gs_logreg honour the masks; gs_ridge needs gs_set_data's fold partition. */
+int gs_set_splits(gs_handle *h, const uint64_t *test_mask, const uint64_t *train_mask, int32_t n_splits);
+
 /* Scorer of the following gs_svc / gs_logreg / gs_ridge calls.  Replaces: check_scoring(estimator, scoring) and the scorer
  * call inside _fit_and_score (reference base_search.py:43,83-87; grid_search.py:212-214 `scoring=`).  The score is
  * computed on the device from the decision values / Gram statistics already in HBM.  pos_class: class id (index into the

@@ -83,7 +83,7 @@ class B200BaseSearchCV(BaseSearchCV):
                 % (self.scoring, type(estimator).__name__, sorted(k for k in getattr(adapter, "scorers", {}) if k)))
         X_arr = np.asarray(X)
         y_arr = None if y is None else np.asarray(y)
-        fold_id = _est.fold_ids_from_splits(splits, len(X_arr))
+        fold_id = _est.Folds(splits, len(X_arr))               # fold ids for partition splitters, split masks otherwise
 
         # ---- the fan-out: every (candidate, fold) task in one engine call per GPU ----
         devices = _dist.local_devices() if (world == 1 and getattr(adapter, "multi_device", False)) else [None]

@@ -168,7 +168,7 @@ void gs_destroy(gs_handle *h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
-    h->dX.release(); h->dY.release(); h->dFold.release(); h->dYt.release();
+    h->dX.release(); h->dY.release(); h->dFold.release(); h->dYt.release(); h->dTe.release(); h->dTr.release();
     h->dS.release(); h->dXsq.release(); h->dK.release(); h->dX64.release();
     h->evp.release(); h->dScore.release();
     for (auto &w : h->dWork) w.release();
@@ -182,6 +182,7 @@ int gs_set_data(gs_handle *h, const void *X, int32_t x_dtype, int64_t n, int64_t
                 const float *y_target, const int8_t *fold_id, int32_t n_splits)
 {
     if (!h) return GS_ERR_ARG;
+    if (n_splits > 127) { if (h) gs_set_error(h, "gs_set_data: more than 127 CV splits"); return GS_ERR_UNSUPPORTED; }
     if (!X || n <= 0 || d <= 0 || !fold_id || n_splits < 1 || (!y_class && !y_target) ||
         (x_dtype != GS_F32 && x_dtype != GS_F64)) {
         gs_set_error(h, "gs_set_data: bad arguments"); return GS_ERR_ARG;
@@ -218,6 +219,12 @@ int gs_set_data(gs_handle *h, const void *X, int32_t x_dtype, int64_t n, int64_t
         if (fold_id[o] >= n_splits) { gs_set_error(h, "gs_set_data: fold id >= n_splits"); return GS_ERR_ARG; }
     }
     for (int c = 0; c < h->n_classes; c++) h->class_start[c + 1] += h->class_start[c];
+    // split membership from the fold ids: row r is tested by split fold[r] and trains every other split
+    h->partition = true;
+    h->te_mask.assign((size_t)n * 2, 0); h->tr_mask.assign((size_t)n * 2, 0);
+    for (int64_t i = 0; i < n; i++)
+        for (int k = 0; k < n_splits; k++)
+            (h->fold[i] == k ? h->te_mask : h->tr_mask)[(size_t)i * 2 + (k >> 6)] |= 1ull << (k & 63);
 
     h->evp.reset();
     cudaEvent_t e0 = h->evp.get(), e1 = h->evp.get();
@@ -229,6 +236,7 @@ int gs_set_data(gs_handle *h, const void *X, int32_t x_dtype, int64_t n, int64_t
     GS_CUDA(h->dWork[1].reserve((size_t)n * 4));
     GS_CUDA(h->dY.reserve((size_t)n * 4));
     GS_CUDA(h->dFold.reserve((size_t)n));
+    GS_CUDA(h->dTe.reserve((size_t)n * 16)); GS_CUDA(h->dTr.reserve((size_t)n * 16));
     GS_CUDA(h->dYt.reserve((size_t)n * 4));
     GS_CUDA(cudaMemcpyAsync(h->dWork[0].p, X, (size_t)n * d * esz, cudaMemcpyHostToDevice, h->stream));
     GS_CUDA(cudaMemcpyAsync(h->dWork[1].p, h->perm.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
@@ -241,6 +249,8 @@ int gs_set_data(gs_handle *h, const void *X, int32_t x_dtype, int64_t n, int64_t
     GS_CUDA(cudaGetLastError());
     GS_CUDA(cudaMemcpyAsync(h->dY.p, h->yc.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
     GS_CUDA(cudaMemcpyAsync(h->dFold.p, h->fold.data(), (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    GS_CUDA(cudaMemcpyAsync(h->dTe.p, h->te_mask.data(), (size_t)n * 16, cudaMemcpyHostToDevice, h->stream));
+    GS_CUDA(cudaMemcpyAsync(h->dTr.p, h->tr_mask.data(), (size_t)n * 16, cudaMemcpyHostToDevice, h->stream));
     if (y_target) {
         std::vector<float> yt(n);
         for (int64_t i = 0; i < n; i++) yt[i] = y_target[h->perm[i]];
@@ -251,6 +261,30 @@ int gs_set_data(gs_handle *h, const void *X, int32_t x_dtype, int64_t n, int64_t
     GS_CUDA(cudaStreamSynchronize(h->stream));
     cudaEventElapsedTime(&h->prof.ms_h2d, e0, e1);
     h->prof.h2d_bytes = (int64_t)n * d * (int64_t)esz + n * 9;
+    return GS_OK;
+}
+
+int gs_set_splits(gs_handle *h, const uint64_t *test_mask, const uint64_t *train_mask, int32_t n_splits)
+{
+    if (!h) return GS_ERR_ARG;
+    if (h->n == 0) { gs_set_error(h, "gs_set_splits: no dataset (call gs_set_data first)"); return GS_ERR_NO_DATA; }
+    if (!test_mask || !train_mask || n_splits < 1 || n_splits > 128) { gs_set_error(h, "gs_set_splits: bad arguments (1..128 splits)"); return GS_ERR_ARG; }
+    GS_CUDA(cudaSetDevice(h->device));
+    const int64_t n = h->n;
+    for (int64_t i = 0; i < n; i++) {
+        const int o = h->perm[i];
+        for (int wd = 0; wd < 2; wd++) {
+            const uint64_t te = test_mask[(size_t)o * 2 + wd], tr = train_mask[(size_t)o * 2 + wd];
+            if (te & tr) { gs_set_error(h, "gs_set_splits: a row is in both the training and the test set of a split"); return GS_ERR_ARG; }
+            h->te_mask[(size_t)i * 2 + wd] = te; h->tr_mask[(size_t)i * 2 + wd] = tr;
+        }
+    }
+    h->n_splits = n_splits;
+    h->partition = false;                                    // fold-block algorithms (Ridge) need gs_set_data's fold ids
+    GS_CUDA(cudaMemcpyAsync(h->dTe.p, h->te_mask.data(), (size_t)n * 16, cudaMemcpyHostToDevice, h->stream));
+    GS_CUDA(cudaMemcpyAsync(h->dTr.p, h->tr_mask.data(), (size_t)n * 16, cudaMemcpyHostToDevice, h->stream));
+    GS_CUDA(cudaStreamSynchronize(h->stream));
+    h->prof.h2d_bytes += n * 32;
     return GS_OK;
 }
 
@@ -379,7 +413,7 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
         TcBatch hb{0, 0, 0, dpad, bs.as<float>(), ld32};
         GS_CUDA(cudaMemcpyAsync(bb.p, &hb, sizeof hb, cudaMemcpyHostToDevice, st));
         h->tt.begin(h->evp, st);
-        GS_CUDA(launch_gemm_nt_tf32x3(mh, ml, mh, ml, bb.as<TcBatch>(), 1, n, n, 1.0f, false, st));
+        GS_CUDA(launch_gemm_nt_tf32x3(mh, ml, mh, ml, bb.as<TcBatch>(), 1, n, n, 1.0f, false, st, true));
         h->tt.end(h->evp, st, 3.0 * 2.0 * n * (double)n * dpad);
         GS_CUDA(launch_widen_gram(bs.as<float>(), n, ld32, h->dS.as<double>(), h->dXsq.as<double>(), st));
         pf.launches += 3;
@@ -402,10 +436,10 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
                 const size_t s = (size_t)k * n_pairs + p;
                 sp_off[s] = (int)rows_all.size();
                 for (int r = h->class_start[a]; r < h->class_start[a + 1]; r++)
-                    if (refit || h->fold[r] != k) rows_all.push_back(r);
+                    if (refit || h->is_train(r, k)) rows_all.push_back(r);
                 sp_npos[s] = (int)rows_all.size() - sp_off[s];
                 for (int r = h->class_start[b]; r < h->class_start[b + 1]; r++)
-                    if (refit || h->fold[r] != k) rows_all.push_back(r);
+                    if (refit || h->is_train(r, k)) rows_all.push_back(r);
                 const int l = (int)rows_all.size() - sp_off[s];
                 if (sp_npos[s] == 0 || sp_npos[s] == l) {
                     gs_set_error(h, "gs_svc: a training fold lacks one of the classes"); return GS_ERR_ARG;
@@ -694,7 +728,7 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
             }
             const int kind = h->score_kind, nvt = (int)vtasks.size();
             if (kind == GS_SCORE_DEFAULT) {
-                GS_CUDA(launch_vote(h->dWork[4].as<double>(), d_rho, n, nc, h->dY.as<int>(), h->dFold.as<signed char>(),
+                GS_CUDA(launch_vote(h->dWork[4].as<double>(), d_rho, n, nc, h->dY.as<int>(), h->masks(),
                                     d_vt, nvt, d_counts, st));
             } else if (kind == GS_SCORE_ROC_AUC) {
                 // rank statistic of the decision values already in HBM (scikit-learn: roc_auc_score(y, decision_function(X)))
@@ -705,14 +739,14 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
                 int *d_meta = (int *)(d_auc + (size_t)nvt * 4);
                 GS_CUDA(cudaMemcpyAsync(d_meta, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice, st));
                 GS_CUDA(cudaMemsetAsync(d_auc, 0, (size_t)nvt * 32, st));
-                GS_CUDA(launch_auc_pairs_f64(h->dWork[4].as<double>(), n, n, h->class_start[1], h->dFold.as<signed char>(), d_meta, d_meta + nvt,
+                GS_CUDA(launch_auc_pairs_f64(h->dWork[4].as<double>(), n, n, h->class_start[1], h->masks(), d_meta, d_meta + nvt,
                                              nvt, -1, d_auc, st));
                 score_raw.resize((size_t)nvt * 4);
                 GS_CUDA(cudaMemcpyAsync(score_raw.data(), d_auc, (size_t)nvt * 32, cudaMemcpyDeviceToHost, st));
             } else {
                 GS_CUDA(h->dScore.reserve((size_t)nvt * 2 * nc * 3 * 4));
                 GS_CUDA(cudaMemsetAsync(h->dScore.p, 0, (size_t)nvt * 2 * nc * 3 * 4, st));
-                GS_CUDA(launch_vote_classes(h->dWork[4].as<double>(), d_rho, n, nc, h->dY.as<int>(), h->dFold.as<signed char>(),
+                GS_CUDA(launch_vote_classes(h->dWork[4].as<double>(), d_rho, n, nc, h->dY.as<int>(), h->masks(),
                                             d_vt, nvt, h->dScore.as<int>(), st));
                 class_counts.resize((size_t)nvt * 2 * nc * 3);
                 GS_CUDA(cudaMemcpyAsync(class_counts.data(), h->dScore.p, class_counts.size() * 4, cudaMemcpyDeviceToHost, st));
@@ -765,8 +799,9 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
                 const int k = vtasks[v].fold;
                 double na_te = 0, nb_te = 0, na_tr = 0, nb_tr = 0;            // rows of the first / second class inside / outside fold k
                 for (int r = 0; r < n; r++) {
-                    const bool b = r >= h->class_start[1], te = h->fold[r] == k;
-                    (te ? (b ? nb_te : na_te) : (b ? nb_tr : na_tr)) += 1;
+                    const bool b = r >= h->class_start[1];
+                    if (h->is_test(r, k)) (b ? nb_te : na_te) += 1;
+                    else if (h->is_train(r, k)) (b ? nb_tr : na_tr) += 1;
                 }
                 const unsigned long long *a = &score_raw[v * 4];
                 task_score[(size_t)vtask_id[v] * 2 + 0] = na_te * nb_te > 0 ? ((double)a[0] + 0.5 * (double)a[1]) / (na_te * nb_te) : NAN;

@@ -68,6 +68,23 @@ struct TensorTimer {
     }
 };
 
+// Membership of every row in the training / test set of every CV split: two 64-bit words per row and kind (splits 0..127).
+// Replaces the per-task index arrays of the reference (base_search.py:81-82 islice(cv.split(...))): any splitter fits --
+// overlapping test sets (RepeatedKFold), rows in neither set (ShuffleSplit), rows that only ever train (PredefinedSplit -1).
+struct SplitMasks {
+    const unsigned long long *te, *tr;
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ bool split_test(const SplitMasks &m, int r, int k)      // k < 0 (refit): nobody is tested
+{
+    return k >= 0 && ((m.te[(size_t)r * 2 + (k >> 6)] >> (k & 63)) & 1ull);
+}
+__device__ __forceinline__ bool split_train(const SplitMasks &m, int r, int k)     // k < 0 (refit): every row trains
+{
+    return k < 0 || ((m.tr[(size_t)r * 2 + (k >> 6)] >> (k & 63)) & 1ull);
+}
+#endif
+
 struct gs_handle {
     int device = 0;
     int sm_count = 148;
@@ -81,9 +98,15 @@ struct gs_handle {
     bool classification = false;
     std::vector<int32_t> perm;        // internal row -> original row
     std::vector<int32_t> yc;          // [n] class ids, internal order
-    std::vector<int8_t> fold;         // [n] fold ids, internal order
+    std::vector<int8_t> fold;         // [n] fold ids, internal order (partition splitters; Ridge's fold blocks)
+    std::vector<uint64_t> te_mask, tr_mask;   // [n][2] split membership, internal order
+    bool partition = true;            // the splits are a partition into test folds whose complements train (gs_set_data's fold ids)
+    bool is_test(int r, int k) const { return k >= 0 && ((te_mask[(size_t)r * 2 + (k >> 6)] >> (k & 63)) & 1ull); }
+    bool is_train(int r, int k) const { return k < 0 || ((tr_mask[(size_t)r * 2 + (k >> 6)] >> (k & 63)) & 1ull); }
+    SplitMasks masks() const { return SplitMasks{dTe.as<unsigned long long>(), dTr.as<unsigned long long>()}; }
     std::vector<int32_t> class_start; // [n_classes+1] internal row ranges per class
     DevBuf dX, dY, dFold, dYt;        // float X[n][d], int32 y[n], int8 fold[n], float yt[n]
+    DevBuf dTe, dTr;                  // uint64 [n][2] test / training membership of every split
     DevBuf dX64;                      // double X[n][d] when the caller's matrix is float64
     int x_dtype = GS_F32;
     DevBuf dS, dXsq;                  // float64 Gram [n][n], squared norms [n]
@@ -154,17 +177,17 @@ struct VoteTask {          // one (candidate, fold) task
 };
 // counts[task][0..3] = {test correct, test total, train correct, train total}
 cudaError_t launch_vote(const double *dec, const double *rho, int n, int n_classes, const int *y,
-                        const signed char *fold, const VoteTask *tasks, int n_tasks, int *counts,
+                        SplitMasks sm, const VoteTask *tasks, int n_tasks, int *counts,
                         cudaStream_t st);
 
 // per-class counts for the count-based scorers: counts[task][split (0 test, 1 train)][class][3 = support, tp, predicted]
 cudaError_t launch_vote_classes(const double *dec, const double *rho, int n, int n_classes, const int *y,
-                                const signed char *fold, const VoteTask *tasks, int n_tasks, int *counts, cudaStream_t st);
+                                SplitMasks sm, const VoteTask *tasks, int n_tasks, int *counts, cudaStream_t st);
 // ROC-AUC pair counts of binary tasks: out[task][4] = {test wins, test ties, train wins, train ties}; rows are class-sorted
 // (negative class = rows [0, n_a)); score row of task t = score + col_of_task[t] * ld; sign -1 for libsvm decision values
-cudaError_t launch_auc_pairs_f64(const double *score, int64_t ld, int n, int n_a, const signed char *fold, const int *col_of_task,
+cudaError_t launch_auc_pairs_f64(const double *score, int64_t ld, int n, int n_a, SplitMasks sm, const int *col_of_task,
                                  const int *fold_of_task, int n_tasks, int sign, unsigned long long *out, cudaStream_t st);
-cudaError_t launch_auc_pairs_f32(const float *score, int64_t ld, int n, int n_a, const signed char *fold, const int *col_of_task,
+cudaError_t launch_auc_pairs_f32(const float *score, int64_t ld, int n, int n_a, SplitMasks sm, const int *col_of_task,
                                  const int *fold_of_task, int n_tasks, int sign, unsigned long long *out, cudaStream_t st);
 // score of one (task, split) from the class counts cnt[class][3] (float64, scikit-learn's formulas); NaN when undefined
 double gs_score_from_counts(int kind, int pos_class, int n_classes, const int *cnt);
@@ -181,6 +204,8 @@ cudaError_t tc_make_map(TcMap *out, const float *base, int64_t rows, int64_t col
 cudaError_t launch_split_tf32(const float *x, float *hi, float *lo, size_t n, cudaStream_t st);
 constexpr int TC_KCHUNK = 512;   // longest accumulation chain kept inside the (truncating) TMEM accumulator
 cudaError_t launch_sum_partials(const float *partial, int n_chunks, int64_t per, float *out, cudaStream_t st);
+// symmetric: the A and B operands are the same matrix (M == N): tiles below the diagonal are not computed, their values are
+// stored as transposes of the tiles above it (bitwise symmetric result)
 cudaError_t launch_gemm_nt_tf32x3(const TcMap &a_hi, const TcMap &a_lo, const TcMap &b_hi, const TcMap &b_lo,
                                   const TcBatch *d_batches, int n_batches, int M, int N, float alpha, bool accumulate,
-                                  cudaStream_t st);
+                                  cudaStream_t st, bool symmetric = false);

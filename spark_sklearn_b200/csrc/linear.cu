@@ -281,6 +281,11 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     if (h->n == 0) { gs_set_error(h, "gs_ridge: no dataset (call gs_set_data first)"); return GS_ERR_NO_DATA; }
     if (h->classification) { gs_set_error(h, "gs_ridge: dataset has no regression targets"); return GS_ERR_ARG; }
     if (n_cand <= 0 || !alpha) { gs_set_error(h, "gs_ridge: bad arguments"); return GS_ERR_ARG; }
+    if (!refit && !h->partition) {
+        gs_set_error(h, "gs_ridge: the fold-Gram algorithm needs a partition of the rows into test folds (gs_set_data fold ids); "
+                        "general splits (gs_set_splits) are supported by gs_svc and gs_logreg");
+        return GS_ERR_UNSUPPORTED;
+    }
     for (int c = 0; c < n_cand; c++)
         if (!(alpha[c] >= 0)) { gs_set_error(h, "gs_ridge: alpha must be >= 0"); return GS_ERR_ARG; }
     if (h->score_kind != GS_SCORE_DEFAULT && h->score_kind != GS_SCORE_NEG_MSE && h->score_kind != GS_SCORE_NEG_RMSE) {
@@ -381,8 +386,8 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     GS_CUDA(tc_make_map(&mzh, bZh.as<float>(), Dp, ldz, ldz));
     GS_CUDA(tc_make_map(&mzl, bZl.as<float>(), Dp, ldz, ldz));
     h->tt.begin(h->evp, st);
-    GS_CUDA(launch_gemm_nt_tf32x3(mzh, mzl, mzh, mzl, dBatchG, nq, D, D, 1.0f, false, st));
-    h->tt.end(h->evp, st, 3.0 * 2.0 * (double)D * D * (double)ldz);
+    GS_CUDA(launch_gemm_nt_tf32x3(mzh, mzl, mzh, mzl, dBatchG, nq, D, D, 1.0f, false, st, true));   // Gram: upper tiles + mirror
+    h->tt.end(h->evp, st, 3.0 * 2.0 * (double)D * D * (double)ldz * (((D + 127) / 128 + 1) / (2.0 * ((D + 127) / 128))));   // tiles on/above the diagonal
     sum_grams_kernel<<<592, 256, 0, st>>>(dGq, dQs, nb, (int64_t)Dp * Dp, bG.as<float>(), dT);
     GS_CUDA(cudaGetLastError());
     launches += 5;
@@ -529,7 +534,7 @@ int gs_debug_gemm_nt(gs_handle *h, const float *A, int32_t M, const float *B, in
     GS_CUDA(tc_make_map(&mbh, bh.as<float>(), N, Kp, Kp)); GS_CUDA(tc_make_map(&mbl, bl.as<float>(), N, Kp, Kp));
     TcBatch hb{0, 0, 0, Kp, c.as<float>(), (int64_t)N};
     GS_CUDA(cudaMemcpyAsync(bt.p, &hb, sizeof hb, cudaMemcpyHostToDevice, st));
-    GS_CUDA(launch_gemm_nt_tf32x3(mah, mal, mbh, mbl, bt.as<TcBatch>(), 1, M, N, 1.0f, false, st));
+    GS_CUDA(launch_gemm_nt_tf32x3(mah, mal, mbh, mbl, bt.as<TcBatch>(), 1, M, N, 1.0f, false, st, A == B && M == N));   // same matrix: Gram mode
     GS_CUDA(cudaMemcpyAsync(C, c.p, (size_t)M * N * 4, cudaMemcpyDeviceToHost, st));
     GS_CUDA(cudaStreamSynchronize(st));
     a.release(); ah.release(); al.release(); b.release(); bh.release(); bl.release(); c.release(); bt.release();

@@ -327,7 +327,7 @@ __global__ void lbfgs_export_kernel(const double *__restrict__ Vall, int ncol, i
 // Element-wise pass over Z^T [ncol][ldz]: loss, masked residual (hi/lo split), per-column loss sum.
 // column c trains on rows whose fold id != fold_of_col[c] (or on all rows when fold_of_col[c] < 0).
 __global__ void logistic_residual_kernel(const float *__restrict__ Zt, int64_t ldz, int n, const int *__restrict__ y,
-                                         const signed char *__restrict__ fold, const int *__restrict__ fold_of_col,
+                                         SplitMasks sm, const int *__restrict__ fold_of_col,
                                          const double *__restrict__ inv_ntrain, LbScalars *__restrict__ Sc,
                                          float *__restrict__ Rh, float *__restrict__ Rl)
 {
@@ -339,7 +339,7 @@ __global__ void logistic_residual_kernel(const float *__restrict__ Zt, int64_t l
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const size_t idx = (size_t)c * ldz + i;
         float rres = 0.f;
-        if (fold[i] != fc) {
+        if (split_train(sm, i, fc)) {
             const float z = Zt[idx];
             const float yi = (float)y[i];
             // half binomial loss log(1+e^z) - y z, evaluated the numerically stable way
@@ -365,14 +365,15 @@ __global__ void logistic_residual_kernel(const float *__restrict__ Zt, int64_t l
 
 // accuracy counts: z > 0 -> class 1
 __global__ void logistic_count_kernel(const float *__restrict__ Zt, int64_t ldz, int n, const int *__restrict__ y,
-                                      const signed char *__restrict__ fold, const int *__restrict__ fold_of_col, int *__restrict__ counts)
+                                      SplitMasks sm, const int *__restrict__ fold_of_col, int *__restrict__ counts)
 {
     const int c = blockIdx.y, fc = fold_of_col[c];
     int cte = 0, nte = 0, ctr = 0, ntr = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int pred = Zt[(size_t)c * ldz + i] > 0.f ? 1 : 0;
         const bool ok = pred == y[i];
-        if (fold[i] == fc) { nte++; cte += ok; } else { ntr++; ctr += ok; }
+        if (split_test(sm, i, fc)) { nte++; cte += ok; }
+        if (split_train(sm, i, fc)) { ntr++; ctr += ok; }
     }
 #pragma unroll
     for (int m = 16; m; m >>= 1) {
@@ -387,7 +388,7 @@ __global__ void logistic_count_kernel(const float *__restrict__ Zt, int64_t ldz,
 
 // per-class counts for the count-based scorers: counts[col][split (0 test, 1 train)][class (0, 1)][3 = support, tp, predicted]
 __global__ void logistic_classes_kernel(const float *__restrict__ Zt, int64_t ldz, int n, const int *__restrict__ y,
-                                        const signed char *__restrict__ fold, const int *__restrict__ fold_of_col, int *__restrict__ counts)
+                                        SplitMasks sm, const int *__restrict__ fold_of_col, int *__restrict__ counts)
 {
     __shared__ int sh[12];
     if (threadIdx.x < 12) sh[threadIdx.x] = 0;
@@ -395,7 +396,8 @@ __global__ void logistic_classes_kernel(const float *__restrict__ Zt, int64_t ld
     const int c = blockIdx.y, fc = fold_of_col[c];
     int loc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int pred = Zt[(size_t)c * ldz + i] > 0.f ? 1 : 0, yc = y[i], sp = fold[i] == fc ? 0 : 1;
+        const int pred = Zt[(size_t)c * ldz + i] > 0.f ? 1 : 0, yc = y[i];
+        const int sp = split_test(sm, i, fc) ? 0 : (split_train(sm, i, fc) ? 1 : 2);     // 2: in neither set
 #pragma unroll
         for (int q = 0; q < 4; q++) {                                   // (split, class) = q
             const int qs = q >> 1, qc = q & 1;
@@ -481,15 +483,15 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
     TcBatch *dBatch = reinterpret_cast<TcBatch *>(((uintptr_t)mp + 15) & ~(uintptr_t)15);
 
     // per-column constants
-    std::vector<int> cnt(std::max(ns, 1), 0);
-    if (!refit) for (int i = 0; i < n; i++) if (h->fold[i] >= 0) cnt[h->fold[i]]++;
+    std::vector<int> ntrain(std::max(ns, 1), 0);                           // training rows of every split
+    if (!refit) for (int k = 0; k < ns; k++) for (int i = 0; i < n; i++) ntrain[k] += h->is_train(i, k) ? 1 : 0;
     std::vector<LbScalars> hs(ncol);
     std::vector<double> inv(ncol);
     std::vector<int> foldof(ncol);
     for (int c = 0; c < n_cand; c++)
         for (int k = 0; k < ns; k++) {
             const int col = c * ns + k;
-            const int ntr = refit ? n : n - cnt[k];
+            const int ntr = refit ? n : ntrain[k];
             memset(&hs[col], 0, sizeof(LbScalars));
             hs[col].task = T_FG_START; hs[col].theta = 1.0; hs[col].fresh = 1;
             hs[col].l2 = 1.0 / (Cv[c] * (double)ntr);
@@ -533,7 +535,7 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
         GS_CUDA(launch_gemm_nt_tf32x3(mWh, mWl, mXh, mXl, dBatch, 1, ncol, n, 1.0f, false, st));
         h->tt.end(h->evp, st, 3.0 * 2.0 * (double)ncol * n * nvp);
         dim3 grid(64, ncol);
-        logistic_residual_kernel<<<grid, 256, 0, st>>>(dZ, npad, n, h->dY.as<int>(), h->dFold.as<signed char>(), dFoldOf, dInv, dS, dRh, dRl);
+        logistic_residual_kernel<<<grid, 256, 0, st>>>(dZ, npad, n, h->dY.as<int>(), h->masks(), dFoldOf, dInv, dS, dRh, dRl);
         GS_CUDA(cudaGetLastError());
         h->tt.begin(h->evp, st);
         GS_CUDA(launch_gemm_nt_tf32x3(mRh, mRl, mXth, mXtl, dBatch + 1, nchunk, ncol, nv, 1.0f, false, st));
@@ -561,7 +563,7 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
         h->tt.end(h->evp, st, 3.0 * 2.0 * (double)ncol * n * nvp);
         GS_CUDA(cudaMemsetAsync(dCounts, 0, (size_t)ncol * 16, st));
         dim3 grid(64, ncol);
-        logistic_count_kernel<<<grid, 256, 0, st>>>(dZ, npad, n, h->dY.as<int>(), h->dFold.as<signed char>(), dFoldOf, dCounts);
+        logistic_count_kernel<<<grid, 256, 0, st>>>(dZ, npad, n, h->dY.as<int>(), h->masks(), dFoldOf, dCounts);
         GS_CUDA(cudaGetLastError());
         launches += 3;
         std::vector<int> counts((size_t)ncol * 4);
@@ -578,14 +580,14 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
             int *d_meta = (int *)(d_auc + (size_t)ncol * 4);
             GS_CUDA(cudaMemcpyAsync(d_meta, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice, st));
             GS_CUDA(cudaMemsetAsync(d_auc, 0, (size_t)ncol * 32, st));
-            GS_CUDA(launch_auc_pairs_f32(dZ, npad, n, h->class_start[1], h->dFold.as<signed char>(), d_meta, d_meta + ncol, ncol, +1, d_auc, st));
+            GS_CUDA(launch_auc_pairs_f32(dZ, npad, n, h->class_start[1], h->masks(), d_meta, d_meta + ncol, ncol, +1, d_auc, st));
             araw.resize((size_t)ncol * 4);
             GS_CUDA(cudaMemcpyAsync(araw.data(), d_auc, (size_t)ncol * 32, cudaMemcpyDeviceToHost, st));
             launches++;
         } else if (kind != GS_SCORE_DEFAULT) {
             GS_CUDA(h->dScore.reserve((size_t)ncol * 48));
             GS_CUDA(cudaMemsetAsync(h->dScore.p, 0, (size_t)ncol * 48, st));
-            logistic_classes_kernel<<<grid, 256, 0, st>>>(dZ, npad, n, h->dY.as<int>(), h->dFold.as<signed char>(), dFoldOf, h->dScore.as<int>());
+            logistic_classes_kernel<<<grid, 256, 0, st>>>(dZ, npad, n, h->dY.as<int>(), h->masks(), dFoldOf, h->dScore.as<int>());
             GS_CUDA(cudaGetLastError());
             ccounts.resize((size_t)ncol * 12);
             GS_CUDA(cudaMemcpyAsync(ccounts.data(), h->dScore.p, ccounts.size() * 4, cudaMemcpyDeviceToHost, st));
@@ -602,8 +604,9 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
                 const int k = col % ns;
                 double na_te = 0, nb_te = 0, na_tr = 0, nb_tr = 0;
                 for (int r = 0; r < n; r++) {
-                    const bool b = r >= h->class_start[1], te = h->fold[r] == k;
-                    (te ? (b ? nb_te : na_te) : (b ? nb_tr : na_tr)) += 1;
+                    const bool b = r >= h->class_start[1];
+                    if (h->is_test(r, k)) (b ? nb_te : na_te) += 1;
+                    else if (h->is_train(r, k)) (b ? nb_tr : na_tr) += 1;
                 }
                 const unsigned long long *a = &araw[(size_t)col * 4];
                 test_scores[col] = na_te * nb_te > 0 ? ((double)a[0] + 0.5 * (double)a[1]) / (na_te * nb_te) : NAN;

@@ -102,7 +102,7 @@ __global__ void sum_slabs_kernel(const double *__restrict__ part, size_t count, 
 // higher; first maximum wins.  Accuracy counts split by fold membership.
 __global__ void __launch_bounds__(256)
 vote_kernel(const double *__restrict__ dec, const double *__restrict__ rho, int n, int n_classes,
-            const int *__restrict__ y, const signed char *__restrict__ fold,
+            const int *__restrict__ y, SplitMasks sm,
             const VoteTask *__restrict__ tasks, int *__restrict__ counts)
 {
     const VoteTask T = tasks[blockIdx.y];
@@ -126,7 +126,8 @@ vote_kernel(const double *__restrict__ dec, const double *__restrict__ rho, int 
             for (int c = 1; c < n_classes; c++) if (votes[c] > votes[pred]) pred = c;
         }
         const bool ok = pred == y[r];
-        if (fold[r] == T.fold) { n_te = 1; c_te = ok; } else { n_tr = 1; c_tr = ok; }
+        if (split_test(sm, r, T.fold)) { n_te = 1; c_te = ok; }
+        if (split_train(sm, r, T.fold)) { n_tr = 1; c_tr = ok; }
     }
     // block reduce the four counters
     __shared__ int sh[4][8];
@@ -151,7 +152,7 @@ vote_kernel(const double *__restrict__ dec, const double *__restrict__ rho, int 
 // counts[task][split][class][3]; block-level shared-memory accumulation, one global atomic per non-zero cell.
 __global__ void __launch_bounds__(256)
 vote_classes_kernel(const double *__restrict__ dec, const double *__restrict__ rho, int n, int n_classes,
-                    const int *__restrict__ y, const signed char *__restrict__ fold,
+                    const int *__restrict__ y, SplitMasks sm,
                     const VoteTask *__restrict__ tasks, int *__restrict__ counts)
 {
     __shared__ int sh[2 * 32 * 3];
@@ -176,10 +177,15 @@ vote_classes_kernel(const double *__restrict__ dec, const double *__restrict__ r
             pred = 0;
             for (int c = 1; c < n_classes; c++) if (votes[c] > votes[pred]) pred = c;
         }
-        const int sp = fold[r] == T.fold ? 0 : 1, yc = y[r];
-        atomicAdd(&sh[(sp * n_classes + yc) * 3 + 0], 1);
-        if (pred == yc) atomicAdd(&sh[(sp * n_classes + yc) * 3 + 1], 1);
-        atomicAdd(&sh[(sp * n_classes + pred) * 3 + 2], 1);
+        const int yc = y[r];
+#pragma unroll
+        for (int sp = 0; sp < 2; sp++) {
+            if (sp == 0 ? split_test(sm, r, T.fold) : split_train(sm, r, T.fold)) {
+                atomicAdd(&sh[(sp * n_classes + yc) * 3 + 0], 1);
+                if (pred == yc) atomicAdd(&sh[(sp * n_classes + yc) * 3 + 1], 1);
+                atomicAdd(&sh[(sp * n_classes + pred) * 3 + 2], 1);
+            }
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * n_classes * 3; i += blockDim.x)
@@ -194,7 +200,7 @@ vote_classes_kernel(const double *__restrict__ dec, const double *__restrict__ r
 // the FIRST class, svm.cpp:2862; scikit-learn negates it for its binary decision_function).
 template <typename T>
 __global__ void __launch_bounds__(256)
-auc_pairs_kernel(const T *__restrict__ score, int64_t ld, int n, int n_a, const signed char *__restrict__ fold,
+auc_pairs_kernel(const T *__restrict__ score, int64_t ld, int n, int n_a, SplitMasks sm,
                  const int *__restrict__ col_of_task, const int *__restrict__ fold_of_task, int sign,
                  unsigned long long *__restrict__ out)
 {
@@ -206,22 +212,21 @@ auc_pairs_kernel(const T *__restrict__ score, int64_t ld, int n, int n_a, const 
     const int p = n_a + blockIdx.x * blockDim.x + threadIdx.x;
     const bool has = p < n;
     const T sp = has ? (sign > 0 ? sc[p] : -sc[p]) : T(0);
-    const bool p_test = has && fold[p] == k;
+    const int p_st = !has ? 2 : (split_test(sm, p, k) ? 1 : (split_train(sm, p, k) ? 0 : 2));     // 1 test, 0 training, 2 neither
     unsigned w_te = 0, t_te = 0, w_tr = 0, t_tr = 0;
     if (threadIdx.x < 4) red[threadIdx.x] = 0ull;
     for (int q0 = 0; q0 < n_a; q0 += 256) {
         __syncthreads();
         const int q = q0 + threadIdx.x;
         s_a[threadIdx.x] = q < n_a ? (sign > 0 ? sc[q] : -sc[q]) : T(0);
-        f_a[threadIdx.x] = q < n_a ? (fold[q] == k ? 1 : 0) : (signed char)2;          // 2: no row
+        f_a[threadIdx.x] = q < n_a ? (split_test(sm, q, k) ? 1 : (split_train(sm, q, k) ? 0 : 2)) : (signed char)2;   // 2: no row / neither set
         __syncthreads();
-        if (has) {
+        if (p_st != 2) {
             const int lim = min(256, n_a - q0);
             for (int j = 0; j < lim; j++) {
-                const bool q_test = f_a[j] == 1;
-                if (q_test == p_test) {                                                  // both test rows or both training rows
+                if (f_a[j] == p_st) {                                                    // both test rows or both training rows
                     const unsigned win = sp > s_a[j], tie = sp == s_a[j];
-                    if (p_test) { w_te += win; t_te += tie; } else { w_tr += win; t_tr += tie; }
+                    if (p_st == 1) { w_te += win; t_te += tie; } else { w_tr += win; t_tr += tie; }
                 }
             }
         }
@@ -241,37 +246,37 @@ auc_pairs_kernel(const T *__restrict__ score, int64_t ld, int n, int n_a, const 
 }  // namespace
 
 cudaError_t launch_vote_classes(const double *dec, const double *rho, int n, int n_classes, const int *y,
-                                const signed char *fold, const VoteTask *tasks, int n_tasks, int *counts, cudaStream_t st)
+                                SplitMasks sm, const VoteTask *tasks, int n_tasks, int *counts, cudaStream_t st)
 {
     if (n_tasks <= 0) return cudaSuccess;
     for (int t0 = 0; t0 < n_tasks; t0 += 32768) {                     // gridDim.y <= 65535
         const int nt = std::min(32768, n_tasks - t0);
         dim3 grid((n + 255) / 256, nt);
-        vote_classes_kernel<<<grid, 256, 0, st>>>(dec, rho, n, n_classes, y, fold, tasks + t0, counts + (size_t)t0 * 2 * n_classes * 3);
+        vote_classes_kernel<<<grid, 256, 0, st>>>(dec, rho, n, n_classes, y, sm, tasks + t0, counts + (size_t)t0 * 2 * n_classes * 3);
     }
     return cudaGetLastError();
 }
 
-cudaError_t launch_auc_pairs_f64(const double *score, int64_t ld, int n, int n_a, const signed char *fold, const int *col_of_task,
+cudaError_t launch_auc_pairs_f64(const double *score, int64_t ld, int n, int n_a, SplitMasks sm, const int *col_of_task,
                                  const int *fold_of_task, int n_tasks, int sign, unsigned long long *out, cudaStream_t st)
 {
     if (n_tasks <= 0 || n - n_a <= 0) return cudaSuccess;
     for (int t0 = 0; t0 < n_tasks; t0 += 32768) {
         const int nt = std::min(32768, n_tasks - t0);
         dim3 grid((n - n_a + 255) / 256, nt);
-        auc_pairs_kernel<double><<<grid, 256, 0, st>>>(score, ld, n, n_a, fold, col_of_task + t0, fold_of_task + t0, sign, out + (size_t)t0 * 4);
+        auc_pairs_kernel<double><<<grid, 256, 0, st>>>(score, ld, n, n_a, sm, col_of_task + t0, fold_of_task + t0, sign, out + (size_t)t0 * 4);
     }
     return cudaGetLastError();
 }
 
-cudaError_t launch_auc_pairs_f32(const float *score, int64_t ld, int n, int n_a, const signed char *fold, const int *col_of_task,
+cudaError_t launch_auc_pairs_f32(const float *score, int64_t ld, int n, int n_a, SplitMasks sm, const int *col_of_task,
                                  const int *fold_of_task, int n_tasks, int sign, unsigned long long *out, cudaStream_t st)
 {
     if (n_tasks <= 0 || n - n_a <= 0) return cudaSuccess;
     for (int t0 = 0; t0 < n_tasks; t0 += 32768) {
         const int nt = std::min(32768, n_tasks - t0);
         dim3 grid((n - n_a + 255) / 256, nt);
-        auc_pairs_kernel<float><<<grid, 256, 0, st>>>(score, ld, n, n_a, fold, col_of_task + t0, fold_of_task + t0, sign, out + (size_t)t0 * 4);
+        auc_pairs_kernel<float><<<grid, 256, 0, st>>>(score, ld, n, n_a, sm, col_of_task + t0, fold_of_task + t0, sign, out + (size_t)t0 * 4);
     }
     return cudaGetLastError();
 }
@@ -302,14 +307,14 @@ cudaError_t launch_decision(const double *S, const double *xsq, int n, int kerne
 }
 
 cudaError_t launch_vote(const double *dec, const double *rho, int n, int n_classes, const int *y,
-                        const signed char *fold, const VoteTask *tasks, int n_tasks, int *counts,
+                        SplitMasks sm, const VoteTask *tasks, int n_tasks, int *counts,
                         cudaStream_t st)
 {
     if (n_tasks <= 0) return cudaSuccess;
     for (int t0 = 0; t0 < n_tasks; t0 += 32768) {                     // gridDim.y <= 65535
         const int nt = std::min(32768, n_tasks - t0);
         dim3 grid((n + 255) / 256, nt);
-        vote_kernel<<<grid, 256, 0, st>>>(dec, rho, n, n_classes, y, fold, tasks + t0, counts + (size_t)t0 * 4);
+        vote_kernel<<<grid, 256, 0, st>>>(dec, rho, n, n_classes, y, sm, tasks + t0, counts + (size_t)t0 * 4);
     }
     return cudaGetLastError();
 }

@@ -46,6 +46,8 @@ def load_library():
     vp, i32, i64, u32, dbl = c.c_void_p, c.c_int32, c.c_int64, c.c_uint32, c.c_double
     L.gs_version.restype = c.c_int
     L.gs_device_count.restype = c.c_int
+    L.gs_set_splits.argtypes = [vp, vp, vp, i32]
+    L.gs_set_splits.restype = c.c_int
     L.gs_set_scoring.argtypes = [vp, i32, i32]
     L.gs_set_scoring.restype = c.c_int
     L.gs_create.argtypes = [c.c_int, c.POINTER(vp)]
@@ -111,6 +113,14 @@ class Engine:
     def _check(self, st):
         if st != 0:
             raise EngineError(st, (self._L.gs_last_error(self._h) or b"").decode())
+
+    def set_splits(self, test_mask, train_mask, n_splits):
+        """General CV splits (include/b200gs.h gs_set_splits): uint64 [n][2] membership masks, after set_data."""
+        te = np.ascontiguousarray(test_mask, np.uint64)
+        tr = np.ascontiguousarray(train_mask, np.uint64)
+        assert te.shape == (self.n, 2) and tr.shape == (self.n, 2)
+        self.n_splits = int(n_splits)
+        self._check(self._L.gs_set_splits(self._h, _ptr(te), _ptr(tr), int(n_splits)))
 
     def set_scoring(self, kind=0, pos_class=1):
         """Scorer of the following search calls (include/b200gs.h GS_SCORE_*): reference base_search.py:43 check_scoring."""

@@ -26,22 +26,64 @@ def get_engine(device=None):
 
 
 def fold_ids_from_splits(splits, n):
-    """fold_id[row] = index of the split whose TEST set holds the row.  The engine keeps one int8 per
-    row instead of per-task index arrays (reference base_search.py:81-82), which requires what every
-    (Stratified)KFold/GroupKFold/LeaveOneOut-style splitter gives: disjoint test sets whose complement
-    is the training set."""
+    """fold_id[row] = index of the split whose TEST set holds the row -- the compact form for the splitters every
+    (Stratified)KFold/GroupKFold/LeaveOneOut-style cv gives: disjoint test sets whose complement is the training set.
+    Raises NotImplementedError for any other splitter (see split_masks)."""
     if len(splits) > 127:
         raise NotImplementedError("more than 127 CV splits")
     fold_id = np.full(n, -1, np.int8)
     for k, (tr, te) in enumerate(splits):
         te = np.asarray(te)
         if np.any(fold_id[te] != -1):
-            raise NotImplementedError("CV splitter with overlapping test sets is not supported by the CUDA path")
+            raise NotImplementedError("CV splitter with overlapping test sets needs split masks")
         fold_id[te] = k
         if len(tr) + len(te) != n or len(np.intersect1d(tr, te)):
-            raise NotImplementedError("CV splitter whose train set is not the complement of its test set "
-                                      "is not supported by the CUDA path")
+            raise NotImplementedError("CV splitter whose train set is not the complement of its test set needs split masks")
     return fold_id
+
+
+def split_masks(splits, n):
+    """(test_mask, train_mask): uint64 [n][2], bit k of word k // 64 = the row belongs to the test / training set of split k
+    (include/b200gs.h gs_set_splits).  The general form of the reference's per-task index arrays (base_search.py:81-82): fits
+    ShuffleSplit, RepeatedKFold, PredefinedSplit with -1 entries ... up to 128 splits."""
+    if len(splits) > 128:
+        raise NotImplementedError("more than 128 CV splits")
+    te_m = np.zeros((n, 2), np.uint64)
+    tr_m = np.zeros((n, 2), np.uint64)
+    for k, (tr, te) in enumerate(splits):
+        bit = np.uint64(1) << np.uint64(k & 63)
+        te_m[np.asarray(te, np.int64), k >> 6] |= bit
+        tr_m[np.asarray(tr, np.int64), k >> 6] |= bit
+    if np.any(te_m & tr_m):
+        raise ValueError("a row is in both the training and the test set of a CV split")
+    return te_m, tr_m
+
+
+class Folds:
+    """The CV splits of one search in the forms the engine takes: fold ids when the splits are a partition (every estimator),
+    split masks otherwise (SVC, LogisticRegression)."""
+
+    def __init__(self, splits, n):
+        self.n_splits = len(splits)
+        self.n = n
+        try:
+            self.fold_id = fold_ids_from_splits(splits, n)
+            self.masks = None
+        except NotImplementedError:
+            self.fold_id = None
+            self.masks = split_masks(splits, n)
+
+    @property
+    def partition(self):
+        return self.fold_id is not None
+
+    def train_rows(self, k):
+        """boolean [n]: the training rows of split k (all rows for k < 0)"""
+        if k < 0:
+            return np.ones(self.n, bool)
+        if self.fold_id is not None:
+            return self.fold_id != k
+        return (self.masks[1][:, k >> 6] >> np.uint64(k & 63)) & np.uint64(1) == 1
 
 
 def adapter_for(estimator):
@@ -81,13 +123,35 @@ REGRESSION_SCORERS = {None: 0, "r2": 0, "neg_mean_squared_error": 16, "neg_root_
 class _Plan:
     def __init__(self, estimator, cands, X, y, fold_id, n_splits, device=None):
         self.estimator, self.cands = estimator, cands
-        self.X, self.y, self.fold_id, self.n_splits = _as_matrix(X), y, fold_id, n_splits
+        self.X, self.y, self.n_splits = _as_matrix(X), y, n_splits
+        if isinstance(fold_id, Folds):
+            self.folds, self.fold_id = fold_id, fold_id.fold_id
+        else:
+            self.folds, self.fold_id = None, fold_id
         self.engine = get_engine(device)
         self._prof = {}
         self.score_kind, self.score_pos = 0, 1
 
     def profile(self):
         return dict(self._prof)
+
+    def _set_data(self, X, **kw):
+        """gs_set_data (+ gs_set_splits when the splits are no partition)"""
+        if self.folds is not None and not self.folds.partition:
+            if not self.general_splits:
+                raise NotImplementedError("%s needs a CV splitter whose test sets partition the rows (KFold-like); the fold-Gram "
+                                          "algorithm has no CUDA path for %d overlapping / partial splits"
+                                          % (type(self.estimator).__name__, self.n_splits))
+            self.engine.set_data(X, np.full(len(X), -1, np.int8), self.n_splits, **kw)
+            self.engine.set_splits(self.folds.masks[0], self.folds.masks[1], self.n_splits)
+        else:
+            self.engine.set_data(X, self.fold_id, self.n_splits, **kw)
+
+    general_splits = True
+    def _train_rows(self, k):
+        if self.folds is not None:
+            return self.folds.train_rows(k)
+        return self.fold_id != k if k >= 0 else np.ones(len(self.fold_id), bool)
 
     scorers = {None: 0}
 
@@ -164,7 +228,7 @@ class SVCPlan(_Plan):
         self.classes, self.y_class = np.unique(np.asarray(y), return_inverse=True)
         if len(self.classes) < 2:
             raise ValueError("The number of classes has to be greater than one; got %d class" % len(self.classes))
-        self.engine.set_data(self.X, fold_id, n_splits, y_class=self.y_class.astype(np.int32))
+        self._set_data(self.X, y_class=self.y_class.astype(np.int32))
         self._var_cache = {}
 
     def _check(self, p):
@@ -186,8 +250,7 @@ class SVCPlan(_Plan):
                 return 1.0 / self.X.shape[1]
             if g == "scale":
                 if k not in self._var_cache:
-                    rows = self.fold_id != k if k >= 0 else np.ones(len(self.fold_id), bool)
-                    self._var_cache[k] = np.asarray(self.X[rows], np.float64).var()
+                    self._var_cache[k] = np.asarray(self.X[self._train_rows(k)], np.float64).var()
                 v = self._var_cache[k]
                 return 1.0 / (self.X.shape[1] * v) if v != 0 else 1.0
             raise ValueError("gamma=%r" % (g,))
@@ -322,6 +385,7 @@ class RidgeAdapter:
 
 class RidgePlan(_Plan):
     scorers = REGRESSION_SCORERS
+    general_splits = False         # fold Grams: T - G_k needs test folds that partition the rows
 
     def __init__(self, estimator, cands, X, y, fold_id, n_splits, device=None):
         super().__init__(estimator, cands, X, y, fold_id, n_splits, device)
@@ -332,7 +396,7 @@ class RidgePlan(_Plan):
             # scikit-learn solves float64 input in float64; the tensor-core Grams are fp32-faithful (3xTF32 split)
             warnings.warn("spark_sklearn_b200 Ridge computes in float32: float64 X is rounded to float32 before the "
                           "search (scores agree with scikit-learn's float64 fit to about 1e-6 relative)", UserWarning)
-        self.engine.set_data(self.X.astype(np.float32, copy=False), fold_id, n_splits, y_target=y.astype(np.float32))
+        self._set_data(self.X.astype(np.float32, copy=False), y_target=y.astype(np.float32))
 
     def _check(self, p):
         if p.get("solver", "auto") not in ("auto", "cholesky"):
@@ -399,8 +463,7 @@ class LogRegPlan(_Plan):
         if self.X.dtype != np.float32:
             warnings.warn("spark_sklearn_b200 LogisticRegression computes in float32: float64 X is rounded to float32 "
                           "before the search", UserWarning)
-        self.engine.set_data(self.X.astype(np.float32, copy=False), fold_id, n_splits,
-                             y_class=self.y_class.astype(np.int32))
+        self._set_data(self.X.astype(np.float32, copy=False), y_class=self.y_class.astype(np.int32))
 
     def _check(self, p):
         if p.get("solver", "lbfgs") != "lbfgs":

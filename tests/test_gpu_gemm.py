@@ -17,3 +17,26 @@ def test_gemm_nt_tf32x3(engine, M, N, K):
     assert err.max() < 2e-6, err.max()            # fp32-faithful: ~2^-22 split error + fp32 accumulation
     # plain TF32 (10-bit mantissa) would sit at ~1e-3: make sure the split really is in effect
     assert np.median(err) < 5e-7
+
+
+@pytest.mark.parametrize("M,K", [(128, 64), (300, 100), (1026, 512), (129, 33)])
+def test_gemm_gram_mode_is_symmetric_and_exact_enough(engine, M, K):
+    """A == B: only the tiles on or above the diagonal are computed, the rest are stored as their transposes."""
+    rng = np.random.RandomState(M + K)
+    A = (rng.randn(M, K) * rng.lognormal(0, 1, (M, 1))).astype(np.float32)
+    C = engine.debug_gemm_nt(A, A)
+    np.testing.assert_array_equal(C, C.T)
+    ref = A.astype(np.float64) @ A.astype(np.float64).T
+    scale = np.abs(A).astype(np.float64) @ np.abs(A).astype(np.float64).T
+    assert (np.abs(C - ref) / np.maximum(scale, 1e-30)).max() < 2e-6
+
+
+def test_gemm_many_tiles_per_cta(engine):
+    """More tiles than SMs: every persistent CTA walks several tiles through both TMEM accumulators and the smem ring."""
+    rng = np.random.RandomState(5)
+    A = rng.randn(2500, 96).astype(np.float32)
+    B = rng.randn(1700, 96).astype(np.float32)                      # 20 x 14 = 280 tiles
+    C = engine.debug_gemm_nt(A, B)
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    scale = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64).T
+    assert (np.abs(C - ref) / scale).max() < 2e-6

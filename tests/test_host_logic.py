@@ -79,6 +79,7 @@ def test_product_code_never_imports_the_oracle():
 # ------------------------------------------------------------------ oracle-backed plan ------------
 class OraclePlan:
     def __init__(self, estimator, cands, X, y, fold_id, n_splits):
+        fold_id = getattr(fold_id, "fold_id", fold_id)                     # base_search hands over an estimators.Folds
         self.estimator, self.cands, self.X, self.y, self.fold_id, self.n_splits = estimator, cands, np.asarray(X), y, fold_id, n_splits
 
     def evaluate(self, my, return_train=True, error_score="raise"):
@@ -209,6 +210,37 @@ def test_fold_ids_reject_non_partition_splitters():
     assert set(f) == {0, 1, 2, 3, 4} and f.dtype == np.int8
     with pytest.raises(NotImplementedError):
         fold_ids_from_splits(list(ShuffleSplit(3, test_size=0.5, random_state=0).split(X)), len(y))
+
+
+def test_split_masks_cover_general_splitters():
+    """reference base_search.py:34,81-82 re-derives ANY cv.split per task; here: fold ids for partitions, 128-bit membership
+    masks per row otherwise (overlapping test sets, rows in neither set, rows that only train)."""
+    from sklearn.model_selection import PredefinedSplit, RepeatedStratifiedKFold, ShuffleSplit, StratifiedKFold
+    from spark_sklearn_b200.estimators import Folds, split_masks
+    X, y = _iris()
+    n = len(y)
+    f = Folds(list(StratifiedKFold(5).split(X, y)), n)
+    assert f.partition and f.masks is None and f.train_rows(2).sum() == 120 and f.train_rows(-1).all()
+    cases = {"shuffle": list(ShuffleSplit(70, test_size=0.3, train_size=0.5, random_state=0).split(X)),
+             "repeated": list(RepeatedStratifiedKFold(n_splits=3, n_repeats=2, random_state=1).split(X, y)),
+             "predefined": list(PredefinedSplit(np.r_[np.full(50, -1), np.arange(100) % 2]).split())}
+    fp = Folds(cases["predefined"], n)                     # test folds disjoint, -1 rows train everywhere: still fold ids (-1)
+    assert fp.partition and (fp.fold_id[:50] == -1).all()
+    for name, splits in cases.items():
+        f = Folds(splits, n)
+        assert f.n_splits == len(splits) and f.partition == (name == "predefined"), name
+        te, tr = split_masks(splits, n)
+        assert te.shape == (n, 2) and te.dtype == np.uint64
+        for k, (a, b) in enumerate(splits):
+            got_tr = np.flatnonzero((tr[:, k >> 6] >> np.uint64(k & 63)) & np.uint64(1))
+            got_te = np.flatnonzero((te[:, k >> 6] >> np.uint64(k & 63)) & np.uint64(1))
+            np.testing.assert_array_equal(got_tr, np.sort(a)); np.testing.assert_array_equal(got_te, np.sort(b))
+            np.testing.assert_array_equal(np.flatnonzero(f.train_rows(k)), np.sort(a))
+    assert cases["predefined"][0][0][:50].tolist() == list(range(50))           # the -1 rows train in every split
+    with pytest.raises(ValueError):
+        split_masks([(np.arange(10), np.arange(5, 15))], n)                      # a row in both sets of one split
+    with pytest.raises(NotImplementedError):
+        split_masks([(np.arange(10), np.arange(10, 20))] * 129, n)
 
 
 def test_materialize_svc_binary_equals_sklearn_fit():
@@ -422,8 +454,10 @@ def test_bench_weak_scaling_grids_keep_64_candidates_per_gpu():
     w = bench.scaled_workload("c2", 1)
     cands = W.candidates(w)
     for cores in (6, 16, 96):
-        idx, rel = bench.cpu_sample(w, cands, cores)
-        assert len(idx) == min(cores, 64) and len(set(idx)) == len(idx)
+        idx, rel, src = bench.cpu_sample(w, cands, cores)
+        assert len(idx) == min(cores, 64) and len(set(idx)) == len(idx) and src == "golden n_iter_"
         assert 0.7 <= rel <= 1.3 or cores >= 64                          # sample mean cost ~ grid mean cost
+    idx, rel, _ = bench.cpu_sample(w, cands, 16, 0.4)                     # many steps: cheaper tasks, stated in the line
+    assert 0.3 <= rel <= 0.5
     assert bench.scaled_workload("c2", 4)["golden"] == "c4_svc_rbf_16x16"    # the N=4 weak grid is config 4: parity asserted in-run
 
