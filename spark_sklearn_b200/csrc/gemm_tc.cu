@@ -210,7 +210,9 @@ gemm_nt_tf32x3_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_con
             mbar_wait(b_tfull + 8 * buf, ((uint32_t)ti >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int m0 = mi * BM + q * 32, n0 = ni * BN;
-            const bool mirror = symmetric && mi != ni;
+            const bool diag = symmetric && mi == ni;       // diagonal tile: store j >= i, mirror the strict upper part (bitwise symmetric:
+                                                           // the hi*lo and lo*hi products of C[i][j] and C[j][i] accumulate in swapped order)
+            const bool mirror = symmetric != 0;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t r[32];
@@ -237,7 +239,7 @@ gemm_nt_tf32x3_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_con
 #pragma unroll 4
                     for (int rr = 0; rr < 32; rr++) {                            // a warp request = 32 consecutive columns of one row
                         const int row = m0 + rr;
-                        if (row < M) {
+                        if (row < M && !(diag && col < row)) {
                             float *dst = bt.c + (size_t)row * bt.ldc + col;
                             const float v = stg[rr * STG_LD + lane];
                             *dst = accumulate_c ? *dst + v : v;
@@ -250,7 +252,7 @@ gemm_nt_tf32x3_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_con
 #pragma unroll 4
                         for (int jj = 0; jj < 32; jj++) {
                             const int mrow = n0 + c0 + jj;
-                            if (mrow < N) {
+                            if (mrow < N && !(diag && mrow <= mcol)) {
                                 float *dst = bt.c + (size_t)mrow * bt.ldc + mcol;
                                 const float v = stg[lane * STG_LD + jj];
                                 *dst = accumulate_c ? *dst + v : v;
