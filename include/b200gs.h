@@ -64,6 +64,13 @@ int gs_version(void);
  * in neither.  gs_svc and gs_logreg honour the masks; gs_ridge needs gs_set_data's fold partition. */
 int gs_set_splits(gs_handle *h, const uint64_t *test_mask, const uint64_t *train_mask, int32_t n_splits);
 
+/* Class weights of the following gs_svc / gs_svc_refit calls: the C of a training row is C x w[class of the row].
+ * Replaces: SVC(class_weight=...) forwarded through clone(estimator).set_params / fit_params into every task (reference
+ * base_search.py:69,83-87); scikit-learn computes `class_weight_` from the TRAINING labels of each fit ('balanced' differs
+ * per fold), hence one weight set per split: w is [n_sets][n_classes], n_sets = n_splits (search), 1 (refit, or the same
+ * weights for every split); w == NULL resets to all ones. */
+int gs_set_class_weight(gs_handle *h, const double *w, int32_t n_sets);
+
 /* Scorer of the following gs_svc / gs_logreg / gs_ridge calls.  Replaces: check_scoring(estimator, scoring) and the scorer
  * call inside _fit_and_score (reference base_search.py:43,83-87; grid_search.py:212-214 `scoring=`).  The score is
  * computed on the device from the decision values / Gram statistics already in HBM.  pos_class: class id (index into the

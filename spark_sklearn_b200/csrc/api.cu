@@ -103,6 +103,18 @@ extern "C" {
 
 int gs_version(void) { return 101; }
 
+int gs_set_class_weight(gs_handle *h, const double *w, int32_t n_sets)
+{
+    if (!h) return GS_ERR_ARG;
+    if (!w || n_sets <= 0) { h->class_w.clear(); h->class_w_sets = 0; return GS_OK; }
+    if (h->n_classes <= 0) { gs_set_error(h, "gs_set_class_weight: no classification dataset"); return GS_ERR_NO_DATA; }
+    for (int64_t i = 0; i < (int64_t)n_sets * h->n_classes; i++)
+        if (!(w[i] > 0) || !std::isfinite(w[i])) { gs_set_error(h, "gs_set_class_weight: weights must be positive and finite"); return GS_ERR_ARG; }
+    h->class_w.assign(w, w + (size_t)n_sets * h->n_classes);
+    h->class_w_sets = n_sets;
+    return GS_OK;
+}
+
 int gs_set_scoring(gs_handle *h, int32_t kind, int32_t pos_class)
 {
     if (!h) return GS_ERR_ARG;
@@ -368,6 +380,9 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
     if (!h->classification) { gs_set_error(h, "gs_svc: dataset has no class labels"); return GS_ERR_ARG; }
     if (h->n_classes < 2 || h->n_classes > 32) { gs_set_error(h, "gs_svc: need 2..32 classes"); return GS_ERR_UNSUPPORTED; }
     if (n_cand <= 0 || !kernel || !Cv || !gamma) { gs_set_error(h, "gs_svc: bad arguments"); return GS_ERR_ARG; }
+    if (h->class_w_sets > 1 && h->class_w_sets != (refit ? 1 : h->n_splits)) {
+        gs_set_error(h, "gs_svc: gs_set_class_weight was given a weight set per split, but not for this number of splits"); return GS_ERR_ARG;
+    }
     GS_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     const int n = (int)h->n, d = (int)h->d, nc = h->n_classes;
@@ -565,7 +580,13 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
                     P.nseg = sp_nseg[s];
                     for (int e = 0; e < 4; e++) { P.seg_start[e] = sp_seg[s * 8 + e]; P.seg_len[e] = sp_seg[s * 8 + 4 + e]; }
                     P.n_pos = sp_npos[s];
-                    P.ldk = ldk; P.C = Cv[c]; P.eps = tol; P.max_iter = max_iter;
+                    P.ldk = ldk; P.C = Cv[c]; P.Cn = Cv[c]; P.eps = tol; P.max_iter = max_iter;
+                    if (h->class_w_sets > 0) {               // C_i = C x class_weight[class of i] (svm.cpp:2441-2470 weighted_C)
+                        const double *cw = &h->class_w[(size_t)(h->class_w_sets == 1 ? 0 : k) * nc];
+                        int a_ = 0, b_ = 0, q_ = 0;
+                        for (int a = 0; a < nc; a++) for (int b = a + 1; b < nc; b++, q_++) if (q_ == p) { a_ = a; b_ = b; }
+                        P.C = Cv[c] * cw[a_]; P.Cn = Cv[c] * cw[b_];
+                    }
                     P.shrinking = (flags & GS_NO_SHRINKING) ? 0 : 1;
                     P.nslots = 0;
                     for (int e = 0; e < P.nseg; e++) P.nslots += P.seg_len[e];

@@ -114,6 +114,8 @@ struct gs_handle {
     DevBuf dWork[9];                  // per-search scratch
     DevBuf dScore;                    // class counts / AUC pair counts of the non-default scorers
     int score_kind = 0, score_pos = 1;   // gs_set_scoring
+    std::vector<double> class_w;         // gs_set_class_weight: [sets][n_classes]; empty = all ones
+    int class_w_sets = 0;
     gs_profile prof;
     EventPool evp;                    // timing events of the current call
     TensorTimer tt;
@@ -143,7 +145,7 @@ struct SmoProblem {
     int *out_info;        // out: [0] n_iter [1] timed_out [2] n_sv [3] n_bounded_sv
     unsigned long long *out_ns;   // out: [0] start [1] end (globaltimer)
     int64_t ldk;
-    double C, eps;
+    double C, Cn, eps;    // C of the +1 class (the pair's first class) and of the -1 class: C x class_weight
     int l, n_pos, max_iter, shrinking;
     // up to 4 column ranges (floats, multiples of 4) that cover this sub-problem's dataset rows: the single-CTA kernel
     // copies only these parts of a K row into shared memory (a fold's training rows are 2-3 contiguous runs of the

@@ -502,8 +502,8 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
             }
         }
         if (warp == 0) {                                         // analytic 2-variable update, once per CTA
-            const double C = Pp->C;
             const bool yi = (pi & F_YPOS) != 0, yj = (pj & F_YPOS) != 0;
+            const double Ci = yi ? Pp->C : Pp->Cn, Cj = yj ? Pp->C : Pp->Cn;   // per-class C (class_weight, svm.cpp:1393-1396 get_C)
             const double Gi = yi ? -gmax : gmax;                 // G = -y m (exact)
             const double Gj = yj ? -mg_j : mg_j;
             const double QDi = QD(i), QDj = QD(j);
@@ -517,17 +517,17 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
                 ai = __dadd_rn(ai, delta); aj = __dadd_rn(aj, delta);
                 if (diff > 0) { if (aj < 0) { aj = 0; ai = diff; } }
                 else          { if (ai < 0) { ai = 0; aj = -diff; } }
-                if (diff > __dsub_rn(C, C)) { if (ai > C) { ai = C; aj = __dsub_rn(C, diff); } }
-                else                        { if (aj > C) { aj = C; ai = __dadd_rn(C, diff); } }
+                if (diff > __dsub_rn(Ci, Cj)) { if (ai > Ci) { ai = Ci; aj = __dsub_rn(Ci, diff); } }
+                else                          { if (aj > Cj) { aj = Cj; ai = __dadd_rn(Cj, diff); } }
             } else {                                             // svm.cpp:816-862
                 double quad = __dsub_rn(__dadd_rn(QDi, QDj), __dmul_rn(2.0, Qij));
                 if (quad <= 0) quad = TAU;
                 const double delta = __ddiv_rn(__dsub_rn(Gi, Gj), quad);
                 const double sum = __dadd_rn(ai, aj);
                 ai = __dsub_rn(ai, delta); aj = __dadd_rn(aj, delta);
-                if (sum > C) { if (ai > C) { ai = C; aj = __dsub_rn(sum, C); } }
+                if (sum > Ci) { if (ai > Ci) { ai = Ci; aj = __dsub_rn(sum, Ci); } }
                 else         { if (aj < 0) { aj = 0; ai = sum; } }
-                if (sum > C) { if (aj > C) { aj = C; ai = __dsub_rn(sum, C); } }
+                if (sum > Cj) { if (aj > Cj) { aj = Cj; ai = __dsub_rn(sum, Cj); } }
                 else         { if (ai < 0) { ai = 0; aj = sum; } }
             }
             if (lane == 0) {
@@ -535,8 +535,8 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
                 red.bc_d[0] = yi ? -dai : dai;                   // a = -y_i dalpha_i
                 red.bc_d[1] = yj ? -daj : daj;                   // b = -y_j dalpha_j
                 red.bc_d[2] = ai; red.bc_d[3] = aj;
-                red.bc_i[0] = ai >= C ? ST_UPPER : (ai <= 0 ? ST_LOWER : ST_FREE);
-                red.bc_i[1] = aj >= C ? ST_UPPER : (aj <= 0 ? ST_LOWER : ST_FREE);
+                red.bc_i[0] = ai >= Ci ? ST_UPPER : (ai <= 0 ? ST_LOWER : ST_FREE);
+                red.bc_i[1] = aj >= Cj ? ST_UPPER : (aj <= 0 ? ST_LOWER : ST_FREE);
             }
         }
         tick(4);
@@ -575,10 +575,10 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
         const bool need_j = use_gbar && (((pj & 3) == ST_UPPER) != (stj == ST_UPPER));
         if (need_i || need_j) {
             // Gbar -= C Q_i (was upper) / += C Q_i (became upper)  <=>  mbar += fl(c K_i), c = +/- y_i C
-            const double C = Pp->C;
+            const double Cmi = (pi & F_YPOS) ? Pp->C : Pp->Cn, Cmj = (pj & F_YPOS) ? Pp->C : Pp->Cn;
             const float *__restrict__ Ki = K + (size_t)col[i] * ldk;
-            const double ci = (((pi & 3) == ST_UPPER) == ((pi & F_YPOS) != 0)) ? C : -C;
-            const double cj = (((pj & 3) == ST_UPPER) == ((pj & F_YPOS) != 0)) ? C : -C;
+            const double ci = (((pi & 3) == ST_UPPER) == ((pi & F_YPOS) != 0)) ? Cmi : -Cmi;
+            const double cj = (((pj & 3) == ST_UPPER) == ((pj & F_YPOS) != 0)) ? Cmj : -Cmj;
 #pragma unroll
             for (int k = 0; k < KPT; k++) {
                 const int t = k * NT + tid;
@@ -596,7 +596,7 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
 
     // ---------------- calculate_rho (svm.cpp:1131-1168): sequential float64 sum in libsvm's order ----
     __syncthreads();
-    const double C = Pp->C;
+    const double C = Pp->C, Cng = Pp->Cn;
     if (tid == 0) {
         int nfree = 0;
         double ub = CUDART_INF, lb = -CUDART_INF, sum = 0;
@@ -617,7 +617,7 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
             const double av = alpha[t];
             coef[col[t]] = (fl[t] & F_YPOS) ? av : -av;
             nsv += av > 0;
-            nbsv += av >= C;
+            nbsv += av >= ((fl[t] & F_YPOS) ? C : Cng);
         }
     }
 #pragma unroll

@@ -111,7 +111,7 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
     const float *__restrict__ const K = Pp->K;
     const int64_t ldk = Pp->ldk;
     const double eps = Pp->eps;
-    const double Cc = Pp->C;
+    const double Cc = Pp->C, Cneg = Pp->Cn;                                   // C of the +1 / -1 class
     const bool use_gbar = Pp->shrinking != 0;
     const double *__restrict__ const qd = FAST ? nullptr : Pp->qd;
     int *const scratch = Pp->scratch;                                        // global ints, >= 2*l
@@ -655,8 +655,8 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
 #pragma unroll
         for (int k = 0; k < KPT; k++) kvj[k] = pos[k] < active ? __ldg(Kj + colr[k]) : 0.f;     // in flight during the scalar update
         if (warp == 0) {                                         // leader: analytic two-variable update, published to the workers
-            const double C = Cc;
             const bool yi = (pi & F_YPOS) != 0, yj = (pj & F_YPOS) != 0;
+            const double Ci = yi ? Cc : Cneg, Cj = yj ? Cc : Cneg;             // per-class C (class_weight, svm.cpp:1393-1396 get_C)
             const double Gi = yi ? -gmax : gmax;                 // G = -y m (exact)
             const double Gj = yj ? -mg_j : mg_j;
             const double QDi = QDc(col_i), QDj = QDc(col_j);
@@ -670,23 +670,23 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
                 ai = __dadd_rn(ai, delta); aj = __dadd_rn(aj, delta);
                 if (diff > 0) { if (aj < 0) { aj = 0; ai = diff; } }
                 else          { if (ai < 0) { ai = 0; aj = -diff; } }
-                if (diff > __dsub_rn(C, C)) { if (ai > C) { ai = C; aj = __dsub_rn(C, diff); } }
-                else                        { if (aj > C) { aj = C; ai = __dadd_rn(C, diff); } }
+                if (diff > __dsub_rn(Ci, Cj)) { if (ai > Ci) { ai = Ci; aj = __dsub_rn(Ci, diff); } }
+                else                          { if (aj > Cj) { aj = Cj; ai = __dadd_rn(Cj, diff); } }
             } else {                                             // svm.cpp:816-862
                 double quad = __dsub_rn(__dadd_rn(QDi, QDj), __dmul_rn(2.0, Qij));
                 if (quad <= 0) quad = TAU;
                 const double delta = __ddiv_rn(__dsub_rn(Gi, Gj), quad);
                 const double sum = __dadd_rn(ai, aj);
                 ai = __dsub_rn(ai, delta); aj = __dadd_rn(aj, delta);
-                if (sum > C) { if (ai > C) { ai = C; aj = __dsub_rn(sum, C); } }
+                if (sum > Ci) { if (ai > Ci) { ai = Ci; aj = __dsub_rn(sum, Ci); } }
                 else         { if (aj < 0) { aj = 0; ai = sum; } }
-                if (sum > C) { if (aj > C) { aj = C; ai = __dsub_rn(sum, C); } }
+                if (sum > Cj) { if (aj > Cj) { aj = Cj; ai = __dsub_rn(sum, Cj); } }
                 else         { if (ai < 0) { ai = 0; aj = sum; } }
             }
             if (lane == 0) {
                 const double dai = __dsub_rn(ai, alpha_i), daj = __dsub_rn(aj, alpha_j);
                 const double av = yi ? -dai : dai, bv = yj ? -daj : daj;       // a = -y_i dalpha_i, b = -y_j dalpha_j
-                const int si = ai >= C ? ST_UPPER : (ai <= 0 ? ST_LOWER : ST_FREE), sj = aj >= C ? ST_UPPER : (aj <= 0 ? ST_LOWER : ST_FREE);
+                const int si = ai >= Ci ? ST_UPPER : (ai <= 0 ? ST_LOWER : ST_FREE), sj = aj >= Cj ? ST_UPPER : (aj <= 0 ? ST_LOWER : ST_FREE);
                 *reinterpret_cast<uint4 *>(&hot.resB2[0]) = make_uint4(lo32(av), hi32(av), lo32(bv), hi32(bv));
                 *reinterpret_cast<uint4 *>(&hot.resB2[4]) = make_uint4(lo32(ai), hi32(ai), lo32(aj), hi32(aj));
                 *reinterpret_cast<uint2 *>(&hot.resB2[8]) = make_uint2((unsigned)si, (unsigned)sj);
@@ -724,8 +724,9 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
         if (need_i || need_j) {
             // Gbar -= C Q_i (was upper) / += C Q_i (became upper)  <=>  mbar += fl(c K_i), c = +/- y_i C
             const float *__restrict__ Ki = K + (size_t)col_i * ldk;
-            const double ci = (((pi & 3) == ST_UPPER) == ((pi & F_YPOS) != 0)) ? Cc : -Cc;
-            const double cj = (((pj & 3) == ST_UPPER) == ((pj & F_YPOS) != 0)) ? Cc : -Cc;
+            const double Cmi = (pi & F_YPOS) ? Cc : Cneg, Cmj = (pj & F_YPOS) ? Cc : Cneg;
+            const double ci = (((pi & 3) == ST_UPPER) == ((pi & F_YPOS) != 0)) ? Cmi : -Cmi;
+            const double cj = (((pj & 3) == ST_UPPER) == ((pj & F_YPOS) != 0)) ? Cmj : -Cmj;
 #pragma unroll
             for (int k = 0; k < KPT; k++) {
                 if (pos[k] != NOPOS) {
@@ -772,7 +773,7 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
                 const double av = alpha[k * NT + tid];
                 coef[colr[k]] = (fl[k] & F_YPOS) ? av : -av;
                 nsv += av > 0;
-                nbsv += av >= Cc;
+                nbsv += av >= ((fl[k] & F_YPOS) ? Cc : Cneg);
             }
         }
     }

@@ -173,7 +173,7 @@ smo_lean_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ or
     const float *__restrict__ const K = Pp->K;
     const int64_t ldk = Pp->ldk;
     const double eps = Pp->eps;
-    const double Cc = Pp->C;
+    const double Cc = Pp->C, Cneg = Pp->Cn;                                   // C of the +1 / -1 class
     const bool use_gbar = Pp->shrinking != 0;
     const double *__restrict__ const qd = FAST ? nullptr : Pp->qd;
 
@@ -710,8 +710,8 @@ smo_lean_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ or
         double a, b;
         int sti, stj;
         {
-            const double C = Cc;
             const bool yi = slot_i < ysplit, yj = slot_j < ysplit;
+            const double Ci = yi ? Cc : Cneg, Cj = yj ? Cc : Cneg;             // per-class C (class_weight, svm.cpp:1393-1396 get_C)
             const double Gi = yi ? -gmax : gmax;                 // G = -y m (exact)
             const double Gj = yj ? -mg_j : mg_j;
             const double QDi = QDc(col_i), QDj = QDc(col_j);
@@ -725,22 +725,22 @@ smo_lean_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ or
                 ai = __dadd_rn(ai, delta); aj = __dadd_rn(aj, delta);
                 if (diff > 0) { if (aj < 0) { aj = 0; ai = diff; } }
                 else          { if (ai < 0) { ai = 0; aj = -diff; } }
-                if (diff > __dsub_rn(C, C)) { if (ai > C) { ai = C; aj = __dsub_rn(C, diff); } }
-                else                        { if (aj > C) { aj = C; ai = __dadd_rn(C, diff); } }
+                if (diff > __dsub_rn(Ci, Cj)) { if (ai > Ci) { ai = Ci; aj = __dsub_rn(Ci, diff); } }
+                else                          { if (aj > Cj) { aj = Cj; ai = __dadd_rn(Cj, diff); } }
             } else {                                             // svm.cpp:816-862
                 double quad = __dsub_rn(__dadd_rn(QDi, QDj), __dmul_rn(2.0, Qij));
                 if (quad <= 0) quad = TAU;
                 const double delta = __ddiv_rn(__dsub_rn(Gi, Gj), quad);
                 const double sum = __dadd_rn(ai, aj);
                 ai = __dsub_rn(ai, delta); aj = __dadd_rn(aj, delta);
-                if (sum > C) { if (ai > C) { ai = C; aj = __dsub_rn(sum, C); } }
+                if (sum > Ci) { if (ai > Ci) { ai = Ci; aj = __dsub_rn(sum, Ci); } }
                 else         { if (aj < 0) { aj = 0; ai = sum; } }
-                if (sum > C) { if (aj > C) { aj = C; ai = __dsub_rn(sum, C); } }
+                if (sum > Cj) { if (aj > Cj) { aj = Cj; ai = __dsub_rn(sum, Cj); } }
                 else         { if (ai < 0) { ai = 0; aj = sum; } }
             }
             const double dai = __dsub_rn(ai, alpha_i), daj = __dsub_rn(aj, alpha_j);
-            sti = ai >= C ? ST_UPPER : (ai <= 0 ? ST_LOWER : ST_FREE);
-            stj = aj >= C ? ST_UPPER : (aj <= 0 ? ST_LOWER : ST_FREE);
+            sti = ai >= Ci ? ST_UPPER : (ai <= 0 ? ST_LOWER : ST_FREE);
+            stj = aj >= Cj ? ST_UPPER : (aj <= 0 ? ST_LOWER : ST_FREE);
             a = yi ? -dai : dai;                                 // a = -y_i dalpha_i
             b = yj ? -daj : daj;                                 // b = -y_j dalpha_j
             // the OWNERS of i and j store alpha and the slot word (new status and set membership) and patch their flag mask;
@@ -801,8 +801,9 @@ smo_lean_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ or
         const bool need_j = use_gbar && (((pj & 3u) == ST_UPPER) != (stj == ST_UPPER));
         if (need_i || need_j) {
             // Gbar -= C Q_i (was upper) / += C Q_i (became upper)  <=>  mbar += fl(c K_i), c = +/- y_i C
-            const double ci = (((pi & 3u) == ST_UPPER) == (slot_i < ysplit)) ? Cc : -Cc;
-            const double cj = (((pj & 3u) == ST_UPPER) == (slot_j < ysplit)) ? Cc : -Cc;
+            const double Cmi = slot_i < ysplit ? Cc : Cneg, Cmj = slot_j < ysplit ? Cc : Cneg;
+            const double ci = (((pi & 3u) == ST_UPPER) == (slot_i < ysplit)) ? Cmi : -Cmi;
+            const double cj = (((pj & 3u) == ST_UPPER) == (slot_j < ysplit)) ? Cmj : -Cmj;
             // one group of 4 slots at a time, the next group's G_bar already in flight (all of it at once spills)
             double2 nx0 = make_double2(0, 0), nx1 = nx0;
             if (tid * 4 < nslots) { nx0 = *reinterpret_cast<const double2 *>(gbar_g + tid * 4); nx1 = *reinterpret_cast<const double2 *>(gbar_g + tid * 4 + 2); }
@@ -853,7 +854,7 @@ smo_lean_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ or
                     const double av = __ldcg(alpha_g + s4 + q);
                     coef[gcol[g] + q] = s4 + q < ysplit ? av : -av;
                     nsv += av > 0;
-                    nbsv += av >= Cc;
+                    nbsv += av >= (s4 + q < ysplit ? Cc : Cneg);
                 }
             }
         }

@@ -48,6 +48,8 @@ def load_library():
     L.gs_device_count.restype = c.c_int
     L.gs_set_splits.argtypes = [vp, vp, vp, i32]
     L.gs_set_splits.restype = c.c_int
+    L.gs_set_class_weight.argtypes = [vp, vp, i32]
+    L.gs_set_class_weight.restype = c.c_int
     L.gs_set_scoring.argtypes = [vp, i32, i32]
     L.gs_set_scoring.restype = c.c_int
     L.gs_create.argtypes = [c.c_int, c.POINTER(vp)]
@@ -121,6 +123,14 @@ class Engine:
         assert te.shape == (self.n, 2) and tr.shape == (self.n, 2)
         self.n_splits = int(n_splits)
         self._check(self._L.gs_set_splits(self._h, _ptr(te), _ptr(tr), int(n_splits)))
+
+    def set_class_weight(self, w=None):
+        """[n_sets][n_classes] class weights of the following svc / svc_refit calls (None: all ones)."""
+        if w is None:
+            self._check(self._L.gs_set_class_weight(self._h, None, 0))
+            return
+        w = np.ascontiguousarray(np.atleast_2d(w), np.float64)
+        self._check(self._L.gs_set_class_weight(self._h, _ptr(w), w.shape[0]))
 
     def set_scoring(self, kind=0, pos_class=1):
         """Scorer of the following search calls (include/b200gs.h GS_SCORE_*): reference base_search.py:43 check_scoring."""

@@ -234,8 +234,6 @@ class SVCPlan(_Plan):
     def _check(self, p):
         if p["kernel"] not in ("rbf", "linear"):
             raise NotImplementedError("SVC kernel=%r has no CUDA path (rbf and linear do)" % (p["kernel"],))
-        if p.get("class_weight") is not None:
-            raise NotImplementedError("SVC class_weight is not supported by the CUDA path")
         if p.get("probability") not in (False, "deprecated", None):
             raise NotImplementedError("SVC probability=True is not supported by the CUDA path")
         if p.get("break_ties"):
@@ -257,6 +255,23 @@ class SVCPlan(_Plan):
         if not (isinstance(g, numbers.Real) and g >= 0):
             raise ValueError("gamma must be >= 0 or 'scale'/'auto'; got %r" % (g,))
         return float(g)
+
+    def _class_weights(self, cw, k):
+        """scikit-learn's class_weight_ of one fit (svm/_base.py:  compute_class_weight(class_weight, classes, y_train)):
+        None -> ones; dict -> by label (missing labels 1.0); 'balanced' -> n / (n_classes * bincount) on the TRAINING rows of
+        split k (k < 0: all rows)."""
+        from sklearn.utils.class_weight import compute_class_weight
+        rows = self._train_rows(k)
+        return compute_class_weight(cw, classes=self.classes, y=np.asarray(self.y)[rows])
+
+    def _set_class_weight(self, cw, refit=False):
+        if cw is None:
+            self.engine.set_class_weight(None)
+            return np.ones(len(self.classes))
+        ks = [-1] if refit else range(self.n_splits)
+        w = np.stack([self._class_weights(cw, k) for k in ks])
+        self.engine.set_class_weight(w)
+        return w[0]
 
     def costs(self):
         """Predicted SMO iterations per candidate from the library's own model (gs_svc_predicted_iterations: the one
@@ -296,9 +311,12 @@ class SVCPlan(_Plan):
             p = self._base_params(self.cands[ci])
             self._check(p)
             params.append(p)
-            groups.setdefault((float(p["tol"]), int(p["max_iter"]), bool(p["shrinking"])), []).append(j)
+            cw = p.get("class_weight")
+            cwk = None if cw is None else (cw if isinstance(cw, str) else tuple(sorted(cw.items())))
+            groups.setdefault((float(p["tol"]), int(p["max_iter"]), bool(p["shrinking"]), cwk), []).append(j)
         prof = {}
-        for (tol, max_iter, shrinking), idx in groups.items():
+        for (tol, max_iter, shrinking, _cwk), idx in groups.items():
+            self._set_class_weight(params[idx[0]].get("class_weight"))
             kern = [params[j]["kernel"] for j in idx]
             C = [float(params[j]["C"]) for j in idx]
             gam = np.array([[self._gamma(params[j]["gamma"], k) if params[j]["kernel"] == "rbf" else 0.0
@@ -315,6 +333,7 @@ class SVCPlan(_Plan):
                 res["train"][idx] = r["train"]
             for k, v in self.engine.profile().items():
                 prof[k] = prof.get(k, 0) + v
+        self.engine.set_class_weight(None)
         self._prof = prof
         self.n_iter_ = res["n_iter"]
         return self._finish(res, return_train, error_score, len(my))
@@ -323,11 +342,15 @@ class SVCPlan(_Plan):
         p = self._base_params(best_params)
         self._check(p)
         gamma = self._gamma(p["gamma"], -1)          # all rows train (svm/_base.py:278-286)
+        cw_ = self._set_class_weight(p.get("class_weight"), refit=True)
         coef, rho, n_iter = self.engine.svc_refit(p["kernel"], p["C"], gamma if p["kernel"] == "rbf" else 0.0,
                                                   len(self.classes), tol=p["tol"], max_iter=p["max_iter"],
                                                   shrinking=p["shrinking"])
+        self.engine.set_class_weight(None)
         est = clone(self.estimator).set_params(**best_params)
-        return materialize_svc(est, self.X, self.y_class, self.classes, coef, rho, n_iter, gamma)
+        est = materialize_svc(est, self.X, self.y_class, self.classes, coef, rho, n_iter, gamma)
+        est.class_weight_ = np.asarray(cw_, np.float64)
+        return est
 
 
 def materialize_svc(est, X, y_class, classes, pair_coef, rho, n_iter, gamma):

@@ -285,3 +285,38 @@ def test_in_process_multi_gpu_equals_single_gpu(monkeypatch):
     for k in one.cv_results_:
         if k.endswith("_score"):                                   # every split / mean / std / rank score; not the *_score_time keys
             np.testing.assert_array_equal(np.asarray(one.cv_results_[k], float), np.asarray(many.cv_results_[k], float), err_msg=k)
+
+
+@pytest.mark.parametrize("cl", [0, 4])
+def test_class_weight_vs_sklearn(engine, monkeypatch, cl):
+    """SVC(class_weight=...): the C of a training row is C x the weight of its class, 'balanced' recomputed from the
+    training labels of every fold (reference base_search.py:69,83-87 forwards the estimator's parameters into every task).
+    Slot-layout and cluster solver, binary and one-vs-one, against scikit-learn: identical split scores and predictions."""
+    from sklearn import svm
+    from sklearn.model_selection import GridSearchCV as SkGrid
+    from spark_sklearn_b200 import GridSearchCV
+    monkeypatch.setenv("B200GS_SMO_CLUSTER", str(cl))
+    if cl:
+        monkeypatch.setenv("B200GS_SMO_CLUSTER_N", "100000")
+    w = W.make_workload("c2_mid")
+    X, y = w["X"][:1500], w["y"][:1500].copy()
+    y[:350] = 0                                                     # unbalanced classes
+    grid = {"C": [0.5, 8.0], "class_weight": [None, "balanced", {0: 1.0, 1: 6.0}]}
+    a = GridSearchCV(None, svm.SVC(kernel="rbf", gamma=1 / 128), grid, cv=4).fit(X, y)
+    b = SkGrid(svm.SVC(kernel="rbf", gamma=1 / 128), grid, cv=4, return_train_score=True).fit(X, y)
+    for k in range(4):
+        for part in ("test", "train"):
+            key = "split%d_%s_score" % (k, part)
+            np.testing.assert_array_equal(a.cv_results_[key], b.cv_results_[key], err_msg=key)
+    assert a.best_params_ == b.best_params_
+    np.testing.assert_array_equal(a.predict(X), b.predict(X))
+    np.testing.assert_allclose(a.best_estimator_.class_weight_, b.best_estimator_.class_weight_, rtol=1e-15)
+    np.testing.assert_array_equal(a.best_estimator_.n_iter_, b.best_estimator_.n_iter_)
+    if cl == 0:
+        wi = W.make_workload("c1")                                  # three classes, one-vs-one pairs with different C per side
+        gi = {"C": [1, 10], "class_weight": ["balanced", {0: 2.0, 2: 0.5}]}
+        ai = GridSearchCV(None, svm.SVC(gamma="auto"), gi, cv=5).fit(wi["X"], wi["y"])
+        bi = SkGrid(svm.SVC(gamma="auto"), gi, cv=5, return_train_score=True).fit(wi["X"], wi["y"])
+        for k in range(5):
+            np.testing.assert_array_equal(ai.cv_results_["split%d_test_score" % k], bi.cv_results_["split%d_test_score" % k])
+        np.testing.assert_array_equal(ai.predict(wi["X"]), bi.predict(wi["X"]))

@@ -202,6 +202,51 @@ def test_unsupported_configurations_raise_instead_of_falling_back():
         GridSearchCV(None, svm.SVC(), {"C": 1.0})          # _check_param_grid (grid_search.py:226)
 
 
+def test_three_tier_schedule_on_measured_and_synthetic_costs():
+    """gs_svc_schedule (clusters / exclusive SMs / shared SMs): on the measured iteration counts of configs 2 and 4 and on
+    cost profiles it was not calibrated on.  Properties, not constants: a throughput-bound profile gets no latency tier; a
+    profile with a few dominant problems puts exactly those on clusters; the predicted makespan never exceeds the
+    all-shared schedule's; specialised SMs never exceed the GPU."""
+    import ctypes
+    from spark_sklearn_b200 import engine
+    L = engine.load_library()
+
+    def sched(cost, sms=148):
+        c = np.sort(np.asarray(cost, float))[::-1].copy()
+        a, b = ctypes.c_int32(), ctypes.c_int32()
+        L.gs_svc_schedule(c.ctypes.data, len(c), sms, ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value, c
+
+    def makespan(c, nc, ne, sms=148):
+        left = sms - 4 * nc - ne
+        t = max(0.5 * c[nc + ne:].sum() / left, 0.78 * c[nc + ne] if nc + ne < len(c) else 0.0)
+        if nc: t = max(t, 0.34 * c[0])
+        if ne: t = max(t, 0.55 * c[nc])
+        return t
+
+    _, _, it2 = _golden_svc("c2_svc_rbf_8x8")
+    _, _, it4 = _golden_svc("c4_svc_rbf_16x16")
+    nc, ne, c = sched(it2.ravel())
+    assert 10 <= nc <= 20 and 10 <= ne <= 40 and 4 * nc + ne <= 140           # the 66-68k group on clusters, the 43-48k tier alone
+    assert makespan(c, nc, ne) <= 0.75 * makespan(c, 0, 0)                     # measured: 279 ms vs 442 ms all shared
+    assert sched(it4.ravel())[:2] == (0, 0)                                    # 1280 problems: throughput-bound
+    rng = np.random.default_rng(0)
+    for trial in range(20):                                                    # unseen profiles
+        n = int(rng.integers(150, 3000))
+        cost = rng.lognormal(0.0, rng.uniform(0.2, 1.5), n)
+        nc, ne, c = sched(cost)
+        assert 4 * nc + ne <= 140 and nc + ne < n
+        assert makespan(c, nc, ne) <= makespan(c, 0, 0) * (1 + 1e-12)
+    flat = np.ones(2000)
+    assert sched(flat)[:2] == (0, 0)
+    spiky = np.r_[np.full(5, 100.0), np.ones(400)]                             # five dominant problems
+    nc, ne, _ = sched(spiky)
+    assert nc == 5 and ne == 0
+    a, b = ctypes.c_int32(7), ctypes.c_int32(7)
+    L.gs_svc_schedule(None, 0, 148, ctypes.byref(a), ctypes.byref(b))
+    assert (a.value, b.value) == (0, 0)
+
+
 def test_fold_ids_reject_non_partition_splitters():
     from sklearn.model_selection import ShuffleSplit, StratifiedKFold
     from spark_sklearn_b200.estimators import fold_ids_from_splits
