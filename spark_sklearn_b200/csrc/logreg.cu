@@ -328,8 +328,8 @@ __global__ void lbfgs_export_kernel(const double *__restrict__ Vall, int ncol, i
 // column c trains on rows whose fold id != fold_of_col[c] (or on all rows when fold_of_col[c] < 0).
 __global__ void logistic_residual_kernel(const float *__restrict__ Zt, int64_t ldz, int n, const int *__restrict__ y,
                                          SplitMasks sm, const int *__restrict__ fold_of_col,
-                                         const double *__restrict__ inv_ntrain, LbScalars *__restrict__ Sc,
-                                         float *__restrict__ Rh, float *__restrict__ Rl)
+                                         const double *__restrict__ inv_ntrain, const float *__restrict__ cw /* [ncol][2] class weights or null */,
+                                         LbScalars *__restrict__ Sc, float *__restrict__ Rh, float *__restrict__ Rl)
 {
     const int c = blockIdx.y;
     if (Sc[c].task == T_DONE) return;
@@ -344,9 +344,15 @@ __global__ void logistic_residual_kernel(const float *__restrict__ Zt, int64_t l
             const float yi = (float)y[i];
             // half binomial loss log(1+e^z) - y z, evaluated the numerically stable way
             const float lz = z > 0.f ? z + log1pf(expf(-z)) : log1pf(expf(z));
-            acc += (double)(lz - yi * z);
             const float p = 1.f / (1.f + expf(-z));
-            rres = (p - yi) * invn;
+            if (cw) {                                    // sample_weight = class_weight_[y] multiplies the pointwise loss and gradient
+                const float wi = cw[c * 2 + y[i]];       // (_logistic.py: sample_weight *= class_weight_[y]; _loss: loss_out *= sample_weight)
+                acc += (double)(wi * (lz - yi * z));
+                rres = (wi * (p - yi)) * invn;
+            } else {
+                acc += (double)(lz - yi * z);
+                rres = (p - yi) * invn;
+            }
         }
         const float hh = __uint_as_float(__float_as_uint(rres) & 0xffffe000u);
         Rh[idx] = hh; Rl[idx] = rres - hh;
@@ -467,7 +473,7 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
     GS_CUDA(bW.reserve((size_t)ncol * nvp * 4 * (3 + (size_t)nchunk)));
     GS_CUDA(bV.reserve((size_t)ncol * (5 + 2 * MCOR) * nvp * 8));
     GS_CUDA(bS.reserve((size_t)ncol * sizeof(LbScalars)));
-    GS_CUDA(bMeta.reserve((size_t)ncol * (4 + 8 + 16) + (size_t)(nchunk + 4) * sizeof(TcBatch) + 256));
+    GS_CUDA(bMeta.reserve((size_t)ncol * (4 + 8 + 16 + 8) + (size_t)(nchunk + 4) * sizeof(TcBatch) + 256));
     float *dXa = bXa.as<float>(), *dXat = dXa + (size_t)n * nvp;
     // hi parts of [Xa | Xa^T] contiguous, then the lo parts: one split launch covers both matrices
     float *dXah = bXs.as<float>(), *dXath = dXah + (size_t)n * nvp, *dXal = dXath + (size_t)nvp * npad, *dXatl = dXal + (size_t)n * nvp;
@@ -477,29 +483,47 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
     LbScalars *dS = bS.as<LbScalars>();
     unsigned char *mp = bMeta.as<unsigned char>();
     double *dInv = reinterpret_cast<double *>(mp); mp += (size_t)ncol * 8;
+    float *dCwBuf = reinterpret_cast<float *>(mp); mp += (size_t)ncol * 8;
     int *dFoldOf = reinterpret_cast<int *>(mp); mp += (size_t)ncol * 4;
     int *dCounts = reinterpret_cast<int *>(mp); mp += (size_t)ncol * 16;
     int *dOpen = reinterpret_cast<int *>(mp); mp += 16;
     TcBatch *dBatch = reinterpret_cast<TcBatch *>(((uintptr_t)mp + 15) & ~(uintptr_t)15);
 
     // per-column constants
-    std::vector<int> ntrain(std::max(ns, 1), 0);                           // training rows of every split
-    if (!refit) for (int k = 0; k < ns; k++) for (int i = 0; i < n; i++) ntrain[k] += h->is_train(i, k) ? 1 : 0;
+    std::vector<int> ntrain(std::max(ns, 1), 0), ntrain1(std::max(ns, 1), 0);   // training rows of every split, and those of class 1
+    for (int k = 0; k < ns; k++)
+        for (int i = 0; i < n; i++)
+            if (refit || h->is_train(i, k)) { ntrain[k]++; ntrain1[k] += h->yc[i] == 1; }
+    const bool weighted = h->class_w_sets > 0;
+    if (weighted && h->class_w_sets != 1 && h->class_w_sets != ns) {
+        gs_set_error(h, "gs_logreg: gs_set_class_weight was given a weight set per split, but not for this number of splits"); return GS_ERR_ARG;
+    }
+    std::vector<float> cwcol((size_t)ncol * 2, 1.f);
     std::vector<LbScalars> hs(ncol);
     std::vector<double> inv(ncol);
     std::vector<int> foldof(ncol);
     for (int c = 0; c < n_cand; c++)
         for (int k = 0; k < ns; k++) {
             const int col = c * ns + k;
-            const int ntr = refit ? n : ntrain[k];
+            double sw_sum = (double)ntrain[k];                     // sum of the sample weights of the training rows
+            if (weighted) {
+                const double *cw = &h->class_w[(size_t)(h->class_w_sets == 1 ? 0 : k) * 2];
+                cwcol[(size_t)col * 2] = (float)cw[0]; cwcol[(size_t)col * 2 + 1] = (float)cw[1];
+                sw_sum = (double)((float)cw[0]) * (ntrain[k] - ntrain1[k]) + (double)((float)cw[1]) * ntrain1[k];
+            }
             memset(&hs[col], 0, sizeof(LbScalars));
             hs[col].task = T_FG_START; hs[col].theta = 1.0; hs[col].fresh = 1;
-            hs[col].l2 = 1.0 / (Cv[c] * (double)ntr);
-            inv[col] = 1.0 / (double)ntr;
+            hs[col].l2 = 1.0 / (Cv[c] * sw_sum);
+            inv[col] = 1.0 / sw_sum;
             foldof[col] = refit ? -100 : k;
         }
     GS_CUDA(cudaMemcpyAsync(dS, hs.data(), (size_t)ncol * sizeof(LbScalars), cudaMemcpyHostToDevice, st));
     GS_CUDA(cudaMemcpyAsync(dInv, inv.data(), (size_t)ncol * 8, cudaMemcpyHostToDevice, st));
+    const float *dCw = nullptr;
+    if (weighted) {
+        GS_CUDA(cudaMemcpyAsync(dCwBuf, cwcol.data(), (size_t)ncol * 8, cudaMemcpyHostToDevice, st));
+        dCw = dCwBuf;
+    }
     GS_CUDA(cudaMemcpyAsync(dFoldOf, foldof.data(), (size_t)ncol * 4, cudaMemcpyHostToDevice, st));
     GS_CUDA(cudaMemsetAsync(dV, 0, (size_t)ncol * (5 + 2 * MCOR) * nvp * 8, st));        // x0 = 0
     GS_CUDA(cudaMemsetAsync(dWh, 0, (size_t)ncol * nvp * 4 * 2, st));                      // trial point = x0
@@ -535,7 +559,7 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
         GS_CUDA(launch_gemm_nt_tf32x3(mWh, mWl, mXh, mXl, dBatch, 1, ncol, n, 1.0f, false, st));
         h->tt.end(h->evp, st, 3.0 * 2.0 * (double)ncol * n * nvp);
         dim3 grid(64, ncol);
-        logistic_residual_kernel<<<grid, 256, 0, st>>>(dZ, npad, n, h->dY.as<int>(), h->masks(), dFoldOf, dInv, dS, dRh, dRl);
+        logistic_residual_kernel<<<grid, 256, 0, st>>>(dZ, npad, n, h->dY.as<int>(), h->masks(), dFoldOf, dInv, dCw, dS, dRh, dRl);
         GS_CUDA(cudaGetLastError());
         h->tt.begin(h->evp, st);
         GS_CUDA(launch_gemm_nt_tf32x3(mRh, mRl, mXth, mXtl, dBatch + 1, nchunk, ncol, nv, 1.0f, false, st));

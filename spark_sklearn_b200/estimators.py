@@ -148,6 +148,23 @@ class _Plan:
             self.engine.set_data(X, self.fold_id, self.n_splits, **kw)
 
     general_splits = True
+    def _class_weights(self, cw, k):
+        """scikit-learn's class_weight_ of one fit (svm/_base.py, linear_model/_logistic.py: compute_class_weight(class_weight, classes, y_train)):
+        None -> ones; dict -> by label (missing labels 1.0); 'balanced' -> n / (n_classes * bincount) on the TRAINING rows of
+        split k (k < 0: all rows)."""
+        from sklearn.utils.class_weight import compute_class_weight
+        rows = self._train_rows(k)
+        return compute_class_weight(cw, classes=self.classes, y=np.asarray(self.y)[rows])
+
+    def _set_class_weight(self, cw, refit=False):
+        if cw is None:
+            self.engine.set_class_weight(None)
+            return np.ones(len(self.classes))
+        ks = [-1] if refit else range(self.n_splits)
+        w = np.stack([self._class_weights(cw, k) for k in ks])
+        self.engine.set_class_weight(w)
+        return w[0]
+
     def _train_rows(self, k):
         if self.folds is not None:
             return self.folds.train_rows(k)
@@ -255,23 +272,6 @@ class SVCPlan(_Plan):
         if not (isinstance(g, numbers.Real) and g >= 0):
             raise ValueError("gamma must be >= 0 or 'scale'/'auto'; got %r" % (g,))
         return float(g)
-
-    def _class_weights(self, cw, k):
-        """scikit-learn's class_weight_ of one fit (svm/_base.py:  compute_class_weight(class_weight, classes, y_train)):
-        None -> ones; dict -> by label (missing labels 1.0); 'balanced' -> n / (n_classes * bincount) on the TRAINING rows of
-        split k (k < 0: all rows)."""
-        from sklearn.utils.class_weight import compute_class_weight
-        rows = self._train_rows(k)
-        return compute_class_weight(cw, classes=self.classes, y=np.asarray(self.y)[rows])
-
-    def _set_class_weight(self, cw, refit=False):
-        if cw is None:
-            self.engine.set_class_weight(None)
-            return np.ones(len(self.classes))
-        ks = [-1] if refit else range(self.n_splits)
-        w = np.stack([self._class_weights(cw, k) for k in ks])
-        self.engine.set_class_weight(w)
-        return w[0]
 
     def costs(self):
         """Predicted SMO iterations per candidate from the library's own model (gs_svc_predicted_iterations: the one
@@ -496,8 +496,6 @@ class LogRegPlan(_Plan):
         if p.get("penalty", "l2") not in ("l2", "deprecated") or p.get("l1_ratio") not in (None, 0, 0.0):
             raise NotImplementedError("LogisticRegression penalty=%r, l1_ratio=%r has no CUDA path (only the L2 penalty does)"
                                       % (p.get("penalty"), p.get("l1_ratio")))
-        if p.get("class_weight") is not None:
-            raise NotImplementedError("LogisticRegression class_weight is not supported by the CUDA path")
         if not (isinstance(p["C"], numbers.Real) and p["C"] > 0):
             raise ValueError("C must be a positive number; got %r" % (p["C"],))
 
@@ -508,12 +506,15 @@ class LogRegPlan(_Plan):
         for j, ci in enumerate(my):
             p = self._base_params(self.cands[ci])
             self._check(p)
-            groups.setdefault((float(p["tol"]), int(p["max_iter"]), bool(p["fit_intercept"])), []).append((j, float(p["C"])))
+            cw = p.get("class_weight")
+            cwk = None if cw is None else (cw if isinstance(cw, str) else tuple(sorted(cw.items())))
+            groups.setdefault((float(p["tol"]), int(p["max_iter"]), bool(p["fit_intercept"]), cwk), []).append((j, float(p["C"]), cw))
         prof = {}
-        for (tol, mi, fi), items in groups.items():
-            idx = [j for j, _ in items]
+        for (tol, mi, fi, _cwk), items in groups.items():
+            idx = [j for j, _, _ in items]
+            self._set_class_weight(items[0][2])
             self.engine.set_scoring(self.score_kind, self.score_pos)
-            r = self.engine.logreg([c for _, c in items], tol=tol, max_iter=mi, fit_intercept=fi,
+            r = self.engine.logreg([c for _, c, _ in items], tol=tol, max_iter=mi, fit_intercept=fi,
                                    return_train=return_train)
             for key in ("test", "fit_ms", "score_ms"):
                 res[key][idx] = r[key]
@@ -521,13 +522,16 @@ class LogRegPlan(_Plan):
                 res["train"][idx] = r["train"]
             for k, v in self.engine.profile().items():
                 prof[k] = prof.get(k, 0) + v
+        self.engine.set_class_weight(None)
         self._prof = prof
         return self._finish(res, return_train, error_score, len(my))
 
     def refit(self, best_params):
         p = self._base_params(best_params)
         self._check(p)
+        self._set_class_weight(p.get("class_weight"), refit=True)
         w, b, it = self.engine.logreg_refit(p["C"], p["tol"], p["max_iter"], p["fit_intercept"])
+        self.engine.set_class_weight(None)
         est = clone(self.estimator).set_params(**best_params)
         est.classes_ = self.classes
         est.coef_ = w.reshape(1, -1)

@@ -59,3 +59,23 @@ def test_logreg_c3_full_size_vs_golden(engine):
     r = engine.logreg([c["C"] for c in W.candidates(w)])
     assert np.mean(r["n_iter"] == g["diag"][:, :, 0].astype(np.int32)) >= 0.995
     assert np.abs(r["test"].mean(1) - g["test_scores"].mean(1)).max() <= 1e-4 + 1e-12
+
+
+def test_logreg_class_weight_vs_sklearn(engine):
+    """LogisticRegression(class_weight=...): sample_weight = class_weight_[y] multiplies the pointwise loss and gradient and
+    replaces n by the weight sum in the l2 scaling (_logistic.py); 'balanced' is recomputed from every fold's training labels."""
+    from sklearn.linear_model import LogisticRegression
+    from sklearn.model_selection import GridSearchCV as SkGrid
+    from spark_sklearn_b200 import GridSearchCV
+    w = W.make_workload("c3_small")
+    X, y = w["X"], w["y"].copy()
+    y[:900] = 0                                                     # unbalanced
+    grid = {"C": [1e-2, 1.0], "class_weight": [None, "balanced", {0: 1.0, 1: 3.0}]}
+    a = GridSearchCV(None, LogisticRegression(), grid, cv=5).fit(X, y)
+    b = SkGrid(LogisticRegression(), grid, cv=5, return_train_score=True).fit(X, y)
+    assert np.abs(a.cv_results_["mean_test_score"] - b.cv_results_["mean_test_score"]).max() <= 7.5e-4      # <= 3 flips / 4000
+    assert np.abs(a.cv_results_["mean_train_score"] - b.cv_results_["mean_train_score"]).max() <= 7.5e-4
+    assert a.best_params_ == b.best_params_
+    ca, cb = a.best_estimator_.coef_, b.best_estimator_.coef_
+    assert np.abs(ca - cb).max() <= 2e-4 * np.abs(cb).max()
+    assert np.mean(a.predict(X) != b.predict(X)) <= 1e-3
