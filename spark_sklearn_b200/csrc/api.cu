@@ -524,6 +524,7 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
     std::vector<double> task_fit_ms(n_tasks, 0.0);
     std::vector<int> all_counts((size_t)n_tasks * 4, 0);
     std::vector<double> task_score((size_t)n_tasks * 2, 0.0);         // non-default scorers: test, train
+    std::vector<char> task_bad(n_tasks, 0);
     std::vector<int> class_counts;
     std::vector<unsigned long long> score_raw;
     if (!refit && h->score_kind != GS_SCORE_DEFAULT) {
@@ -799,7 +800,9 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
             total_iter += info[(size_t)q * 4];
             // two gathered K rows of the problem's (initially full) active set per iteration
             solve_bytes += (double)info[(size_t)q * 4] * 2.0 * probs[q].l * 4.0;
-            if (!std::isfinite(rho[q])) { gs_set_error(h, "gs_svc: non-finite intercept"); return GS_ERR_NUMERIC; }
+            // a task whose solve went non-finite scores NaN; the caller applies error_score to THAT task only
+            // (reference base_search.py:69,87: _fit_and_score(..., error_score) fills per task)
+            if (!std::isfinite(rho[q])) { if (refit) { gs_set_error(h, "gs_svc_refit: non-finite intercept"); return GS_ERR_NUMERIC; } task_bad[t] = 1; }
         }
         if (getenv("B200GS_SMO_PROF") && atoi(getenv("B200GS_SMO_PROF"))) {
             int qmax = 0;
@@ -862,6 +865,7 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
                 test_scores[t] = task_score[(size_t)t * 2];
                 if (train_scores) train_scores[t] = task_score[(size_t)t * 2 + 1];
             }
+            if (task_bad[t]) { test_scores[t] = NAN; if (train_scores) train_scores[t] = NAN; }
             if (n_iter) n_iter[t] = task_iter[t];
             if (n_sv) n_sv[t] = task_sv[t];
             if (fit_ms) fit_ms[t] = (float)task_fit_ms[t];
