@@ -61,7 +61,8 @@ int gs_version(void);
  * islice(cv.split(X, y, groups))) for splitters whose test sets overlap or whose training set is not the complement of the
  * test set (ShuffleSplit, RepeatedKFold, PredefinedSplit with -1).  Call after gs_set_data (whose fold ids may all be -1).
  * test_mask / train_mask: [n][2] uint64, bit k of word k/64 = row belongs to the test / training set of split k; a row may be
- * in neither.  gs_svc and gs_logreg honour the masks; gs_ridge needs gs_set_data's fold partition. */
+ * in neither.  gs_svc, gs_logreg and gs_ridge honour the masks (gs_ridge then contracts one Gram per training / test row
+ * list of a split instead of the fold Grams T - G_fold of a partition). */
 int gs_set_splits(gs_handle *h, const uint64_t *test_mask, const uint64_t *train_mask, int32_t n_splits);
 
 /* Class weights of the following gs_svc / gs_svc_refit calls: the C of a training row is C x w[class of the row].
@@ -83,7 +84,7 @@ enum {
     GS_SCORE_F1_MACRO = 6, GS_SCORE_F1_MICRO = 7, GS_SCORE_F1_WEIGHTED = 8,
     GS_SCORE_NEG_MSE = 16, GS_SCORE_NEG_RMSE = 17                          /* Ridge                         */
 };
-int gs_set_scoring(gs_handle *h, int32_t kind, int32_t pos_class);
+int gs_set_scoring(gs_handle *h, int32_t kind, int32_t pos_class);   /* gs_set_data resets scoring and class weights to their defaults */
 
 /* Number of sm_100 GPUs this process can drive (0: none).  Replaces: the executor count Spark reports to the driver
  * (reference base_search.py:62 sc.parallelize(..., len(tasks)) leaves placement to Spark); the in-process scheduler of

@@ -203,6 +203,8 @@ int gs_set_data(gs_handle *h, const void *X, int32_t x_dtype, int64_t n, int64_t
     GS_CUDA(cudaSetDevice(h->device));
     h->n = n; h->d = d; h->n_splits = n_splits; h->x_dtype = x_dtype;
     h->classification = y_class != nullptr;
+    h->score_kind = GS_SCORE_DEFAULT; h->score_pos = 1;      // a new dataset starts from the estimator's own score and unit class weights
+    h->class_w.clear(); h->class_w_sets = 0;
     h->perm.resize(n);
     std::iota(h->perm.begin(), h->perm.end(), 0);
     h->n_classes = 0;

@@ -45,10 +45,11 @@ __global__ void column_means_kernel(const float *__restrict__ X, const float *__
     }
 }
 
-// Zt[j][poff[b] + r] = X[row][j] - shift[j] (j<d) | y[row] - shift[d] (j==d) | 1 (j==d+1); rows of block b are row0[b] .. row0[b]+cnt[b]
+// Zt[j][poff[b] + r] = X[row][j] - shift[j] (j<d) | y[row] - shift[d] (j==d) | 1 (j==d+1); rows of block b are row0[b] .. row0[b]+cnt[b],
+// or rowidx[row0[b] .. row0[b]+cnt[b]) when the blocks are row lists (general splits: the training / test rows of a split)
 __global__ void build_zt_kernel(const float *__restrict__ X, const float *__restrict__ y, const float *__restrict__ shift, int d, int n_blocks,
                                 const int *__restrict__ row0, const int *__restrict__ cnt, const int *__restrict__ poff,
-                                float *__restrict__ Zt, int64_t ldz)
+                                const int *__restrict__ rowidx, float *__restrict__ Zt, int64_t ldz)
 {
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
@@ -59,7 +60,7 @@ __global__ void build_zt_kernel(const float *__restrict__ X, const float *__rest
         const int r = r0 + threadIdx.y, j = j0 + threadIdx.x;
         float v = 0.f;
         if (r < cnt[b]) {
-            const int row = row0[b] + r;
+            const int row = rowidx ? rowidx[row0[b] + r] : row0[b] + r;
             if (j < d) v = X[(size_t)row * d + j] - shift[j];
             else if (j == d) v = y[row] - shift[d];
             else if (j == d + 1) v = 1.f;
@@ -90,16 +91,22 @@ __global__ void sum_grams_kernel(const float *__restrict__ Gq, const int *__rest
     }
 }
 
-// Per system-group g (a fold, or "all rows" for the refit): training statistics S = T - G_test, centred normal matrix
+// Per system-group g (a split, or "all rows" for the refit): training statistics S = T - G_test (test folds that
+// partition the rows) or S = G_train (general splits: the split's own training block), centred normal matrix
 // A (float32, [dp][dp], zero padded) and rhs (float32 [dp]); means kept in float64 for the intercept.
 __global__ void build_systems_kernel(const double *__restrict__ T, const float *__restrict__ G, const int *__restrict__ test_block,
+                                     const int *__restrict__ train_block,
                                      int d, int Dp, int dp, int fit_intercept, float *__restrict__ A, float *__restrict__ rhs,
                                      double *__restrict__ means /* [groups][dp + 2]: xbar[0..d), ybar, n_train */)
 {
     const int g = blockIdx.z;
-    const int tb = test_block[g];
+    const int tb = test_block[g], trb = train_block[g];
     const float *Gt = tb >= 0 ? G + (size_t)tb * Dp * Dp : nullptr;
-    auto S = [&](int a, int b) -> double { return T[(size_t)a * Dp + b] - (Gt ? (double)Gt[(size_t)a * Dp + b] : 0.0); };
+    const float *Gtr = trb >= 0 ? G + (size_t)trb * Dp * Dp : nullptr;
+    auto S = [&](int a, int b) -> double {
+        if (Gtr) return (double)Gtr[(size_t)a * Dp + b];
+        return T[(size_t)a * Dp + b] - (Gt ? (double)Gt[(size_t)a * Dp + b] : 0.0);
+    };
     const double ntr = S(d + 1, d + 1);
     const double ybar = fit_intercept ? S(d, d + 1) / ntr : 0.0;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
@@ -220,42 +227,95 @@ __global__ void cg_step_kernel(const float *__restrict__ Q, const double *__rest
     }
 }
 
-// R^2 of system s on its test block and on its training rows, from Gram statistics (float64 quadratic forms)
+// Quadratic forms w_s^T M w_s of every system s against its test-block Gram (z = 0) and its training statistics (z = 1):
+// a float64 tile product C[s][j] = sum_l w_s[l] M[l][j] (M symmetric, so row l is read along j: coalesced) with the
+// row-dot against w_s[j] fused into the epilogue.  One CTA = 64 systems x 64 columns j; the partial of column tile jt
+// goes to part[s][z][jt] and is summed in a fixed order by ridge_r2_kernel (deterministic, no atomics).
+constexpr int QT = 64, QL = 16;
+__global__ void __launch_bounds__(256) ridge_quad_kernel(const float *__restrict__ Xs, const double *__restrict__ T,
+                                                         const float *__restrict__ G, const int *__restrict__ test_block,
+                                                         const int *__restrict__ train_block, int n_cand, int d, int Dp, int dp,
+                                                         int njt, double *__restrict__ part)
+{
+    __shared__ double Ws[QL][QT + 1], Ms[QL][QT + 1];
+    const int g = blockIdx.y, z = blockIdx.z;
+    const int s0 = (blockIdx.x / njt) * QT, jt = blockIdx.x % njt, j0 = jt * QT;
+    const int tb = test_block[g], trb = train_block[g];
+    const float *Mf = z == 0 ? G + (size_t)tb * Dp * Dp : (trb >= 0 ? G + (size_t)trb * Dp * Dp : nullptr);   // else T (float64)
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int mj = threadIdx.x & 63, ml = threadIdx.x >> 6;
+    const float *Wg = Xs + (size_t)g * n_cand * dp;
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc[i][k] = 0.0;
+    for (int l0 = 0; l0 < d; l0 += QL) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int sl = ty + 16 * q, c = s0 + sl, l = l0 + tx;
+            Ws[tx][sl] = (c < n_cand && l < d) ? (double)Wg[(size_t)c * dp + l] : 0.0;
+            const int lm = l0 + ml + 4 * q, j = j0 + mj;                     // lm < Dp: d + 2 <= Dp and QL | Dp
+            double v = 0.0;
+            if (j < d && lm < d) v = Mf ? (double)Mf[(size_t)lm * Dp + j] : T[(size_t)lm * Dp + j];
+            Ms[ml + 4 * q][mj] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int l = 0; l < QL; l++) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { a[i] = Ws[l][ty + 16 * i]; b[i] = Ms[l][tx + 16 * i]; }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) acc[i][k] += a[i] * b[k];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int c = s0 + ty + 16 * i;
+        double v = 0.0;
+        if (c < n_cand) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int j = j0 + tx + 16 * k;
+                if (j < d) v += acc[i][k] * (double)Wg[(size_t)c * dp + j];
+            }
+        }
+#pragma unroll
+        for (int m = 8; m; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+        if (tx == 0 && c < n_cand) part[(((size_t)g * n_cand + c) * 2 + z) * njt + jt] = v;
+    }
+}
+
+// R^2 (or -MSE / -RMSE) of system s on its test block and on its training rows, from Gram statistics in float64: the
+// quadratic forms come from ridge_quad_kernel, the linear terms (rows d and d+1 of the symmetric Grams) are read here.
 __global__ void ridge_r2_kernel(const float *__restrict__ Xs, const double *__restrict__ T, const float *__restrict__ G,
-                                const int *__restrict__ test_block, const double *__restrict__ means, int n_cand, int d, int Dp,
+                                const int *__restrict__ test_block, const int *__restrict__ train_block,
+                                const double *__restrict__ means, const double *__restrict__ part, int njt, int n_cand, int d, int Dp,
                                 int dp, int fit_intercept, int kind, double *__restrict__ out /* [systems][2] */)
 {
     __shared__ double sh[32];
-    extern __shared__ double wsh[];                               // w in float64
     const int s = blockIdx.x, g = s / n_cand;
-    const int tb = test_block[g];
+    const int tb = test_block[g], trb = train_block[g];
     const float *Gk = G + (size_t)tb * Dp * Dp;
-    for (int j = threadIdx.x; j < d; j += blockDim.x) wsh[j] = (double)Xs[(size_t)s * dp + j];
-    __syncthreads();
-    // quadratic forms w^T Gk w and w^T T w: one warp per row, lanes along the row (coalesced)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    double qk = 0, qt = 0;
-    for (int j = warp; j < d; j += nw) {
-        double ak = 0, at = 0;
-        for (int l = lane; l < d; l += 32) {
-            const double wl = wsh[l];
-            ak += (double)Gk[(size_t)j * Dp + l] * wl;
-            at += T[(size_t)j * Dp + l] * wl;
-        }
-        qk += ak * wsh[j]; qt += at * wsh[j];
-    }
+    const float *Gtr = trb >= 0 ? G + (size_t)trb * Dp * Dp : nullptr;      // general splits: own training block; else T - Gk
+    auto Tr = [&](int a, int b) -> double { return Gtr ? (double)Gtr[(size_t)a * Dp + b] : T[(size_t)a * Dp + b]; };
     double wxy_k = 0, wxy_t = 0, ws_k = 0, ws_t = 0, xbw = 0;
     for (int j = threadIdx.x; j < d; j += blockDim.x) {
-        const double w = wsh[j];
-        wxy_k += w * (double)Gk[(size_t)j * Dp + d]; wxy_t += w * T[(size_t)j * Dp + d];
-        ws_k += w * (double)Gk[(size_t)j * Dp + d + 1]; ws_t += w * T[(size_t)j * Dp + d + 1];
+        const double w = (double)Xs[(size_t)s * dp + j];
+        wxy_k += w * (double)Gk[(size_t)d * Dp + j]; wxy_t += w * Tr(d, j);
+        ws_k += w * (double)Gk[(size_t)(d + 1) * Dp + j]; ws_t += w * Tr(d + 1, j);
         xbw += w * means[(size_t)g * (dp + 2) + j];
     }
-    qk = block_sum(qk, sh); qt = block_sum(qt, sh);
     wxy_k = block_sum(wxy_k, sh); wxy_t = block_sum(wxy_t, sh);
     ws_k = block_sum(ws_k, sh); ws_t = block_sum(ws_t, sh);
     xbw = block_sum(xbw, sh);
     if (threadIdx.x == 0) {
+        double qk = 0, qt = 0;
+        for (int t = 0; t < njt; t++) { qk += part[((size_t)s * 2) * njt + t]; qt += part[((size_t)s * 2 + 1) * njt + t]; }
         const double b0 = fit_intercept ? means[(size_t)g * (dp + 2) + dp] - xbw : 0.0;
         auto r2 = [&](double yy, double ys, double nn, double q, double wxy, double ws) {
             const double res = yy - 2 * wxy - 2 * b0 * ys + q + 2 * b0 * ws + nn * b0 * b0;
@@ -265,9 +325,10 @@ __global__ void ridge_r2_kernel(const float *__restrict__ Xs, const double *__re
             return 1.0 - res / tot;
         };
         const double yy_k = Gk[(size_t)d * Dp + d], ys_k = Gk[(size_t)d * Dp + d + 1], n_k = Gk[(size_t)(d + 1) * Dp + d + 1];
-        const double yy_t = T[(size_t)d * Dp + d], ys_t = T[(size_t)d * Dp + d + 1], n_t = T[(size_t)(d + 1) * Dp + d + 1];
+        const double yy_t = Tr(d, d), ys_t = Tr(d, d + 1), n_t = Tr(d + 1, d + 1);
         out[(size_t)s * 2] = r2(yy_k, ys_k, n_k, qk, wxy_k, ws_k);
-        out[(size_t)s * 2 + 1] = r2(yy_t - yy_k, ys_t - ys_k, n_t - n_k, qt - qk, wxy_t - wxy_k, ws_t - ws_k);
+        out[(size_t)s * 2 + 1] = Gtr ? r2(yy_t, ys_t, n_t, qt, wxy_t, ws_t)
+                                     : r2(yy_t - yy_k, ys_t - ys_k, n_t - n_k, qt - qk, wxy_t - wxy_k, ws_t - ws_k);
     }
 }
 
@@ -281,11 +342,6 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     if (h->n == 0) { gs_set_error(h, "gs_ridge: no dataset (call gs_set_data first)"); return GS_ERR_NO_DATA; }
     if (h->classification) { gs_set_error(h, "gs_ridge: dataset has no regression targets"); return GS_ERR_ARG; }
     if (n_cand <= 0 || !alpha) { gs_set_error(h, "gs_ridge: bad arguments"); return GS_ERR_ARG; }
-    if (!refit && !h->partition) {
-        gs_set_error(h, "gs_ridge: the fold-Gram algorithm needs a partition of the rows into test folds (gs_set_data fold ids); "
-                        "general splits (gs_set_splits) are supported by gs_svc and gs_logreg");
-        return GS_ERR_UNSUPPORTED;
-    }
     for (int c = 0; c < n_cand; c++)
         if (!(alpha[c] >= 0)) { gs_set_error(h, "gs_ridge: alpha must be >= 0"); return GS_ERR_ARG; }
     if (h->score_kind != GS_SCORE_DEFAULT && h->score_kind != GS_SCORE_NEG_MSE && h->score_kind != GS_SCORE_NEG_RMSE) {
@@ -297,9 +353,25 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     const int D = d + 2, Dp = (D + 31) & ~31, dp = (d + 31) & ~31;
     if (dp > 8 * 256) { gs_set_error(h, "gs_ridge: more than 2048 features is not supported by the CG kernels"); return GS_ERR_UNSUPPORTED; }
 
-    // row blocks (rows are sorted by fold; fold -1 rows, never tested, form a trailing block)
-    std::vector<int> row0, cnt;
-    {
+    // row blocks.  Test folds that partition the rows: one contiguous block per fold (rows are sorted by fold; fold -1
+    // rows, never tested, form a trailing block), training statistics = T - G_fold.  General splits (gs_set_splits):
+    // blocks 2k / 2k+1 are the row lists of split k's training / test set, each contracted on its own.
+    const bool lists = !h->partition;
+    std::vector<int> row0, cnt, rowidx;
+    if (lists && refit) { row0.push_back(0); cnt.push_back(n); }
+    else if (lists) {
+        for (int k = 0; k < ns; k++)
+            for (int side = 0; side < 2; side++) {
+                row0.push_back((int)rowidx.size());
+                for (int r = 0; r < n; r++)
+                    if (side == 0 ? h->is_train(r, k) : h->is_test(r, k)) rowidx.push_back(r);
+                cnt.push_back((int)rowidx.size() - row0.back());
+                if (cnt.back() == 0) {
+                    gs_set_error(h, std::string("gs_ridge: split ") + std::to_string(k) + " has an empty " + (side ? "test" : "training") + " set");
+                    return GS_ERR_ARG;
+                }
+            }
+    } else {
         int r = 0;
         for (int k = 0; k < ns; k++) {
             int c = 0;
@@ -337,7 +409,7 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     GS_CUDA(bA.reserve((size_t)groups * dp * dp * 4 * 3 + (size_t)groups * dp * 4));
     GS_CUDA(bV.reserve((size_t)nsys * dp * 4 * (6 + (size_t)((dp + TC_KCHUNK - 1) / TC_KCHUNK))));
     const int nkc = (dp + TC_KCHUNK - 1) / TC_KCHUNK;                          // K-chunks of the CG product
-    GS_CUDA(bMeta.reserve((size_t)(nq * 3 + nb + 1 + groups) * 4 + (size_t)(nq + groups * nkc) * sizeof(TcBatch) + (size_t)nsys * 4 + 128));
+    GS_CUDA(bMeta.reserve((size_t)(nq * 3 + nb + 1 + 2 * groups) * 4 + (size_t)(nq + groups * nkc) * sizeof(TcBatch) + (size_t)nsys * 4 + rowidx.size() * 4 + 128));
     double *dT = bMisc.as<double>();
     double *dMeans = dT + (size_t)Dp * Dp;
     double *dRR = dMeans + (size_t)groups * (dp + 2), *dBB = dRR + nsys, *dOut = dBB + nsys, *dAlpha = dOut + 2 * (size_t)nsys;
@@ -347,19 +419,26 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     float *dX = bV.as<float>(), *dR = dX + (size_t)nsys * dp, *dP = dR + (size_t)nsys * dp, *dPh = dP + (size_t)nsys * dp,
           *dPl = dPh + (size_t)nsys * dp, *dQ = dPl + (size_t)nsys * dp, *dQp = dQ + (size_t)nsys * dp;
     float *dGq = bG.as<float>() + (size_t)nb * Dp * Dp;
-    int *dRow0 = bMeta.as<int>(), *dCnt = dRow0 + nq, *dPoff = dCnt + nq, *dQs = dPoff + nq, *dTestBlock = dQs + nb + 1;
-    int *dDone = dTestBlock + groups;
+    int *dRow0 = bMeta.as<int>(), *dCnt = dRow0 + nq, *dPoff = dCnt + nq, *dQs = dPoff + nq, *dTestBlock = dQs + nb + 1,
+        *dTrainBlock = dTestBlock + groups;
+    int *dDone = dTrainBlock + groups;
     int *dOpen = dDone + nsys;
     TcBatch *dBatchG = reinterpret_cast<TcBatch *>(((uintptr_t)(dOpen + 4) + 15) & ~(uintptr_t)15);
     TcBatch *dBatchCG = dBatchG + nq;
+    int *dRowIdx = lists && !rowidx.empty() ? reinterpret_cast<int *>(dBatchCG + (size_t)groups * nkc) : nullptr;
 
-    std::vector<int> testBlock(groups);
-    for (int g = 0; g < groups; g++) testBlock[g] = refit ? -1 : g;
+    std::vector<int> testBlock(groups), trainBlock(groups);
+    for (int g = 0; g < groups; g++) {
+        testBlock[g] = refit ? -1 : (lists ? 2 * g + 1 : g);
+        trainBlock[g] = (!refit && lists) ? 2 * g : -1;
+    }
     GS_CUDA(cudaMemcpyAsync(dRow0, crow0.data(), nq * 4, cudaMemcpyHostToDevice, st));
     GS_CUDA(cudaMemcpyAsync(dCnt, ccnt.data(), nq * 4, cudaMemcpyHostToDevice, st));
     GS_CUDA(cudaMemcpyAsync(dPoff, poff.data(), nq * 4, cudaMemcpyHostToDevice, st));
     GS_CUDA(cudaMemcpyAsync(dQs, qs.data(), (nb + 1) * 4, cudaMemcpyHostToDevice, st));
     GS_CUDA(cudaMemcpyAsync(dTestBlock, testBlock.data(), groups * 4, cudaMemcpyHostToDevice, st));
+    GS_CUDA(cudaMemcpyAsync(dTrainBlock, trainBlock.data(), groups * 4, cudaMemcpyHostToDevice, st));
+    if (dRowIdx) GS_CUDA(cudaMemcpyAsync(dRowIdx, rowidx.data(), rowidx.size() * 4, cudaMemcpyHostToDevice, st));
     GS_CUDA(cudaMemcpyAsync(dAlpha, alpha, (size_t)n_cand * 8, cudaMemcpyHostToDevice, st));
     std::vector<TcBatch> bg(nq), bc;
     for (int q = 0; q < nq; q++) bg[q] = TcBatch{0, 0, poff[q], poff[q + 1], dGq + (size_t)q * Dp * Dp, (int64_t)Dp};
@@ -378,7 +457,7 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
         if (fit_intercept) column_means_kernel<<<(d + 1 + 31) / 32, dim3(32, 32), 0, st>>>(h->dX.as<float>(), h->dYt.as<float>(), n, d, dShift);
         else GS_CUDA(cudaMemsetAsync(dShift, 0, (size_t)(d + 1) * 4, st));
         GS_CUDA(cudaGetLastError());
-        build_zt_kernel<<<grid, block, 0, st>>>(h->dX.as<float>(), h->dYt.as<float>(), dShift, d, nq, dRow0, dCnt, dPoff, bZ.as<float>(), ldz);
+        build_zt_kernel<<<grid, block, 0, st>>>(h->dX.as<float>(), h->dYt.as<float>(), dShift, d, nq, dRow0, dCnt, dPoff, dRowIdx, bZ.as<float>(), ldz);
         GS_CUDA(cudaGetLastError());
     }
     GS_CUDA(launch_split_tf32(bZ.as<float>(), bZh.as<float>(), bZl.as<float>(), (size_t)Dp * ldz, st));
@@ -396,7 +475,7 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     // ---- 2. per-group centred systems ----
     {
         dim3 block(32, 8), grid((dp + 31) / 32, (dp + 7) / 8, groups);
-        build_systems_kernel<<<grid, block, 0, st>>>(dT, bG.as<float>(), dTestBlock, d, Dp, dp, fit_intercept, dA, dRhs, dMeans);
+        build_systems_kernel<<<grid, block, 0, st>>>(dT, bG.as<float>(), dTestBlock, dTrainBlock, d, Dp, dp, fit_intercept, dA, dRhs, dMeans);
         GS_CUDA(cudaGetLastError());
     }
     GS_CUDA(launch_split_tf32(dA, dAh, dAl, (size_t)groups * dp * dp, st));
@@ -435,8 +514,16 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
 
     // ---- 4. scores / coefficients ----
     if (!refit) {
-        ridge_r2_kernel<<<nsys, 256, (size_t)d * 8, st>>>(dX, dT, bG.as<float>(), dTestBlock, dMeans, n_cand, d, Dp, dp, fit_intercept, h->score_kind, dOut);
+        const int njt = (d + QT - 1) / QT;
+        GS_CUDA(h->dWork[8].reserve((size_t)nsys * 2 * njt * 8));
+        double *dPart = h->dWork[8].as<double>();
+        ridge_quad_kernel<<<dim3(((n_cand + QT - 1) / QT) * njt, groups, 2), 256, 0, st>>>(dX, dT, bG.as<float>(), dTestBlock, dTrainBlock,
+                                                                                          n_cand, d, Dp, dp, njt, dPart);
         GS_CUDA(cudaGetLastError());
+        ridge_r2_kernel<<<nsys, 128, 0, st>>>(dX, dT, bG.as<float>(), dTestBlock, dTrainBlock, dMeans, dPart, njt, n_cand, d, Dp, dp,
+                                              fit_intercept, h->score_kind, dOut);
+        GS_CUDA(cudaGetLastError());
+        launches++;
         launches++;
         std::vector<double> out((size_t)nsys * 2);
         GS_CUDA(cudaMemcpyAsync(out.data(), dOut, out.size() * 8, cudaMemcpyDeviceToHost, st));
@@ -478,8 +565,7 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     pf.ms_total = tmr->total; pf.ms_gram = tmr->gram; pf.ms_solve = tmr->solve; pf.ms_score = tmr->score;
     pf.launches = launches;
     pf.smo_iterations = it;                                        // CG iterations
-    pf.gram_flops = 2.0 * (double)n * D * D;
-    pf.gram_bytes = (double)n * D * 4 + (double)nq * D * D * 4;
+    { double rows = 0; for (int c : cnt) rows += c; pf.gram_flops = 2.0 * rows * D * D; pf.gram_bytes = rows * D * 4 + (double)nq * D * D * 4; }
     pf.solve_bytes = 0;
     pf.ms_tensor = h->tt.collect(); pf.tensor_flops = h->tt.flops;
     return GS_OK;

@@ -85,9 +85,15 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
+_device_count = None
+
+
 def device_count():
-    """sm_100 GPUs visible to this process (0 without a GPU or without the library's CUDA runtime)."""
-    return int(load_library().gs_device_count())
+    """sm_100 GPUs visible to this process (0 without a GPU or without the library's CUDA runtime); asked once per process."""
+    global _device_count
+    if _device_count is None:
+        _device_count = int(load_library().gs_device_count())
+    return _device_count
 
 
 class Engine:

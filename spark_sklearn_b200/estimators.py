@@ -32,12 +32,17 @@ def fold_ids_from_splits(splits, n):
     if len(splits) > 127:
         raise NotImplementedError("more than 127 CV splits")
     fold_id = np.full(n, -1, np.int8)
+    seen = np.zeros(n, bool)
     for k, (tr, te) in enumerate(splits):
         te = np.asarray(te)
         if np.any(fold_id[te] != -1):
             raise NotImplementedError("CV splitter with overlapping test sets needs split masks")
         fold_id[te] = k
-        if len(tr) + len(te) != n or len(np.intersect1d(tr, te)):
+        # train == complement of test  <=>  sizes add up to n, no row twice, none of them a test row
+        seen[:] = False
+        seen[te] = True
+        seen[np.asarray(tr)] = True
+        if len(tr) + len(te) != n or not seen.all():
             raise NotImplementedError("CV splitter whose train set is not the complement of its test set needs split masks")
     return fold_id
 
@@ -203,7 +208,10 @@ class _Plan:
         pass
 
     def _base_params(self, cand):
-        p = self.estimator.get_params(deep=False)
+        base = getattr(self, "_est_params", None)
+        if base is None:                                  # the search's estimator is fixed: introspect it once, not per candidate
+            base = self._est_params = self.estimator.get_params(deep=False)
+        p = dict(base)
         unknown = set(cand) - set(p)
         if unknown:
             raise ValueError("Invalid parameter(s) %s for estimator %s" % (sorted(unknown), self.estimator))
@@ -411,7 +419,7 @@ class RidgeAdapter:
 
 class RidgePlan(_Plan):
     scorers = REGRESSION_SCORERS
-    general_splits = False         # fold Grams: T - G_k needs test folds that partition the rows
+    general_splits = True          # partitions: T - G_fold; other splitters: one Gram per training / test row list
 
     def __init__(self, estimator, cands, X, y, fold_id, n_splits, device=None):
         super().__init__(estimator, cands, X, y, fold_id, n_splits, device)

@@ -56,10 +56,32 @@ def test_logreg_shuffle_split(engine):
     assert np.abs(a.cv_results_["mean_train_score"] - b.cv_results_["mean_train_score"]).max() <= 1.5e-3
 
 
-def test_ridge_needs_a_partition(engine):
+@pytest.mark.parametrize("name", ["shuffle", "repeated", "predefined"])
+@pytest.mark.parametrize("scoring", [None, "neg_mean_squared_error"])
+def test_ridge_general_splitters(engine, name, scoring):
+    """Ridge on splitters whose test sets do not partition the rows: one Gram per training / test row list (linear.cu)."""
     from sklearn.linear_model import Ridge
-    from sklearn.model_selection import ShuffleSplit
+    from sklearn.model_selection import GridSearchCV as SkGrid, PredefinedSplit, RepeatedKFold, ShuffleSplit
     from spark_sklearn_b200 import GridSearchCV
     w = W.make_workload("c5_small")
-    with pytest.raises(NotImplementedError):
-        GridSearchCV(None, Ridge(), {"alpha": [1.0]}, cv=ShuffleSplit(3, test_size=0.3, random_state=0)).fit(w["X"], w["y"])
+    X, y = w["X"], w["y"]
+    n = len(y)
+    pre = np.arange(n) % 4
+    pre[: n // 5] = -1
+    cv = {"shuffle": ShuffleSplit(4, test_size=0.25, train_size=0.6, random_state=0),
+          "repeated": RepeatedKFold(n_splits=3, n_repeats=2, random_state=1),
+          "predefined": PredefinedSplit(pre)}[name]
+    grid = {"alpha": [1e-2, 1.0, 100.0], "fit_intercept": [True, False]}
+    a = GridSearchCV(None, Ridge(), grid, cv=cv, iid=False, scoring=scoring).fit(X, y)
+    b = SkGrid(Ridge(), grid, cv=cv, return_train_score=True, scoring=scoring).fit(X, y)
+    assert a.n_splits_ == b.n_splits_
+    for k in range(b.n_splits_):
+        for part in ("test", "train"):
+            key = "split%d_%s_score" % (k, part)
+            # R^2: 2e-5 absolute.  MSE from Gram statistics carries ~1e-6 * tot / res relative error (a difference of quadratic
+            # forms that agree to ~1e-6): 3e-3 relative, as in test_gpu_scoring.py
+            rtol, atol = (3e-3, 0) if scoring else (2e-4, 2e-5)
+            np.testing.assert_allclose(a.cv_results_[key], b.cv_results_[key], rtol=rtol, atol=atol, err_msg=key)
+    assert a.best_params_ == b.best_params_
+    np.testing.assert_allclose(a.best_estimator_.coef_, b.best_estimator_.coef_, rtol=2e-3, atol=2e-4)
+    np.testing.assert_allclose(a.predict(X), b.predict(X), rtol=2e-3, atol=2e-3 * np.abs(y).max())
