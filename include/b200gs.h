@@ -139,6 +139,23 @@ int gs_ridge(gs_handle *h, int32_t n_cand, const double *alpha, int32_t fit_inte
 int gs_ridge_refit(gs_handle *h, double alpha, int32_t fit_intercept, double *coef_out);
 
 /*
+ * ElasticNet / Lasso (replaces ElasticNet.fit/score and Lasso.fit/score -- the estimator of the reference's own search tests,
+ * python/spark_sklearn/tests/test_search_2.py:69-119: sklearn linear_model/_coordinate_descent.py:1170-1280 fit, :781-782
+ * penalty scaling, _cd_fast.pyx:243-506 enet_coordinate_descent, :162-240 duality gap).  alpha[n_cand], l1_ratio[n_cand]
+ * (1.0 = Lasso); tol / max_iter as scikit-learn's; selection='cyclic', positive=False.  Same fold Grams, scorers and split
+ * handling as gs_ridge; the solve is cyclic coordinate descent with scikit-learn's stopping rule and gap-safe screening, run
+ * in the Gram domain (one warp per (candidate, split)).  n_iter (may be NULL): [n_cand][n_splits] sweeps.  No more than 1024
+ * features.  A fit that stops at max_iter is returned as it is (scikit-learn: ConvergenceWarning).
+ * gs_enet_refit: all rows -> [d] weights + intercept at [d]; n_iter / dual_gap (may be NULL): sweeps and the duality gap
+ * (scikit-learn's dual_gap_ = gap / n_samples).
+ */
+int gs_enet(gs_handle *h, int32_t n_cand, const double *alpha, const double *l1_ratio, int32_t fit_intercept, double tol,
+            int32_t max_iter, uint32_t flags, double *test_scores, double *train_scores, int32_t *n_iter, float *fit_ms,
+            float *score_ms);
+int gs_enet_refit(gs_handle *h, double alpha, double l1_ratio, int32_t fit_intercept, double tol, int32_t max_iter,
+                  double *coef_out, int32_t *n_iter, double *dual_gap);
+
+/*
  * LogisticRegression (binary, L2, lbfgs; replaces sklearn linear_model/_logistic.py:219
  * _logistic_regression_path, objective _linear_loss.py:47-64).  C[n_cand].  Scores are accuracy.
  */

@@ -9,6 +9,8 @@ reference, pinned there to >=0.18.1,<0.20 -- python/setup.py:22).
 * SVC: ``svc_oracle.c`` (C restatement of SK/svm/src/libsvm/svm.cpp) driven from here for
   class grouping / one-vs-one / voting (svm.cpp:2246-2327, 2441-2523, 2821-2904).
 * Ridge: numpy restatement of SK/linear_model/_ridge.py:215-227 (+ _base.py:113 centring).
+* Lasso / ElasticNet: numpy restatement of SK/linear_model/_cd_fast.pyx:243-506 (cyclic coordinate descent on the
+  residual, duality-gap stop, gap-safe screening) with the scaling of _coordinate_descent.py:781-782.
 * LogisticRegression: scipy L-BFGS-B on the restated objective of
   SK/linear_model/_linear_loss.py:47-64 with the options of _logistic.py:585-597.
 
@@ -206,6 +208,124 @@ def cv_scores_ridge(X, y, fold_id, n_splits, cands, fit_intercept=True):
             test[ci, k], train[ci, k] = ridge_fit_score(X, y, allrows[fold_id != k], allrows[fold_id == k],
                                                         p.get("alpha", 1.0), fit_intercept)
     return test, train
+
+
+# ------------------------------------------------------- Lasso / ElasticNet -------------
+def enet_cd(X, y, alpha, beta, tol=1e-4, max_iter=1000, do_screening=True):
+    """SK/linear_model/_cd_fast.pyx:243-506 enet_coordinate_descent (dense X, cyclic, positive=False) in the dtype of X.
+    alpha / beta = L1 / L2 penalties already scaled by n_samples.  -> (w, gap, tol * y.y, n_iter)"""
+    dt = X.dtype.type
+    n, d = X.shape
+    alpha, beta = dt(alpha), dt(beta)
+    norm2 = np.einsum("ij,ij->j", X, X, dtype=X.dtype)                # :371-373
+    w = np.zeros(d, X.dtype)
+    R = y.copy()                                                         # :403-406 (w = 0)
+    d_w_tol = dt(tol)
+    tol = dt(tol) * dt(y @ y)                                            # :409
+
+    def gap_enet():                                                      # :162-240
+        R_norm2 = dt(R @ R)
+        w_l2 = dt(w @ w) if beta > 0 else dt(0)
+        Ry = dt(R @ y)
+        XtR = (X.T @ R).astype(X.dtype)
+        if alpha == 0:
+            dn = dt(XtR @ XtR)
+            if beta == 0:
+                return dn, dn, XtR
+            return dt(R_norm2 + dt(0.5) * beta * w_l2 - Ry + dn / (2 * beta)), dn, XtR
+        XtA = (XtR - beta * w).astype(X.dtype)
+        dn = dt(np.abs(XtA).max())
+        primal = dt(0.5) * (R_norm2 + beta * w_l2) + alpha * dt(np.abs(w).sum())      # :138-159
+        scale = alpha / dn if dn > alpha else dt(1)
+        dual = dt(-0.5) * scale * scale * (R_norm2 + beta * w_l2) + scale * Ry
+        return dt(primal - dual), dn, XtA
+
+    screening = do_screening and alpha != 0                              # :391-393
+    active = np.arange(d)
+    excluded = np.zeros(d, bool)
+
+    def screen(gap, dn, XtA, first):                                     # :399-422, :473-492
+        nonlocal active, R
+        keep = []
+        for j in range(d):
+            if first and norm2[j] == 0:
+                w[j] = 0
+                excluded[j] = True
+                continue
+            if not first and excluded[j]:
+                continue
+            with np.errstate(divide="ignore", invalid="ignore"):
+                d_j = (1 - abs(XtA[j] / max(alpha, dn))) / np.sqrt(norm2[j] + beta)
+            if d_j <= np.sqrt(2 * gap) / alpha:
+                keep.append(j)
+                excluded[j] = False
+            else:
+                if w[j] != 0:
+                    R += w[j] * X[:, j]
+                    w[j] = 0
+                excluded[j] = True
+        active = np.array(keep, int)
+
+    gap, dn, XtA = gap_enet()                                            # :411-417
+    if gap <= tol:
+        return w, gap, tol, 0
+    if screening:
+        screen(gap, dn, XtA, True)
+    n_iter = 0
+    for n_iter in range(max_iter):                                       # :424
+        w_max = d_w_max = dt(0)
+        for j in active:
+            if norm2[j] == 0:
+                continue
+            w_j = w[j]
+            tmp = dt(X[:, j] @ R) + w_j * norm2[j]                       # :441
+            w[j] = np.sign(tmp) * max(abs(tmp) - alpha, 0) / (norm2[j] + beta)
+            if w[j] != w_j:
+                R += (w_j - w[j]) * X[:, j]                              # :449-451
+            d_w_max = max(d_w_max, abs(w[j] - w_j))
+            w_max = max(w_max, abs(w[j]))
+        if w_max == 0 or d_w_max / w_max <= d_w_tol or n_iter == max_iter - 1:       # :458-462
+            gap, dn, XtA = gap_enet()
+            if gap <= tol:
+                break
+            if screening:
+                screen(gap, dn, XtA, False)
+    return w, gap, tol, n_iter + 1
+
+
+def enet_fit_score(X, y, train, test, alpha, l1_ratio=1.0, fit_intercept=True, tol=1e-4, max_iter=1000):
+    """SK/linear_model/_coordinate_descent.py:1170-1280 (ElasticNet.fit: centre by the training means, penalties scaled by
+    n_samples :781-782), SK/base.py:716 (r2).  -> (test r2, train r2, n_iter)"""
+    dt = X.dtype
+    Xt, yt = X[train], y[train].astype(dt)
+    if fit_intercept:
+        xm = Xt.mean(0, dtype=np.float64).astype(dt)
+        ym = yt.mean(dtype=np.float64).astype(dt)
+        Xc, yc = Xt - xm, yt - ym
+    else:
+        Xc, yc = Xt, yt
+    n = len(train)
+    w, _gap, _tol, n_iter = enet_cd(np.asfortranarray(Xc), yc, alpha * l1_ratio * n, alpha * (1.0 - l1_ratio) * n, tol, max_iter)
+    b = (ym - xm @ w) if fit_intercept else dt.type(0)
+
+    def r2(rows):
+        yp = X[rows] @ w + b
+        yt_ = y[rows].astype(np.float64)
+        return 1.0 - ((yt_ - yp.astype(np.float64)) ** 2).sum() / ((yt_ - yt_.mean()) ** 2).sum()
+    return r2(test), r2(train), n_iter
+
+
+def cv_scores_enet(X, y, fold_id, n_splits, cands, fit_intercept=True):
+    allrows = np.arange(len(y))
+    test = np.zeros((len(cands), n_splits))
+    train = np.zeros_like(test)
+    iters = np.zeros(test.shape, int)
+    for ci, p in enumerate(cands):
+        for k in range(n_splits):
+            test[ci, k], train[ci, k], iters[ci, k] = enet_fit_score(
+                X, y, allrows[fold_id != k], allrows[fold_id == k], p.get("alpha", 1.0), p.get("l1_ratio", 1.0), fit_intercept,
+                p.get("tol", 1e-4), p.get("max_iter", 1000))
+    return test, train, iters
 
 
 # ------------------------------------------------------- LogisticRegression ------------

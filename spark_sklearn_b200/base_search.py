@@ -81,7 +81,7 @@ class B200BaseSearchCV(BaseSearchCV):
                 "scoring=%r has no fused CUDA scorer for %s (available: %s); callables and multi-metric scoring would need "
                 "the fitted estimators on the host and there is no CPU fallback"
                 % (self.scoring, type(estimator).__name__, sorted(k for k in getattr(adapter, "scorers", {}) if k)))
-        X_arr = np.asarray(X)
+        X_arr = X.toarray() if hasattr(X, "toarray") else np.asarray(X)     # scipy.sparse input: the engine is dense
         y_arr = None if y is None else np.asarray(y)
         fold_id = _est.Folds(splits, len(X_arr))               # fold ids for partition splitters, split masks otherwise
 

@@ -97,7 +97,7 @@ __global__ void sum_grams_kernel(const float *__restrict__ Gq, const int *__rest
 __global__ void build_systems_kernel(const double *__restrict__ T, const float *__restrict__ G, const int *__restrict__ test_block,
                                      const int *__restrict__ train_block,
                                      int d, int Dp, int dp, int fit_intercept, float *__restrict__ A, float *__restrict__ rhs,
-                                     double *__restrict__ means /* [groups][dp + 2]: xbar[0..d), ybar, n_train */)
+                                     double *__restrict__ means /* [groups][dp + 3]: xbar[0..d), ybar, n_train, centred y^T y */)
 {
     const int g = blockIdx.z;
     const int tb = test_block[g], trb = train_block[g];
@@ -123,10 +123,13 @@ __global__ void build_systems_kernel(const double *__restrict__ T, const float *
         if (j < d) {
             r = S(j, d);
             if (fit_intercept) r -= S(j, d + 1) * ybar;                     // n xbar_j ybar
-            means[(size_t)g * (dp + 2) + j] = fit_intercept ? S(j, d + 1) / ntr : 0.0;
+            means[(size_t)g * (dp + 3) + j] = fit_intercept ? S(j, d + 1) / ntr : 0.0;
         }
         rhs[(size_t)g * dp + j] = (float)r;
-        if (j == 0) { means[(size_t)g * (dp + 2) + dp] = ybar; means[(size_t)g * (dp + 2) + dp + 1] = ntr; }
+        if (j == 0) {
+            means[(size_t)g * (dp + 3) + dp] = ybar; means[(size_t)g * (dp + 3) + dp + 1] = ntr;
+            means[(size_t)g * (dp + 3) + dp + 2] = S(d, d) - (fit_intercept ? ntr * ybar * ybar : 0.0);
+        }
     }
 }
 
@@ -227,6 +230,186 @@ __global__ void cg_step_kernel(const float *__restrict__ Q, const double *__rest
     }
 }
 
+// ---- ElasticNet / Lasso: cyclic coordinate descent in the Gram domain -------------------------------------------------
+// scikit-learn minimises  1/2 ||y - Xw||^2 + a ||w||_1 + b/2 ||w||^2  (a = alpha*l1_ratio*n, b = alpha*(1-l1_ratio)*n,
+// linear_model/_coordinate_descent.py:781-782) by cyclic coordinate descent on the residual R = y - Xw
+// (_cd_fast.pyx:243-506 enet_coordinate_descent).  Every quantity of that loop is a function of the centred training Gram
+// A = X^T X, rhs = X^T y and y^T y, which the fold-Gram pipeline above already holds:
+//     X_j . R = q_j  with  q = rhs - A w,       ||X_j||^2 = A_jj,       R . R = yy - w.rhs - w.q,       R . y = yy - w.rhs
+// so one warp runs one (candidate, split) system: q in registers (coordinate k = 128 i + 4 lane + c in register 4 i + c),
+// w in shared memory, one row of A (= column, A is symmetric) streamed from L2 per coordinate.  Same coordinate order,
+// same stopping rule (max |dw| / max |w| <= tol, then duality gap <= tol * yy: _cd_fast.pyx:458-471, gap_enet :162-240)
+// and the same gap-safe screening of provably-zero features (:399-422, :473-492).  State is float64 (scikit-learn: the dtype
+// of X); A and rhs are the float32 system matrices.
+template <int NI>
+__global__ void __launch_bounds__(256) enet_cd_kernel(const float *__restrict__ A, const float *__restrict__ rhs,
+                                                      const double *__restrict__ means, const double *__restrict__ alphas,
+                                                      const double *__restrict__ l1_ratio, int n_cand, int nsys, int d, int dp,
+                                                      int max_iter, double tol_rel, float *__restrict__ Xs,
+                                                      int *__restrict__ n_iter_out, double *__restrict__ gap_out)
+{
+    extern __shared__ double enet_w[];
+    constexpr unsigned FULL = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (s >= nsys) return;                                    // whole warps leave; there is no block-level barrier below
+    const int g = s / n_cand, c = s % n_cand;
+    double *w = enet_w + (size_t)warp * (NI * 128);
+    const float *Ag = A + (size_t)g * dp * dp, *bg = rhs + (size_t)g * dp;
+    const double ntr = means[(size_t)g * (dp + 3) + dp + 1], yy = means[(size_t)g * (dp + 3) + dp + 2];
+    const double alpha = alphas[c] * l1_ratio[c] * ntr, beta = alphas[c] * (1.0 - l1_ratio[c]) * ntr;
+    const double tol = tol_rel * yy;
+
+    double q[NI * 4];
+    unsigned excl = 0;                                        // bit r: the coordinate of register r is screened out (or >= d)
+#pragma unroll
+    for (int i = 0; i < NI; i++)
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) {
+            const int k = 128 * i + 4 * lane + cc;
+            q[i * 4 + cc] = k < d ? (double)bg[k] : 0.0;
+            w[k] = 0.0;
+            if (k >= d) excl |= 1u << (i * 4 + cc);
+        }
+    __syncwarp();
+
+    auto load_row = [&](int j, float4 *col) {
+#pragma unroll
+        for (int i = 0; i < NI; i++) {
+            const int k = 128 * i + 4 * lane;
+            col[i] = k < dp ? __ldg(reinterpret_cast<const float4 *>(Ag + (size_t)j * dp + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto axpy_row = [&](double a, const float4 *col) {         // q += a * A[:, j]
+#pragma unroll
+        for (int i = 0; i < NI; i++) {
+            q[i * 4 + 0] += a * (double)col[i].x; q[i * 4 + 1] += a * (double)col[i].y;
+            q[i * 4 + 2] += a * (double)col[i].z; q[i * 4 + 3] += a * (double)col[i].w;
+        }
+    };
+    auto wsum = [&](double v) {
+#pragma unroll
+        for (int m = 16; m; m >>= 1) v += __shfl_xor_sync(FULL, v, m);
+        return v;
+    };
+
+    double gap = 0.0;
+    // duality gap of the current w (gap_enet, _cd_fast.pyx:162-240); not converged -> gap-safe screening (:473-492)
+    auto converged = [&]() -> bool {
+        double mx = 0, wb = 0, wq = 0, l1 = 0, l2 = 0, qq = 0;
+#pragma unroll
+        for (int r = 0; r < NI * 4; r++) {
+            const int k = 128 * (r >> 2) + 4 * lane + (r & 3);
+            if (k < d) {
+                const double wk = w[k];
+                mx = fmax(mx, fabs(q[r] - beta * wk));
+                wb += wk * (double)bg[k]; wq += wk * q[r]; l1 += fabs(wk); l2 += wk * wk; qq += q[r] * q[r];
+            }
+        }
+#pragma unroll
+        for (int m = 16; m; m >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, m));
+        wb = wsum(wb); wq = wsum(wq); l1 = wsum(l1); l2 = wsum(l2); qq = wsum(qq);
+        const double Rn2 = yy - wb - wq, Ry = yy - wb;
+        double dn;
+        if (alpha == 0.0) {                                   // formulation B (ridge) / OLS first-order condition
+            dn = qq;
+            gap = beta == 0.0 ? qq : Rn2 + 0.5 * beta * l2 - Ry + qq / (2.0 * beta);
+        } else {                                              // formulation A (dual_gap_formulation_A, :138-159)
+            dn = mx;
+            const double primal = 0.5 * (Rn2 + beta * l2) + alpha * l1;
+            const double scale = dn > alpha ? alpha / dn : 1.0;
+            gap = primal - (-0.5 * scale * scale * (Rn2 + beta * l2) + scale * Ry);
+        }
+        if (gap <= tol) return true;
+        if (alpha > 0.0) {
+            const double thr = sqrt(2.0 * gap) / alpha, den = fmax(alpha, dn);
+            unsigned nw = 0;                                  // decided on the X^T R of the gap, before any exclusion changes q
+#pragma unroll
+            for (int r = 0; r < NI * 4; r++) {
+                if ((excl >> r) & 1u) continue;
+                const int k = 128 * (r >> 2) + 4 * lane + (r & 3);
+                const double akk = (double)Ag[(size_t)k * dp + k];
+                const double dk = (1.0 - fabs((q[r] - beta * w[k]) / den)) / sqrt(akk + beta);
+                if (!(dk <= thr)) nw |= 1u << r;
+            }
+#pragma unroll
+            for (int r = 0; r < NI * 4; r++) {
+                const int k = 128 * (r >> 2) + 4 * lane + (r & 3);
+                const bool mine = (nw >> r) & 1u;
+                unsigned m = __ballot_sync(FULL, mine && w[k] != 0.0);
+                while (m) {                                   // R += w_j X_j ; w_j = 0
+                    const int lo = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int j = 128 * (r >> 2) + 4 * lo + (r & 3);
+                    float4 col[NI];
+                    load_row(j, col);
+                    const double wj = __shfl_sync(FULL, w[k], lo);
+                    axpy_row(wj, col);
+                    if (lane == lo) w[k] = 0.0;
+                }
+            }
+            excl |= nw;
+            __syncwarp();
+        }
+        return false;
+    };
+
+    int n_iter = 0;
+    if (!converged()) {
+        int it = 0;
+        for (; it < max_iter; it++) {
+            double w_max = 0.0, d_w_max = 0.0;
+#pragma unroll
+            for (int i = 0; i < NI; i++) {
+                for (int lo = 0; lo < 32; lo++) {
+                    const int jb = 128 * i + 4 * lo;
+                    if (jb >= d) break;
+                    const unsigned ex = __shfl_sync(FULL, excl, lo);
+#pragma unroll
+                    for (int cc = 0; cc < 4; cc++) {
+                        const int r = i * 4 + cc, j = jb + cc;
+                        if ((ex >> r) & 1u) continue;
+                        float4 col[NI];
+                        load_row(j, col);
+                        const float cself = cc == 0 ? col[i].x : cc == 1 ? col[i].y : cc == 2 ? col[i].z : col[i].w;
+                        const double ajj = __shfl_sync(FULL, (double)cself, lo);
+                        if (ajj == 0.0) continue;
+                        const double qj = __shfl_sync(FULL, q[r], lo);
+                        const double wj = __shfl_sync(FULL, lane == 0 ? w[j] : 0.0, 0);     // lane 0 alone reads and writes w[j]
+                        const double tmp = qj + wj * ajj;                                    // X_j . (R + w_j X_j)
+                        const double mag = fmax(fabs(tmp) - alpha, 0.0) / (ajj + beta);
+                        const double wn = tmp > 0.0 ? mag : tmp < 0.0 ? -mag : 0.0;
+                        if (wn != wj) {
+                            axpy_row(wj - wn, col);
+                            if (lane == 0) w[j] = wn;
+                        }
+                        d_w_max = fmax(d_w_max, fabs(wn - wj));
+                        w_max = fmax(w_max, fabs(wn));
+                    }
+                }
+            }
+            __syncwarp();
+            if (w_max == 0.0 || d_w_max / w_max <= tol_rel || it == max_iter - 1)
+                if (converged()) break;
+        }
+        n_iter = it < max_iter ? it + 1 : max_iter;
+    }
+    __syncwarp();
+    for (int k = lane; k < dp; k += 32) Xs[(size_t)s * dp + k] = (float)w[k];
+    if (lane == 0) { n_iter_out[s] = n_iter; gap_out[s] = gap; }
+}
+
+template <int NI>
+cudaError_t launch_enet_cd(const float *A, const float *rhs, const double *means, const double *alphas, const double *l1r, int n_cand,
+                           int nsys, int d, int dp, int max_iter, double tol, float *Xs, int *n_iter, double *gap, cudaStream_t st)
+{
+    const size_t smem = (size_t)8 * NI * 128 * 8;
+    cudaError_t e = cudaFuncSetAttribute(enet_cd_kernel<NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    enet_cd_kernel<NI><<<(nsys + 7) / 8, 256, smem, st>>>(A, rhs, means, alphas, l1r, n_cand, nsys, d, dp, max_iter, tol, Xs, n_iter, gap);
+    return cudaGetLastError();
+}
+
 // Quadratic forms w_s^T M w_s of every system s against its test-block Gram (z = 0) and its training statistics (z = 1):
 // a float64 tile product C[s][j] = sum_l w_s[l] M[l][j] (M symmetric, so row l is read along j: coalesced) with the
 // row-dot against w_s[j] fused into the epilogue.  One CTA = 64 systems x 64 columns j; the partial of column tile jt
@@ -308,7 +491,7 @@ __global__ void ridge_r2_kernel(const float *__restrict__ Xs, const double *__re
         const double w = (double)Xs[(size_t)s * dp + j];
         wxy_k += w * (double)Gk[(size_t)d * Dp + j]; wxy_t += w * Tr(d, j);
         ws_k += w * (double)Gk[(size_t)(d + 1) * Dp + j]; ws_t += w * Tr(d + 1, j);
-        xbw += w * means[(size_t)g * (dp + 2) + j];
+        xbw += w * means[(size_t)g * (dp + 3) + j];
     }
     wxy_k = block_sum(wxy_k, sh); wxy_t = block_sum(wxy_t, sh);
     ws_k = block_sum(ws_k, sh); ws_t = block_sum(ws_t, sh);
@@ -316,7 +499,7 @@ __global__ void ridge_r2_kernel(const float *__restrict__ Xs, const double *__re
     if (threadIdx.x == 0) {
         double qk = 0, qt = 0;
         for (int t = 0; t < njt; t++) { qk += part[((size_t)s * 2) * njt + t]; qt += part[((size_t)s * 2 + 1) * njt + t]; }
-        const double b0 = fit_intercept ? means[(size_t)g * (dp + 2) + dp] - xbw : 0.0;
+        const double b0 = fit_intercept ? means[(size_t)g * (dp + 3) + dp] - xbw : 0.0;
         auto r2 = [&](double yy, double ys, double nn, double q, double wxy, double ws) {
             const double res = yy - 2 * wxy - 2 * b0 * ys + q + 2 * b0 * ws + nn * b0 * b0;
             const double tot = yy - ys * ys / nn;
@@ -333,10 +516,12 @@ __global__ void ridge_r2_kernel(const float *__restrict__ Xs, const double *__re
 }
 
 struct RidgeTimers { float gram = 0, solve = 0, score = 0, total = 0; };
+// ElasticNet / Lasso instead of the Ridge CG solve: per-candidate l1_ratio, scikit-learn's tol / max_iter; outputs [n_cand][n_splits]
+struct EnetSpec { const double *l1_ratio; double tol; int max_iter; int32_t *n_iter; double *dual_gap; };
 
 // groups: fold k (test block k) for the search; one group with test block -1 for the refit
 int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, bool refit,
-              double *test_scores, double *train_scores, double *coef_out, RidgeTimers *tmr)
+              double *test_scores, double *train_scores, double *coef_out, RidgeTimers *tmr, const EnetSpec *en = nullptr)
 {
     if (!h) return GS_ERR_ARG;
     if (h->n == 0) { gs_set_error(h, "gs_ridge: no dataset (call gs_set_data first)"); return GS_ERR_NO_DATA; }
@@ -352,6 +537,12 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     const int n = (int)h->n, d = (int)h->d, ns = h->n_splits;
     const int D = d + 2, Dp = (D + 31) & ~31, dp = (d + 31) & ~31;
     if (dp > 8 * 256) { gs_set_error(h, "gs_ridge: more than 2048 features is not supported by the CG kernels"); return GS_ERR_UNSUPPORTED; }
+    if (en) {
+        if (dp > 1024) { gs_set_error(h, "gs_enet: more than 1024 features is not supported by the coordinate-descent kernel"); return GS_ERR_UNSUPPORTED; }
+        if (!en->l1_ratio || !(en->tol >= 0) || en->max_iter < 1) { gs_set_error(h, "gs_enet: bad arguments"); return GS_ERR_ARG; }
+        for (int c = 0; c < n_cand; c++)
+            if (!(en->l1_ratio[c] >= 0 && en->l1_ratio[c] <= 1)) { gs_set_error(h, "gs_enet: l1_ratio must be in [0, 1]"); return GS_ERR_ARG; }
+    }
 
     // row blocks.  Test folds that partition the rows: one contiguous block per fold (rows are sorted by fold; fold -1
     // rows, never tested, form a trailing block), training statistics = T - G_fold.  General splits (gs_set_splits):
@@ -404,7 +595,7 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
            &bA = h->dWork[5], &bV = h->dWork[6], &bMeta = h->dWork[7];
     GS_CUDA(bZ.reserve((size_t)Dp * ldz * 4)); GS_CUDA(bZh.reserve((size_t)Dp * ldz * 4)); GS_CUDA(bZl.reserve((size_t)Dp * ldz * 4));
     GS_CUDA(bG.reserve((size_t)(nb + nq) * Dp * Dp * 4));                   // per-block Grams, then the chunk partials
-    const size_t tBytes = (size_t)Dp * Dp * 8, meansBytes = (size_t)groups * (dp + 2) * 8;
+    const size_t tBytes = (size_t)Dp * Dp * 8, meansBytes = (size_t)groups * (dp + 3) * 8;
     GS_CUDA(bMisc.reserve(tBytes + meansBytes + (size_t)nsys * (8 + 8 + 16) + (size_t)n_cand * 8 + (size_t)(d + 1) * 4 + 256));
     GS_CUDA(bA.reserve((size_t)groups * dp * dp * 4 * 3 + (size_t)groups * dp * 4));
     GS_CUDA(bV.reserve((size_t)nsys * dp * 4 * (6 + (size_t)((dp + TC_KCHUNK - 1) / TC_KCHUNK))));
@@ -412,7 +603,7 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     GS_CUDA(bMeta.reserve((size_t)(nq * 3 + nb + 1 + 2 * groups) * 4 + (size_t)(nq + groups * nkc) * sizeof(TcBatch) + (size_t)nsys * 4 + rowidx.size() * 4 + 128));
     double *dT = bMisc.as<double>();
     double *dMeans = dT + (size_t)Dp * Dp;
-    double *dRR = dMeans + (size_t)groups * (dp + 2), *dBB = dRR + nsys, *dOut = dBB + nsys, *dAlpha = dOut + 2 * (size_t)nsys;
+    double *dRR = dMeans + (size_t)groups * (dp + 3), *dBB = dRR + nsys, *dOut = dBB + nsys, *dAlpha = dOut + 2 * (size_t)nsys;
     float *dShift = reinterpret_cast<float *>(dAlpha + n_cand);               // [d + 1] column shifts of [X | y]
     float *dA = bA.as<float>(), *dAh = dA + (size_t)groups * dp * dp, *dAl = dAh + (size_t)groups * dp * dp,
           *dRhs = dAl + (size_t)groups * dp * dp;
@@ -478,37 +669,50 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
         build_systems_kernel<<<grid, block, 0, st>>>(dT, bG.as<float>(), dTestBlock, dTrainBlock, d, Dp, dp, fit_intercept, dA, dRhs, dMeans);
         GS_CUDA(cudaGetLastError());
     }
-    GS_CUDA(launch_split_tf32(dA, dAh, dAl, (size_t)groups * dp * dp, st));
-    TcMap mah, mal, mph, mpl;
-    GS_CUDA(tc_make_map(&mah, dAh, (int64_t)groups * dp, dp, dp));
-    GS_CUDA(tc_make_map(&mal, dAl, (int64_t)groups * dp, dp, dp));
-    GS_CUDA(tc_make_map(&mph, dPh, nsys, dp, dp));
-    GS_CUDA(tc_make_map(&mpl, dPl, nsys, dp, dp));
-    launches += 2;
+    int it = 0;
+    if (en) {
+        // ---- 3'. ElasticNet / Lasso: one warp per system, coordinate descent on (A_g, rhs_g) ----
+        GS_CUDA(cudaMemcpyAsync(dBB, en->l1_ratio, (size_t)n_cand * 8, cudaMemcpyHostToDevice, st));
+        cudaError_t e;
+        if (dp <= 128) e = launch_enet_cd<1>(dA, dRhs, dMeans, dAlpha, dBB, n_cand, nsys, d, dp, en->max_iter, en->tol, dX, dDone, dRR, st);
+        else if (dp <= 256) e = launch_enet_cd<2>(dA, dRhs, dMeans, dAlpha, dBB, n_cand, nsys, d, dp, en->max_iter, en->tol, dX, dDone, dRR, st);
+        else if (dp <= 512) e = launch_enet_cd<4>(dA, dRhs, dMeans, dAlpha, dBB, n_cand, nsys, d, dp, en->max_iter, en->tol, dX, dDone, dRR, st);
+        else e = launch_enet_cd<8>(dA, dRhs, dMeans, dAlpha, dBB, n_cand, nsys, d, dp, en->max_iter, en->tol, dX, dDone, dRR, st);
+        GS_CUDA(e);
+        launches++;
+    } else {
+        GS_CUDA(launch_split_tf32(dA, dAh, dAl, (size_t)groups * dp * dp, st));
+        TcMap mah, mal, mph, mpl;
+        GS_CUDA(tc_make_map(&mah, dAh, (int64_t)groups * dp, dp, dp));
+        GS_CUDA(tc_make_map(&mal, dAl, (int64_t)groups * dp, dp, dp));
+        GS_CUDA(tc_make_map(&mph, dPh, nsys, dp, dp));
+        GS_CUDA(tc_make_map(&mpl, dPl, nsys, dp, dp));
+        launches += 2;
 
-    // ---- 3. batched CG: Q = P A_g on tensor cores, vector updates in cg_step_kernel ----
-    cg_init_kernel<<<nsys, 256, 0, st>>>(dRhs, n_cand, dp, dX, dR, dP, dPh, dPl, dRR, dBB, dDone);
-    GS_CUDA(cudaGetLastError());
-    launches++;
-    int open = 1, it = 0;
-    while (open > 0 && it < CG_MAX_ITER) {
-        for (int rep = 0; rep < 4; rep++, it++) {
-            h->tt.begin(h->evp, st);
-            GS_CUDA(launch_gemm_nt_tf32x3(mph, mpl, mah, mal, dBatchCG, groups * nkc, n_cand, dp, 1.0f, false, st));
-            h->tt.end(h->evp, st, 3.0 * 2.0 * (double)groups * n_cand * (double)dp * dp);
-            if (nkc > 1) GS_CUDA(launch_sum_partials(dQp, nkc, (int64_t)nsys * dp, dQ, st));
-            GS_CUDA(cudaMemsetAsync(dOpen, 0, 4, st));
-            cg_step_kernel<<<nsys, 256, 0, st>>>(nkc > 1 ? dQ : dQp, dAlpha, n_cand, dp, dX, dR, dP, dPh, dPl, dRR, dBB, dDone, dOpen, CG_TOL * CG_TOL);
-            GS_CUDA(cudaGetLastError());
-            launches += 2;
+        // ---- 3. batched CG: Q = P A_g on tensor cores, vector updates in cg_step_kernel ----
+        cg_init_kernel<<<nsys, 256, 0, st>>>(dRhs, n_cand, dp, dX, dR, dP, dPh, dPl, dRR, dBB, dDone);
+        GS_CUDA(cudaGetLastError());
+        launches++;
+        int open = 1;
+        while (open > 0 && it < CG_MAX_ITER) {
+            for (int rep = 0; rep < 4; rep++, it++) {
+                h->tt.begin(h->evp, st);
+                GS_CUDA(launch_gemm_nt_tf32x3(mph, mpl, mah, mal, dBatchCG, groups * nkc, n_cand, dp, 1.0f, false, st));
+                h->tt.end(h->evp, st, 3.0 * 2.0 * (double)groups * n_cand * (double)dp * dp);
+                if (nkc > 1) GS_CUDA(launch_sum_partials(dQp, nkc, (int64_t)nsys * dp, dQ, st));
+                GS_CUDA(cudaMemsetAsync(dOpen, 0, 4, st));
+                cg_step_kernel<<<nsys, 256, 0, st>>>(nkc > 1 ? dQ : dQp, dAlpha, n_cand, dp, dX, dR, dP, dPh, dPl, dRR, dBB, dDone, dOpen, CG_TOL * CG_TOL);
+                GS_CUDA(cudaGetLastError());
+                launches += 2;
+            }
+            GS_CUDA(cudaMemcpyAsync(&open, dOpen, 4, cudaMemcpyDeviceToHost, st));
+            GS_CUDA(cudaStreamSynchronize(st));
         }
-        GS_CUDA(cudaMemcpyAsync(&open, dOpen, 4, cudaMemcpyDeviceToHost, st));
-        GS_CUDA(cudaStreamSynchronize(st));
-    }
-    if (open > 0) {
-        gs_set_error(h, "gs_ridge: conjugate gradients did not converge in " + std::to_string(CG_MAX_ITER) + " iterations for " +
-                            std::to_string(open) + " systems (ill-conditioned normal matrix)");
-        return GS_ERR_NUMERIC;
+        if (open > 0) {
+            gs_set_error(h, "gs_ridge: conjugate gradients did not converge in " + std::to_string(CG_MAX_ITER) + " iterations for " +
+                                std::to_string(open) + " systems (ill-conditioned normal matrix)");
+            return GS_ERR_NUMERIC;
+        }
     }
     cudaEventRecord(ev[2], st);
 
@@ -538,10 +742,10 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
         h->prof.d2h_bytes = (int64_t)out.size() * 8;
     } else {
         std::vector<float> w(dp), shift(d + 1);
-        std::vector<double> means(dp + 2);
+        std::vector<double> means(dp + 3);
         GS_CUDA(cudaMemcpyAsync(w.data(), dX, (size_t)dp * 4, cudaMemcpyDeviceToHost, st));
         GS_CUDA(cudaMemcpyAsync(shift.data(), dShift, (size_t)(d + 1) * 4, cudaMemcpyDeviceToHost, st));
-        GS_CUDA(cudaMemcpyAsync(means.data(), dMeans, (size_t)(dp + 2) * 8, cudaMemcpyDeviceToHost, st));
+        GS_CUDA(cudaMemcpyAsync(means.data(), dMeans, (size_t)(dp + 3) * 8, cudaMemcpyDeviceToHost, st));
         cudaEventRecord(ev[3], st);
         GS_CUDA(cudaStreamSynchronize(st));
         double b0 = means[dp] + (double)shift[d];                  // intercept in the caller's (unshifted) coordinates
@@ -551,6 +755,20 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
             b0 -= (means[j] + (double)shift[j]) * (double)w[j];
         }
         coef_out[d] = fit_intercept ? b0 : 0.0;
+    }
+    if (en) {                                                      // sweeps and duality gap of every system
+        std::vector<int> ni(nsys);
+        std::vector<double> gp(nsys);
+        GS_CUDA(cudaMemcpyAsync(ni.data(), dDone, (size_t)nsys * 4, cudaMemcpyDeviceToHost, st));
+        GS_CUDA(cudaMemcpyAsync(gp.data(), dRR, (size_t)nsys * 8, cudaMemcpyDeviceToHost, st));
+        GS_CUDA(cudaStreamSynchronize(st));
+        for (int g = 0; g < groups; g++)
+            for (int c = 0; c < n_cand; c++) {
+                const size_t s = (size_t)g * n_cand + c, o = (size_t)c * groups + g;
+                if (en->n_iter) en->n_iter[o] = ni[s];
+                if (en->dual_gap) en->dual_gap[o] = gp[s];
+                it = std::max(it, ni[s]);
+            }
     }
     cudaEventRecord(ev[4], st);
     GS_CUDA(cudaStreamSynchronize(st));
@@ -596,6 +814,32 @@ int gs_ridge_refit(gs_handle *h, double alpha, int32_t fit_intercept, double *co
     if (h && !coef_out) { gs_set_error(h, "gs_ridge_refit: coef_out is NULL"); return GS_ERR_ARG; }
     RidgeTimers t;
     return ridge_run(h, 1, &alpha, fit_intercept, true, nullptr, nullptr, coef_out, &t);
+}
+
+int gs_enet(gs_handle *h, int32_t n_cand, const double *alpha, const double *l1_ratio, int32_t fit_intercept, double tol,
+            int32_t max_iter, uint32_t flags, double *test_scores, double *train_scores, int32_t *n_iter, float *fit_ms, float *score_ms)
+{
+    if (h && !test_scores) { gs_set_error(h, "gs_enet: test_scores is NULL"); return GS_ERR_ARG; }
+    RidgeTimers t;
+    EnetSpec en{l1_ratio, tol, max_iter, n_iter, nullptr};
+    const int st = ridge_run(h, n_cand, alpha, fit_intercept, false, test_scores, (flags & GS_RETURN_TRAIN) ? train_scores : nullptr,
+                             nullptr, &t, &en);
+    if (st) return st;
+    const int nt = n_cand * h->n_splits;
+    for (int i = 0; i < nt; i++) {
+        if (fit_ms) fit_ms[i] = (t.gram + t.solve) / (float)nt;
+        if (score_ms) score_ms[i] = t.score / (float)nt;
+    }
+    return GS_OK;
+}
+
+int gs_enet_refit(gs_handle *h, double alpha, double l1_ratio, int32_t fit_intercept, double tol, int32_t max_iter, double *coef_out,
+                  int32_t *n_iter, double *dual_gap)
+{
+    if (h && !coef_out) { gs_set_error(h, "gs_enet_refit: coef_out is NULL"); return GS_ERR_ARG; }
+    RidgeTimers t;
+    EnetSpec en{&l1_ratio, tol, max_iter, n_iter, dual_gap};
+    return ridge_run(h, 1, &alpha, fit_intercept, true, nullptr, nullptr, coef_out, &t, &en);
 }
 
 // ---- test hook: one tensor-core GEMM with host buffers ----

@@ -62,6 +62,8 @@ def load_library():
     L.gs_svc_refit.argtypes = [vp, i32, dbl, dbl, dbl, i32, u32, vp, vp, vp]
     L.gs_ridge.argtypes = [vp, i32, vp, i32, u32, vp, vp, vp, vp]
     L.gs_ridge_refit.argtypes = [vp, dbl, i32, vp]
+    L.gs_enet.argtypes = [vp, i32, vp, vp, i32, dbl, i32, u32, vp, vp, vp, vp, vp]
+    L.gs_enet_refit.argtypes = [vp, dbl, dbl, i32, dbl, i32, vp, vp, vp]
     L.gs_logreg.argtypes = [vp, i32, vp, dbl, i32, i32, u32, vp, vp, vp, vp, vp]
     L.gs_logreg_refit.argtypes = [vp, dbl, dbl, i32, i32, vp, vp]
     L.gs_get_profile.argtypes = [vp, c.POINTER(GsProfile)]
@@ -74,7 +76,7 @@ def load_library():
     L.gs_svc_cluster_count.restype = i32
     L.gs_svc_schedule.argtypes = [vp, i32, i32, vp, vp]
     L.gs_svc_schedule.restype = None
-    for f in ("gs_create", "gs_set_data", "gs_svc", "gs_svc_refit", "gs_ridge", "gs_ridge_refit", "gs_logreg",
+    for f in ("gs_create", "gs_set_data", "gs_svc", "gs_svc_refit", "gs_ridge", "gs_ridge_refit", "gs_enet", "gs_enet_refit", "gs_logreg",
               "gs_logreg_refit", "gs_get_profile", "gs_debug_gram", "gs_debug_kernel_matrix", "gs_debug_gemm_nt"):
         getattr(L, f).restype = c.c_int
     _lib = L
@@ -198,6 +200,27 @@ class Engine:
         coef = np.zeros(self.d + 1)
         self._check(self._L.gs_ridge_refit(self._h, float(alpha), int(bool(fit_intercept)), _ptr(coef)))
         return coef[:-1].copy(), float(coef[-1])
+
+    def enet(self, alpha, l1_ratio, fit_intercept=True, tol=1e-4, max_iter=1000, return_train=True):
+        alpha = np.ascontiguousarray(alpha, np.float64)
+        l1_ratio = np.ascontiguousarray(np.broadcast_to(np.asarray(l1_ratio, np.float64), alpha.shape))
+        shape = (len(alpha), self.n_splits)
+        out = dict(test=np.zeros(shape), train=np.zeros(shape), n_iter=np.zeros(shape, np.int32),
+                   fit_ms=np.zeros(shape, np.float32), score_ms=np.zeros(shape, np.float32))
+        self._check(self._L.gs_enet(self._h, len(alpha), _ptr(alpha), _ptr(l1_ratio), int(bool(fit_intercept)), float(tol),
+                                    int(max_iter), GS_RETURN_TRAIN if return_train else 0, _ptr(out["test"]), _ptr(out["train"]),
+                                    _ptr(out["n_iter"]), _ptr(out["fit_ms"]), _ptr(out["score_ms"])))
+        if not return_train:
+            out["train"] = None
+        return out
+
+    def enet_refit(self, alpha, l1_ratio=1.0, fit_intercept=True, tol=1e-4, max_iter=1000):
+        coef = np.zeros(self.d + 1)
+        it = np.zeros(1, np.int32)
+        gap = np.zeros(1)
+        self._check(self._L.gs_enet_refit(self._h, float(alpha), float(l1_ratio), int(bool(fit_intercept)), float(tol),
+                                          int(max_iter), _ptr(coef), _ptr(it), _ptr(gap)))
+        return coef[:-1].copy(), float(coef[-1]), int(it[0]), float(gap[0])
 
     def logreg(self, C, tol=1e-4, max_iter=100, fit_intercept=True, return_train=True):
         C = np.ascontiguousarray(C, np.float64)

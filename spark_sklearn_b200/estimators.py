@@ -92,7 +92,8 @@ class Folds:
 
 
 def adapter_for(estimator):
-    from sklearn.linear_model import LogisticRegression, Ridge
+    from sklearn.linear_model import ElasticNet, Lasso, LogisticRegression, Ridge
+    from sklearn.pipeline import Pipeline
     from sklearn.svm import SVC
     t = type(estimator)
     if t is SVC:
@@ -101,12 +102,21 @@ def adapter_for(estimator):
         return RidgeAdapter
     if t is LogisticRegression:
         return LogRegAdapter
+    if t in (Lasso, ElasticNet):
+        return ENetAdapter
+    if t is Pipeline and len(estimator.steps) == 1:
+        # the reference's own search tests wrap the estimator in a one-step Pipeline and search 'step__param'
+        # (python/spark_sklearn/tests/test_search_2.py:69-93): the step's adapter runs, the names are translated
+        return PipelineAdapter(estimator.steps[0][0], adapter_for(estimator.steps[0][1]))
     raise NotImplementedError(
-        "spark_sklearn_b200 has CUDA paths for SVC, Ridge and LogisticRegression only; got %s "
-        "(no CPU fallback)" % t.__name__)
+        "spark_sklearn_b200 has CUDA paths for SVC, Ridge, Lasso, ElasticNet and LogisticRegression (bare or as the only "
+        "step of a Pipeline); got %s (no CPU fallback)" % t.__name__)
 
 
 def _as_matrix(X):
+    import scipy.sparse as sp
+    if sp.issparse(X):
+        X = X.toarray()                               # the engine is dense (small dense data)
     X = np.asarray(X)
     if X.ndim != 2:
         raise ValueError("X must be 2-dimensional")
@@ -474,6 +484,124 @@ class RidgePlan(_Plan):
         est.solver_ = "cholesky"
         est.n_features_in_ = self.X.shape[1]
         return est
+
+
+# ------------------------------------------------------------------ Lasso / ElasticNet -------
+class ENetAdapter:
+    multi_device = True
+    scorers = REGRESSION_SCORERS
+
+    @staticmethod
+    def plan(estimator, cands, X, y, fold_id, n_splits, device=None):
+        return ENetPlan(estimator, cands, X, y, fold_id, n_splits, device)
+
+
+class ENetPlan(RidgePlan):
+    """sklearn.linear_model.Lasso / ElasticNet on the fold Grams of the Ridge path: cyclic coordinate descent with
+    scikit-learn's stopping rule (linear_model/_cd_fast.pyx:243-506) in the Gram domain, csrc/linear.cu enet_cd_kernel."""
+
+    def __init__(self, estimator, cands, X, y, fold_id, n_splits, device=None):
+        y = np.asarray(y)
+        self._y2d = y.ndim == 2 and y.shape[1] == 1      # column-vector y (reference test_search_2.py:79): one target
+        if self._y2d:
+            y = y[:, 0]
+        super().__init__(estimator, cands, X, y, fold_id, n_splits, device)
+
+    def _check(self, p):
+        if p.get("positive"):
+            raise NotImplementedError("positive=True is not supported by the CUDA path")
+        if p.get("selection", "cyclic") != "cyclic":
+            raise NotImplementedError("selection='random' is not supported by the CUDA path (cyclic is)")
+        if p.get("warm_start"):
+            raise NotImplementedError("warm_start=True is not supported by the CUDA path")
+        if isinstance(p.get("precompute", False), np.ndarray):
+            raise NotImplementedError("a user-supplied Gram matrix is not supported by the CUDA path")
+        if not (isinstance(p["alpha"], numbers.Real) and p["alpha"] >= 0):
+            raise ValueError("alpha must be a non-negative number; got %r" % (p["alpha"],))
+        l1 = p.get("l1_ratio", 1.0)
+        if not (isinstance(l1, numbers.Real) and 0 <= l1 <= 1):
+            raise ValueError("l1_ratio must be in [0, 1]; got %r" % (l1,))
+        if self.X.shape[1] > 1024:
+            raise NotImplementedError("more than 1024 features is not supported by the coordinate-descent kernel")
+
+    def evaluate(self, my, return_train=True, error_score='raise'):
+        shape = (len(my), self.n_splits)
+        res = dict(test=np.zeros(shape), train=np.zeros(shape), fit_ms=np.zeros(shape), score_ms=np.zeros(shape),
+                   n_iter=np.zeros(shape, np.int64))
+        groups = {}
+        for j, ci in enumerate(my):
+            p = self._base_params(self.cands[ci])
+            self._check(p)
+            key = (bool(p["fit_intercept"]), float(p["tol"]), int(p["max_iter"]))
+            groups.setdefault(key, []).append((j, float(p["alpha"]), float(p.get("l1_ratio", 1.0))))
+        prof = {}
+        for (fi, tol, max_iter), items in groups.items():
+            idx = [j for j, _, _ in items]
+            self.engine.set_scoring(self.score_kind, self.score_pos)
+            r = self.engine.enet([a for _, a, _ in items], [l for _, _, l in items], fit_intercept=fi, tol=tol,
+                                 max_iter=max_iter, return_train=return_train)
+            for key in ("test", "fit_ms", "score_ms", "n_iter"):
+                res[key][idx] = r[key]
+            if return_train:
+                res["train"][idx] = r["train"]
+            for k, v in self.engine.profile().items():
+                prof[k] = prof.get(k, 0) + v
+        self._prof = prof
+        self.n_iter_ = res["n_iter"]
+        return self._finish(res, return_train, error_score, len(my))
+
+    def refit(self, best_params):
+        p = self._base_params(best_params)
+        self._check(p)
+        w, b, n_iter, gap = self.engine.enet_refit(p["alpha"], p.get("l1_ratio", 1.0), p["fit_intercept"], p["tol"], p["max_iter"])
+        est = clone(self.estimator).set_params(**best_params)
+        dt = np.float32 if self.X.dtype == np.float32 else np.float64
+        est.coef_ = w.astype(dt)[None, :] if self._y2d else w.astype(dt)
+        b = dt(b) if p["fit_intercept"] else 0.0
+        est.intercept_ = np.array([b], dt) if self._y2d else b
+        est.n_iter_ = n_iter
+        est.dual_gap_ = dt(gap / len(self.X))        # _coordinate_descent.py:862
+        est.n_features_in_ = self.X.shape[1]
+        return est
+
+
+# ------------------------------------------------------------------ one-step Pipeline ---------
+class PipelineAdapter:
+    """Pipeline([(name, estimator)]) searched through 'name__param' (reference tests/test_search_2.py:69-93): the step's plan
+    with the prefix stripped; the refit estimator is returned inside a fitted clone of the Pipeline."""
+
+    def __init__(self, step, inner):
+        self.step, self.inner = step, inner
+        self.multi_device = getattr(inner, "multi_device", False)
+        self.scorers = inner.scorers
+
+    def _strip(self, cand):
+        pre = self.step + "__"
+        out = {}
+        for k, v in cand.items():
+            if not k.startswith(pre):
+                raise NotImplementedError("Pipeline parameter %r: only '%s<param>' of the single step has a CUDA path" % (k, pre))
+            out[k[len(pre):]] = v
+        return out
+
+    def plan(self, estimator, cands, X, y, fold_id, n_splits, device=None):
+        inner_plan = self.inner.plan(estimator.steps[0][1], [self._strip(c) for c in cands], X, y, fold_id, n_splits, device)
+        return _PipelinePlan(self, estimator, inner_plan)
+
+
+class _PipelinePlan:
+    def __init__(self, adapter, pipeline, inner):
+        self._adapter, self._pipeline, self._inner = adapter, pipeline, inner
+
+    def __getattr__(self, name):                      # evaluate, set_scoring, costs, profile, engine, close ...
+        return getattr(self._inner, name)
+
+    def refit(self, best_params):
+        from sklearn.pipeline import Pipeline
+        fitted = self._inner.refit(self._adapter._strip(best_params))
+        pipe = clone(self._pipeline)
+        pipe.steps = [(self._adapter.step, fitted)]
+        return pipe
 
 
 # ------------------------------------------------------------------ LogisticRegression --------

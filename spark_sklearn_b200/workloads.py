@@ -61,6 +61,16 @@ def _c5(n=20000, d=1024, n_alpha=512, cv=10, name="c5_ridge_512"):
                 cv=cv, search="grid")
 
 
+def _lasso(n=20000, d=1024, n_alpha=32, cv=10, name="lasso_1024", enet=False):
+    """The estimator of the reference's own search tests (tests/test_search_2.py:69-119) on config 5's data recipe."""
+    w = _c5(n=n, d=d, n_alpha=2, cv=cv, name=name)
+    if enet:
+        w.update(estimator="ElasticNet", param_grid={"alpha": np.logspace(-2, 1.5, n_alpha), "l1_ratio": [0.2, 0.7]})
+    else:
+        w.update(estimator="Lasso", param_grid={"alpha": np.logspace(-2, 2, n_alpha)})
+    return w
+
+
 WORKLOADS = {
     "c1": _c1, "c2": _c2, "c3": _c3, "c4": _c4, "c5": _c5,
     # reduced-size variants: same recipes, sizes the CPU oracle finishes in seconds
@@ -68,6 +78,10 @@ WORKLOADS = {
     "c2_mid": lambda: _c2(n=3000, d=128, nc=4, ng=4, name="c2_mid"),
     "c3_small": lambda: _c3(n=4000, d=32, n_iter=16, name="c3_small"),
     "c5_small": lambda: _c5(n=2000, d=64, n_alpha=32, cv=10, name="c5_small"),
+    # Lasso / ElasticNet on the fold Grams
+    "lasso_1024": _lasso,
+    "lasso_small": lambda: _lasso(n=2000, d=64, n_alpha=16, cv=5, name="lasso_small"),
+    "enet_small": lambda: _lasso(n=1500, d=200, n_alpha=6, cv=4, name="enet_small", enet=True),
 }
 
 
@@ -86,6 +100,9 @@ def make_estimator(w):
     if w["estimator"] == "Ridge":
         from sklearn.linear_model import Ridge
         return Ridge(**w["est_params"])
+    if w["estimator"] in ("Lasso", "ElasticNet"):
+        import sklearn.linear_model as lm
+        return getattr(lm, w["estimator"])(**w["est_params"])
     raise ValueError(w["estimator"])
 
 

@@ -102,3 +102,35 @@ def test_logreg_oracle_vs_golden():
     # L-BFGS stops early (gtol); the restated objective follows the same path up to float32 rounding
     assert np.abs(test - g["test_scores"][::4]).max() <= 2.5e-3
     assert np.abs(test.mean(1) - g["test_scores"][::4].mean(1)).max() <= 1e-3
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_enet_oracle_matches_sklearn_iterates(dtype):
+    """The coordinate-descent restatement takes scikit-learn's own sweeps: same n_iter_, same coefficients (float64:
+    to the last bit of the score; float32: BLAS summation order shows at 1e-7)."""
+    import warnings
+    from sklearn.datasets import make_regression
+    from sklearn.linear_model import ElasticNet, Lasso
+    X, y = make_regression(n_samples=400, n_features=60, n_informative=10, noise=5.0, random_state=0)
+    X, y = X.astype(dtype), y.astype(dtype)
+    tr, te = np.arange(300), np.arange(300, 400)
+    for alpha, l1 in ((0.01, 1.0), (1.0, 1.0), (30.0, 1.0), (0.5, 0.5), (0.1, 0.0), (200.0, 1.0)):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m = (Lasso(alpha=alpha) if l1 == 1.0 else ElasticNet(alpha=alpha, l1_ratio=l1)).fit(X[tr], y[tr])
+        t, r, it = O.enet_fit_score(X, y, tr, te, alpha, l1)
+        assert it == m.n_iter_, (alpha, l1)
+        tol = 0 if dtype is np.float64 else 2e-7
+        assert abs(m.score(X[te], y[te]) - t) <= tol and abs(m.score(X[tr], y[tr]) - r) <= tol, (alpha, l1)
+
+
+@pytest.mark.parametrize("key", ["lasso_small", "enet_small"])
+def test_enet_oracle_vs_golden(key):
+    g = golden(key)
+    w = W.make_workload(key)
+    fold_id, ns = O.folds_from_cv(w["cv"], w["X"], w["y"], False)
+    cands = W.candidates(w)[::3]
+    test, train, iters = O.cv_scores_enet(w["X"], w["y"], fold_id, ns, cands)
+    np.testing.assert_allclose(test, g["test_scores"][::3], atol=2e-6)
+    np.testing.assert_allclose(train, g["train_scores"][::3], atol=2e-6)
+    np.testing.assert_array_equal(iters, g["diag"][::3, :, 0].astype(int))
