@@ -156,8 +156,11 @@ int gs_enet_refit(gs_handle *h, double alpha, double l1_ratio, int32_t fit_inter
                   double *coef_out, int32_t *n_iter, double *dual_gap);
 
 /*
- * LogisticRegression (binary, L2, lbfgs; replaces sklearn linear_model/_logistic.py:219
- * _logistic_regression_path, objective _linear_loss.py:47-64).  C[n_cand].  Scores are accuracy.
+ * LogisticRegression (L2, lbfgs; replaces sklearn linear_model/_logistic.py:219 _logistic_regression_path, objective
+ * _linear_loss.py:47-64).  C[n_cand].  Scores are accuracy unless gs_set_scoring says otherwise.  Two classes: the binomial
+ * loss on one weight row.  Three to 64 classes: scikit-learn's multinomial loss (_logistic.py:527-545, _loss/_loss.pyx
+ * closs_grad_half_multinomial), one weight row per class, predictions by the first arg-max.
+ * gs_logreg_refit: coef_out is [rows][d + 1] (weights, then the intercept), rows = 1 (binary) or n_classes.
  */
 int gs_logreg(gs_handle *h, int32_t n_cand, const double *C, double tol, int32_t max_iter,
               int32_t fit_intercept, uint32_t flags,

@@ -330,17 +330,54 @@ def cv_scores_enet(X, y, fold_id, n_splits, cands, fit_intercept=True):
 
 # ------------------------------------------------------- LogisticRegression ------------
 def logreg_fit_score(X, y, train, test, C, tol=1e-4, max_iter=100, fit_intercept=True):
-    """Binary L2 logistic regression, lbfgs: SK/linear_model/_logistic.py:403 (dtype kept),
+    """L2 logistic regression, lbfgs: SK/linear_model/_logistic.py:403 (dtype kept),
     :580-604 (scipy L-BFGS-B, maxcor default 10, maxls=50, gtol=tol, ftol=64*eps),
-    objective SK/linear_model/_linear_loss.py:47-64 with l2_reg_strength = 1/(C*n):
-        f(w,b) = (1/n) sum_i [log(1+exp(z_i)) - y_i z_i] + 0.5*l2*|w|^2,   z = Xw + b."""
+    objective SK/linear_model/_linear_loss.py:47-64 with l2_reg_strength = 1/(C*n).
+    Two classes:  f(w,b) = (1/n) sum_i [log(1+exp(z_i)) - y_i z_i] + 0.5*l2*|w|^2,   z = Xw + b.
+    Three or more (multinomial, one weight row per class; SK/_loss/_loss.pyx closs_grad_half_multinomial):
+                  f(W,b) = (1/n) sum_i [logsumexp(z_i) - z_i[y_i]] + 0.5*l2*|W|_F^2,   z_i = W x_i + b."""
     from scipy import optimize
+    from scipy.special import logsumexp
     Xt = X[train]
     dt = Xt.dtype
     classes = np.unique(y[train])
-    yt = (y[train] == classes[1]).astype(dt)
     n, d = Xt.shape
     l2 = 1.0 / (C * n)
+    opts = {"maxiter": max_iter, "maxls": 50, "gtol": tol, "ftol": 64 * np.finfo(float).eps}
+    if len(classes) > 2:
+        # float32 X: scikit-learn casts the weights to X.dtype, keeps raw predictions, pointwise losses and gradients in that
+        # dtype and contracts them with float32 BLAS (_linear_loss.py:216-222, 329-376); the optimiser state is float64 and
+        # the variables are ordered class-fastest (coef.reshape((n_classes, -1), order="F")).
+        K = len(classes)
+        Y = y[train][:, None] == classes[None, :]
+        nv = d + (1 if fit_intercept else 0)
+
+        def fgm(w):
+            Wm = w.reshape((K, nv), order="F")
+            Z = Xt @ Wm[:, :d].astype(dt).T
+            if fit_intercept:
+                Z = Z + Wm[:, d].astype(dt)
+            Z64 = Z.astype(np.float64)
+            mx = Z64.max(1)
+            E = np.exp(Z64 - mx[:, None])
+            se = E.sum(1)
+            loss_i = (np.log(se) + mx - Z64[Y]).astype(dt)
+            P = (E / se[:, None] - Y).astype(dt)
+            loss = float(loss_i.sum() / n) + 0.5 * l2 * float((Wm[:, :d] * Wm[:, :d]).sum())
+            P /= dt.type(n)
+            g = np.empty((K, nv), order="F")
+            g[:, :d] = (P.T @ Xt) + l2 * Wm[:, :d]
+            if fit_intercept:
+                g[:, d] = P.sum(0)
+            return loss, g.ravel(order="F")
+        res = optimize.minimize(fgm, np.zeros(K * nv), method="L-BFGS-B", jac=True, options=opts)
+        Wm = res.x.reshape((K, nv), order="F")
+
+        def accm(rows):
+            Z = X[rows].astype(np.float64) @ Wm[:, :d].T + (Wm[:, d] if fit_intercept else 0.0)
+            return np.mean(classes[Z.argmax(1)] == y[rows])
+        return accm(test), accm(train), res.nit
+    yt = (y[train] == classes[1]).astype(dt)
 
     def fg(w):
         wv = w[:d].astype(dt)
@@ -354,9 +391,7 @@ def logreg_fit_score(X, y, train, test, C, tol=1e-4, max_iter=100, fit_intercept
             g[d] = r.sum()
         return loss, g
     w0 = np.zeros(d + 1 if fit_intercept else d)
-    res = optimize.minimize(fg, w0, method="L-BFGS-B", jac=True,
-                            options={"maxiter": max_iter, "maxls": 50, "gtol": tol,
-                                     "ftol": 64 * np.finfo(float).eps})
+    res = optimize.minimize(fg, w0, method="L-BFGS-B", jac=True, options=opts)
     w = res.x
 
     def acc(rows):
@@ -365,12 +400,13 @@ def logreg_fit_score(X, y, train, test, C, tol=1e-4, max_iter=100, fit_intercept
     return acc(test), acc(train), res.nit
 
 
-def cv_scores_logreg(X, y, fold_id, n_splits, cands):
+def cv_scores_logreg(X, y, fold_id, n_splits, cands, return_n_iter=False):
     allrows = np.arange(len(y))
     test = np.zeros((len(cands), n_splits))
     train = np.zeros_like(test)
+    iters = np.zeros(test.shape, int)
     for ci, p in enumerate(cands):
         for k in range(n_splits):
-            test[ci, k], train[ci, k], _ = logreg_fit_score(X, y, allrows[fold_id != k],
-                                                            allrows[fold_id == k], p.get("C", 1.0))
-    return test, train
+            test[ci, k], train[ci, k], iters[ci, k] = logreg_fit_score(X, y, allrows[fold_id != k],
+                                                                       allrows[fold_id == k], p.get("C", 1.0))
+    return (test, train, iters) if return_n_iter else (test, train)

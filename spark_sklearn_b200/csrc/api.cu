@@ -508,13 +508,19 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
     for (int t = 0; t < n_tasks; t++) group_tasks[task_group[t]].push_back(t);
 
     // ---- 4. memory plan: kernel matrices are processed in batches that fit in free HBM ----
-    size_t free_b = 0, total_b = 0;
-    GS_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    free_b += h->dK.cap;
     const size_t kbytes = (size_t)n * ldk * 4;
-    size_t budget = (size_t)(free_b * 0.6);
-    int gpb = (int)std::max<size_t>(1, std::min<size_t>(n_groups, budget / std::max<size_t>(kbytes, 1)));
-    GS_CUDA(h->dK.reserve(kbytes * gpb));
+    int gpb = n_groups;
+    if (h->dK.cap < kbytes * (size_t)n_groups) {
+        // Ask the driver only when the buffer has to grow: cudaMemGetInfo takes anything from 0.1 to 100+ ms on a busy box
+        // (measured as 16-119 ms outliers of this phase with the Gram already in flight), and a repeated search of the same
+        // shape needs no new plan.
+        size_t free_b = 0, total_b = 0;
+        GS_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        free_b += h->dK.cap;
+        const size_t budget = (size_t)(free_b * 0.6);
+        gpb = (int)std::max<size_t>(1, std::min<size_t>(n_groups, budget / std::max<size_t>(kbytes, 1)));
+        GS_CUDA(h->dK.reserve(kbytes * gpb));
+    }
 
     GS_CUDA(h->dWork[0].reserve(rows_all.size() * 4));
     GS_CUDA(cudaMemcpyAsync(h->dWork[0].p, rows_all.data(), rows_all.size() * 4, cudaMemcpyHostToDevice, st));
@@ -552,13 +558,11 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
             pf.launches++;
             fast = fast && groups[g].first == GS_KERNEL_RBF;
         }
-        {   // the branch-free SMO instance needs rbf (QD == 1) and only positive normal floats in K
-            int special = 0;
-            GS_CUDA(cudaMemcpyAsync(&special, h->dWork[7].p, 4, cudaMemcpyDeviceToHost, st));
-            GS_CUDA(cudaStreamSynchronize(st));
-            pf.d2h_bytes += 4;
-            fast = fast && special == 0;
-        }
+        // The branch-free SMO instance needs rbf (QD == 1) and only positive normal floats in K.  The second condition is a
+        // device flag the kernel-matrix kernels raise: both instances are enqueued and the wrong one returns at once
+        // (SmoProblem::guard), so the host never waits in the middle of a search and everything it prepares below overlaps
+        // the Gram and kernel-matrix kernels already in flight.
+        const int *d_guard = fast ? h->dWork[7].as<int>() : nullptr;
         tm.mark(1);
         // -- problems: ordered by (group, task, pair); column index == problem index --
         std::vector<SmoProblem> probs;
@@ -591,6 +595,7 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
                         P.C = Cv[c] * cw[a_]; P.Cn = Cv[c] * cw[b_];
                     }
                     P.shrinking = (flags & GS_NO_SHRINKING) ? 0 : 1;
+                    P.guard = d_guard;
                     P.nslots = 0;
                     for (int e = 0; e < P.nseg; e++) P.nslots += P.seg_len[e];
                     const size_t wlen = ((size_t)std::max(P.l, P.nslots) + 3) & ~(size_t)3;   // by position or by slot, 32-byte multiples
@@ -669,8 +674,13 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
             max_slots = std::max(max_slots, probs[q].nslots);
         }
         auto launch_single = [&](const int *ord, int cnt, cudaStream_t s_, bool exclusive) -> cudaError_t {
-            if (lean_ok) return launch_smo_lean(d_probs, ord, cnt, max_slots, fast, exclusive, s_);
-            return launch_smo(d_probs, ord, cnt, lmax, fast, (int)ldk, s_, &why);
+            for (int inst = fast ? 1 : 0; inst >= 0; inst--) {              // branch-free instance, then the general one (guarded)
+                const cudaError_t e = lean_ok ? launch_smo_lean(d_probs, ord, cnt, max_slots, inst == 1, exclusive, s_)
+                                              : launch_smo(d_probs, ord, cnt, lmax, inst == 1, (int)ldk, s_, &why);
+                if (e != cudaSuccess) return e;
+                pf.launches++;
+            }
+            return cudaSuccess;
         };
         // Policy (measured on config 2 / config 4, profiles/): clusters and exclusive SMs buy LATENCY for the critical path at
         // the price of SM time (gs_svc_schedule above); a throughput-bound search (config 4) uses neither.
@@ -706,9 +716,11 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
             cudaEventRecord(ready, st);
             cudaError_t ce = cudaSuccess;
             if (n_cl > 0) {
-                ce = launch_smo_colown(d_probs, d_order, n_cl, lmax, cl, fast, st);
+                for (int inst = fast ? 1 : 0; inst >= 0 && ce == cudaSuccess; inst--) {
+                    ce = launch_smo_colown(d_probs, d_order, n_cl, lmax, cl, inst == 1, st);
+                    pf.launches++;
+                }
                 if (ce != cudaSuccess) { gs_set_error(h, std::string("launch_smo_colown: ") + cudaGetErrorString(ce)); return GS_ERR_CUDA; }
-                pf.launches++;
             }
             if (n_ex > 0) {
                 cudaEvent_t done = h->evp.get();
@@ -716,7 +728,7 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
                 launch_delay(30000, h->stream_hi);
                 ce = launch_single(d_order + n_cl, n_ex, h->stream_hi, true);
                 if (ce != cudaSuccess) { gs_set_error(h, why.empty() ? std::string("launch_smo: ") + cudaGetErrorString(ce) : why); return why.empty() ? GS_ERR_CUDA : GS_ERR_UNSUPPORTED; }
-                pf.launches += 2;
+                pf.launches++;
                 cudaEventRecord(done, h->stream_hi);
                 cudaStreamWaitEvent(st, done, 0);
             }
@@ -727,14 +739,13 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
                 launch_delay(n_ex > 0 ? 60000 : 30000, s2);
                 ce = launch_single(d_order + n_cl + n_ex, np - n_cl - n_ex, s2, false);
                 if (ce != cudaSuccess) { gs_set_error(h, why.empty() ? std::string("launch_smo: ") + cudaGetErrorString(ce) : why); return why.empty() ? GS_ERR_CUDA : GS_ERR_UNSUPPORTED; }
-                pf.launches += 2;
+                pf.launches++;
                 cudaEventRecord(done, s2);
                 cudaStreamWaitEvent(st, done, 0);
             }
         } else {
             cudaError_t ce = launch_single(d_order, np, st, false);
             if (ce != cudaSuccess) { gs_set_error(h, why.empty() ? std::string("launch_smo: ") + cudaGetErrorString(ce) : why); return why.empty() ? GS_ERR_CUDA : GS_ERR_UNSUPPORTED; }
-            pf.launches++;
         }
         tm.mark(2);
         // -- score (skipped for refit) --

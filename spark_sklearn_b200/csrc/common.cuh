@@ -144,6 +144,10 @@ struct SmoProblem {
     double *out_rho;      // out
     int *out_info;        // out: [0] n_iter [1] timed_out [2] n_sv [3] n_bounded_sv
     unsigned long long *out_ns;   // out: [0] start [1] end (globaltimer)
+    // Device flag written by kernel_matrix_kernel: != 0 when K holds a zero, denormal or negative entry.  Both solver
+    // instances are enqueued behind it; the branch-free (FAST) one returns at once when it is set, the general one when it
+    // is clear -- the choice needs no host round trip in the middle of a search.  nullptr: run unconditionally.
+    const int *guard;
     int64_t ldk;
     double C, Cn, eps;    // C of the +1 class (the pair's first class) and of the -1 class: C x class_weight
     int l, n_pos, max_iter, shrinking;

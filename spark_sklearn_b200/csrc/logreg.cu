@@ -162,13 +162,17 @@ __device__ __forceinline__ double warp_max(double v)
 struct LbLayout { int nv, nvp; };
 __device__ __forceinline__ double *vec(double *V, int which, int nvp) { return V + (size_t)which * nvp; }
 
-// One warp per column: consume the f/g just evaluated at the trial point and advance the optimiser until the next
-// trial point is ready (or the column is done).  Writes the float32 trial weights (hi/lo split) for the next GEMM.
+// One warp per fit: consume the f/g just evaluated at the trial point and advance the optimiser until the next
+// trial point is ready (or the fit is done).  Writes the float32 trial weights (hi/lo split) for the next GEMM.
+// The variables of a fit are n_class blocks of `per` entries (the first nv of each block are real: features, then the
+// intercept; binary problems have one block), i.e. n_class consecutive rows of the weight / gradient matrices of the GEMMs.
+#define LB_FOR(j) for (int j = lane; j < nvp; j += 32) if ((j % per) < nv)
 __global__ void lbfgs_advance_kernel(LbScalars *__restrict__ Sc, double *__restrict__ Vall, const float *__restrict__ Gmat,
-                                     int64_t ldg, int ncol, int nv, int nvp, int n_feat_pen, double pgtol, double factr_eps,
+                                     int64_t ldg, int ncol, int nv, int per, int n_class, int n_feat_pen, double pgtol, double factr_eps,
                                      int maxiter, int maxfun, int maxls, float *__restrict__ Wh, float *__restrict__ Wl, int64_t ldw,
                                      int *__restrict__ n_open)
 {
+    const int nvp = per * n_class;                                          // length of a fit's vectors
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= ncol) return;
     LbScalars S = Sc[c];
@@ -179,10 +183,10 @@ __global__ void lbfgs_advance_kernel(LbScalars *__restrict__ Sc, double *__restr
 
     // ---- finish f and g at the trial point: f = loss/n + (l2/2)|w|^2, g = G + l2 w (intercept not penalised) ----
     double ww = 0;
-    for (int j = lane; j < nv; j += 32) {
+    LB_FOR(j) {
         const double w = x[j];
         double gj = (double)Gmat[(size_t)c * ldg + j];
-        if (j < n_feat_pen) { gj += S.l2 * w; ww += w * w; }
+        if ((j % per) < n_feat_pen) { gj += S.l2 * w; ww += w * w; }
         g[j] = gj;
     }
     ww = warp_sum(ww);
@@ -193,14 +197,14 @@ __global__ void lbfgs_advance_kernel(LbScalars *__restrict__ Sc, double *__restr
     if (S.task == T_FG_START) {
         S.f = f;
         double m = 0;
-        for (int j = lane; j < nv; j += 32) m = fmax(m, fabs(g[j]));
+        LB_FOR(j) m = fmax(m, fabs(g[j]));
         S.sbgnrm = warp_max(m);
         if (S.sbgnrm <= pgtol) { S.task = T_DONE; S.reason = R_PGTOL; }
         else need_direction = true;
     } else {
         // ---- inside the line search (lnsrlb): gd = g.d at the trial point ----
         double gd = 0;
-        for (int j = lane; j < nv; j += 32) gd += g[j] * d[j];
+        LB_FOR(j) gd += g[j] * d[j];
         gd = warp_sum(gd);
         S.gd = gd;
         const int ret = dcsrch(S, f, gd, false);
@@ -208,19 +212,19 @@ __global__ void lbfgs_advance_kernel(LbScalars *__restrict__ Sc, double *__restr
             S.iback++;
             if (S.iback >= maxls) {
                 // too many backtracks: restore the point; refresh the memory or give up (lnsrlb info = -3... handling)
-                for (int j = lane; j < nv; j += 32) { x[j] = t[j]; g[j] = r[j]; }
+                LB_FOR(j) { x[j] = t[j]; g[j] = r[j]; }
                 S.f = S.fold;
                 if (S.col == 0) { S.task = T_DONE; S.reason = R_ABNORMAL; }
                 else { S.col = 0; S.head = 0; S.theta = 1.0; S.fresh = 1; need_direction = true; }
             } else {
-                for (int j = lane; j < nv; j += 32) x[j] = (S.stp == 1.0) ? t[j] + d[j] : S.stp * d[j] + t[j];
+                LB_FOR(j) x[j] = (S.stp == 1.0) ? t[j] + d[j] : S.stp * d[j] + t[j];
             }
         } else {
             // ---- line search finished: new iterate ----
             S.f = f;
             S.iter++;
             double m = 0;
-            for (int j = lane; j < nv; j += 32) m = fmax(m, fabs(g[j]));
+            LB_FOR(j) m = fmax(m, fabs(g[j]));
             S.sbgnrm = warp_max(m);
             if (S.iter >= maxiter) { S.task = T_DONE; S.reason = R_MAXITER; }
             else if (S.nfev > maxfun) { S.task = T_DONE; S.reason = R_MAXFUN; }
@@ -231,16 +235,16 @@ __global__ void lbfgs_advance_kernel(LbScalars *__restrict__ Sc, double *__restr
                 else {
                     // ---- BFGS pair: y = g - g_old, s = stp * d (mainlb after label 777) ----
                     double rr = 0, dr, ddum2;
-                    for (int j = lane; j < nv; j += 32) { const double yj = g[j] - r[j]; r[j] = yj; rr += yj * yj; }
+                    LB_FOR(j) { const double yj = g[j] - r[j]; r[j] = yj; rr += yj * yj; }
                     rr = warp_sum(rr);
                     if (S.stp == 1.0) { dr = S.gd - S.gdold; ddum2 = -S.gdold; }
                     else {
                         dr = (S.gd - S.gdold) * S.stp; ddum2 = -S.gdold * S.stp;
-                        for (int j = lane; j < nv; j += 32) d[j] *= S.stp;
+                        LB_FOR(j) d[j] *= S.stp;
                     }
                     if (!(dr <= EPSMCH * ddum2)) {
                         const int slot = S.col < MCOR ? (S.head + S.col) % MCOR : S.head;
-                        for (int j = lane; j < nv; j += 32) { WS[(size_t)slot * nvp + j] = d[j]; WY[(size_t)slot * nvp + j] = r[j]; }
+                        LB_FOR(j) { WS[(size_t)slot * nvp + j] = d[j]; WY[(size_t)slot * nvp + j] = r[j]; }
                         S.rho[slot] = 1.0 / dr;
                         if (S.col < MCOR) S.col++; else S.head = (S.head + 1) % MCOR;
                         S.theta = rr / dr;
@@ -255,34 +259,34 @@ __global__ void lbfgs_advance_kernel(LbScalars *__restrict__ Sc, double *__restr
         // ---- direction d = -H g: two-loop recursion, H0 = I/theta (== L-BFGS-B subspace step with no active bound) ----
         __syncwarp();
         double alpha_i[MCOR];
-        for (int j = lane; j < nv; j += 32) d[j] = g[j];                      // q
+        LB_FOR(j) d[j] = g[j];                      // q
         for (int k = S.col - 1; k >= 0; k--) {
             const int slot = (S.head + k) % MCOR;
             double a = 0;
-            for (int j = lane; j < nv; j += 32) a += WS[(size_t)slot * nvp + j] * d[j];
+            LB_FOR(j) a += WS[(size_t)slot * nvp + j] * d[j];
             a = warp_sum(a) * S.rho[slot];
             alpha_i[k] = a;
-            for (int j = lane; j < nv; j += 32) d[j] -= a * WY[(size_t)slot * nvp + j];
+            LB_FOR(j) d[j] -= a * WY[(size_t)slot * nvp + j];
         }
         const double h0 = 1.0 / S.theta;
-        for (int j = lane; j < nv; j += 32) d[j] *= h0;
+        LB_FOR(j) d[j] *= h0;
         for (int k = 0; k < S.col; k++) {
             const int slot = (S.head + k) % MCOR;
             double b = 0;
-            for (int j = lane; j < nv; j += 32) b += WY[(size_t)slot * nvp + j] * d[j];
+            LB_FOR(j) b += WY[(size_t)slot * nvp + j] * d[j];
             b = warp_sum(b) * S.rho[slot];
             const double cf = alpha_i[k] - b;
-            for (int j = lane; j < nv; j += 32) d[j] += cf * WS[(size_t)slot * nvp + j];
+            LB_FOR(j) d[j] += cf * WS[(size_t)slot * nvp + j];
         }
         double dtd = 0, gd = 0;
-        for (int j = lane; j < nv; j += 32) { const double dj = -d[j]; d[j] = dj; dtd += dj * dj; gd += g[j] * dj; }
+        LB_FOR(j) { const double dj = -d[j]; d[j] = dj; dtd += dj * dj; gd += g[j] * dj; }
         dtd = warp_sum(dtd); gd = warp_sum(gd);
         if (gd >= 0.0) {                                                    // not a descent direction: refresh the memory
             if (S.col == 0) { S.task = T_DONE; S.reason = R_ABNORMAL; }
             else {
                 S.col = 0; S.head = 0; S.theta = 1.0;
                 dtd = 0; gd = 0;
-                for (int j = lane; j < nv; j += 32) { const double dj = -g[j]; d[j] = dj; dtd += dj * dj; gd += g[j] * dj; }
+                LB_FOR(j) { const double dj = -g[j]; d[j] = dj; dtd += dj * dj; gd += g[j] * dj; }
                 dtd = warp_sum(dtd); gd = warp_sum(gd);
             }
         }
@@ -291,9 +295,9 @@ __global__ void lbfgs_advance_kernel(LbScalars *__restrict__ Sc, double *__restr
             S.dnorm = sqrt(dtd);
             S.stp = S.iter == 0 ? fmin(1.0 / S.dnorm, STPMX) : 1.0;
             S.fold = S.f; S.iback = 0; S.gd = gd; S.gdold = gd;
-            for (int j = lane; j < nv; j += 32) { t[j] = x[j]; r[j] = g[j]; }
+            LB_FOR(j) { t[j] = x[j]; r[j] = g[j]; }
             dcsrch(S, S.f, gd, true);
-            for (int j = lane; j < nv; j += 32) x[j] = (S.stp == 1.0) ? t[j] + d[j] : S.stp * d[j] + t[j];
+            LB_FOR(j) x[j] = (S.stp == 1.0) ? t[j] + d[j] : S.stp * d[j] + t[j];
             S.task = T_FG_LNSRCH;
         }
     }
@@ -301,7 +305,7 @@ __global__ void lbfgs_advance_kernel(LbScalars *__restrict__ Sc, double *__restr
     // ---- publish: scalars, and the float32 trial point for the next evaluation ----
     if (S.task != T_DONE) {
         for (int j = lane; j < nvp; j += 32) {
-            const float v = j < nv ? (float)x[j] : 0.f;
+            const float v = (j % per) < nv ? (float)x[j] : 0.f;
             const float hh = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
             Wh[(size_t)c * ldw + j] = hh; Wl[(size_t)c * ldw + j] = v - hh;
         }
@@ -312,13 +316,13 @@ __global__ void lbfgs_advance_kernel(LbScalars *__restrict__ Sc, double *__restr
 }
 
 // write float32 weights of every column (final iterate) for the scoring GEMM
-__global__ void lbfgs_export_kernel(const double *__restrict__ Vall, int ncol, int nv, int nvp, float *__restrict__ Wh,
+__global__ void lbfgs_export_kernel(const double *__restrict__ Vall, int ncol, int nv, int per, int n_class, float *__restrict__ Wh,
                                     float *__restrict__ Wl, int64_t ldw)
 {
-    const int c = blockIdx.x;
+    const int c = blockIdx.x, nvp = per * n_class;
     const double *x = Vall + (size_t)c * (5 + 2 * MCOR) * nvp;
     for (int j = threadIdx.x; j < nvp; j += blockDim.x) {
-        const float v = j < nv ? (float)x[j] : 0.f;
+        const float v = (j % per) < nv ? (float)x[j] : 0.f;
         const float hh = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
         Wh[(size_t)c * ldw + j] = hh; Wl[(size_t)c * ldw + j] = v - hh;
     }
@@ -422,6 +426,96 @@ __global__ void logistic_classes_kernel(const float *__restrict__ Zt, int64_t ld
     if (threadIdx.x < 12 && sh[threadIdx.x]) atomicAdd(&counts[(size_t)c * 12 + threadIdx.x], sh[threadIdx.x]);
 }
 
+// Multinomial counterpart of logistic_residual_kernel (n_class >= 3: sklearn/_loss/_loss.pyx closs_grad_half_multinomial --
+// loss_i = logsumexp(z_i) - z_i[y_i], gradient softmax(z_i) - onehot(y_i)).  A fit owns n_class consecutive rows of Z^T / R.
+__global__ void multinomial_residual_kernel(const float *__restrict__ Zt, int64_t ldz, int n, int K, const int *__restrict__ y,
+                                            SplitMasks sm, const int *__restrict__ fold_of_col,
+                                            const double *__restrict__ inv_ntrain, const float *__restrict__ cw /* [nfit][K] or null */,
+                                            LbScalars *__restrict__ Sc, float *__restrict__ Rh, float *__restrict__ Rl)
+{
+    const int f = blockIdx.y;
+    if (Sc[f].task == T_DONE) return;
+    const int fc = fold_of_col[f];
+    const float invn = (float)inv_ntrain[f];
+    double acc = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const size_t base = (size_t)f * K * ldz + i;
+        if (split_train(sm, i, fc)) {
+            float mx = -INFINITY;
+            for (int k = 0; k < K; k++) mx = fmaxf(mx, Zt[base + (size_t)k * ldz]);
+            float se = 0.f;
+            for (int k = 0; k < K; k++) se += expf(Zt[base + (size_t)k * ldz] - mx);
+            const int yi = y[i];
+            const float wi = cw ? cw[(size_t)f * K + yi] : 1.f;
+            acc += (double)(wi * (logf(se) + mx - Zt[base + (size_t)yi * ldz]));
+            const float inv_se = 1.f / se;
+            for (int k = 0; k < K; k++) {
+                const float p = expf(Zt[base + (size_t)k * ldz] - mx) * inv_se;
+                const float rres = (wi * (p - (k == yi ? 1.f : 0.f))) * invn;
+                const float hh = __uint_as_float(__float_as_uint(rres) & 0xffffe000u);
+                Rh[base + (size_t)k * ldz] = hh; Rl[base + (size_t)k * ldz] = rres - hh;
+            }
+        } else {
+            for (int k = 0; k < K; k++) { Rh[base + (size_t)k * ldz] = 0.f; Rl[base + (size_t)k * ldz] = 0.f; }
+        }
+    }
+    __shared__ double sh[8];
+#pragma unroll
+    for (int m = 16; m; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += sh[w];
+        atomicAdd(&Sc[f].loss_acc, s * inv_ntrain[f]);
+    }
+}
+
+// Multinomial predictions (first arg-max of the n_class decision values, like np.argmax in LinearClassifierMixin.predict):
+// accuracy counts [nfit][4] and, when ccounts != null, the per-class counts [nfit][2 splits][K][3] of the count-based scorers
+__global__ void multinomial_count_kernel(const float *__restrict__ Zt, int64_t ldz, int n, int K, const int *__restrict__ y,
+                                         SplitMasks sm, const int *__restrict__ fold_of_col, int *__restrict__ counts,
+                                         int *__restrict__ ccounts)
+{
+    extern __shared__ int shc[];                                         // [2][K][3]
+    const int f = blockIdx.y, fc = fold_of_col[f];
+    if (ccounts) {
+        for (int e = threadIdx.x; e < 6 * K; e += blockDim.x) shc[e] = 0;
+        __syncthreads();
+    }
+    int cte = 0, nte = 0, ctr = 0, ntr = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const size_t base = (size_t)f * K * ldz + i;
+        int pred = 0;
+        float best = Zt[base];
+        for (int k = 1; k < K; k++) { const float z = Zt[base + (size_t)k * ldz]; if (z > best) { best = z; pred = k; } }
+        const int yc = y[i];
+        const bool ok = pred == yc;
+        const int sp = split_test(sm, i, fc) ? 0 : (split_train(sm, i, fc) ? 1 : 2);
+        if (sp == 0) { nte++; cte += ok; }
+        if (sp == 1) { ntr++; ctr += ok; }
+        if (ccounts && sp < 2) {
+            atomicAdd(&shc[(sp * K + yc) * 3 + 0], 1);
+            if (ok) atomicAdd(&shc[(sp * K + yc) * 3 + 1], 1);
+            atomicAdd(&shc[(sp * K + pred) * 3 + 2], 1);
+        }
+    }
+#pragma unroll
+    for (int m = 16; m; m >>= 1) {
+        cte += __shfl_xor_sync(0xffffffffu, cte, m); nte += __shfl_xor_sync(0xffffffffu, nte, m);
+        ctr += __shfl_xor_sync(0xffffffffu, ctr, m); ntr += __shfl_xor_sync(0xffffffffu, ntr, m);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&counts[f * 4 + 0], cte); atomicAdd(&counts[f * 4 + 1], nte);
+        atomicAdd(&counts[f * 4 + 2], ctr); atomicAdd(&counts[f * 4 + 3], ntr);
+    }
+    if (ccounts) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < 6 * K; e += blockDim.x)
+            if (shc[e]) atomicAdd(&ccounts[(size_t)f * 6 * K + e], shc[e]);
+    }
+}
+
 // Xa = [X | 1] padded to [n][nvp] and its transpose [nvp][npad]
 __global__ void build_xa_kernel(const float *__restrict__ X, int n, int d, int fit_intercept, int nvp, int64_t npad,
                                 float *__restrict__ Xa, float *__restrict__ Xat)
@@ -446,7 +540,8 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
 {
     if (!h) return GS_ERR_ARG;
     if (h->n == 0) { gs_set_error(h, "gs_logreg: no dataset (call gs_set_data first)"); return GS_ERR_NO_DATA; }
-    if (!h->classification || h->n_classes != 2) { gs_set_error(h, "gs_logreg: needs a binary classification dataset"); return GS_ERR_UNSUPPORTED; }
+    if (!h->classification || h->n_classes < 2) { gs_set_error(h, "gs_logreg: needs a classification dataset with at least two classes"); return GS_ERR_UNSUPPORTED; }
+    if (h->n_classes > 64) { gs_set_error(h, "gs_logreg: more than 64 classes is not supported"); return GS_ERR_UNSUPPORTED; }
     if (n_cand <= 0 || !Cv) { gs_set_error(h, "gs_logreg: bad arguments"); return GS_ERR_ARG; }
     for (int c = 0; c < n_cand; c++)
         if (!(Cv[c] > 0)) { gs_set_error(h, "gs_logreg: C must be > 0"); return GS_ERR_ARG; }
@@ -455,7 +550,11 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
     const int n = (int)h->n, d = (int)h->d, ns = refit ? 1 : h->n_splits;
     const int nv = d + (fit_intercept ? 1 : 0), nvp = (nv + 31) & ~31;
     const int64_t npad = ((int64_t)n + 31) & ~31LL;
-    const int ncol = n_cand * ns;
+    const int nfit = n_cand * ns;                              // optimiser instances: one per (candidate, split)
+    const int nc = h->n_classes;
+    const int KC = nc > 2 ? nc : 1;                            // weight rows of a fit: 1 (binary: the class-1 logit) or one per class (multinomial)
+    const int ncol = nfit * KC;                                // rows of W / Z^T / R / G in the two contractions
+    const bool multi = KC > 1;
 
     h->evp.reset(); h->tt.reset();
     cudaEvent_t ev[3];
@@ -471,9 +570,9 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
     GS_CUDA(bR.reserve((size_t)ncol * npad * 4 * 2));
     const int nchunk = (int)((npad + GRAD_KCHUNK - 1) / GRAD_KCHUNK);          // split-K of the gradient contraction
     GS_CUDA(bW.reserve((size_t)ncol * nvp * 4 * (3 + (size_t)nchunk)));
-    GS_CUDA(bV.reserve((size_t)ncol * (5 + 2 * MCOR) * nvp * 8));
-    GS_CUDA(bS.reserve((size_t)ncol * sizeof(LbScalars)));
-    GS_CUDA(bMeta.reserve((size_t)ncol * (4 + 8 + 16 + 8) + (size_t)(nchunk + 4) * sizeof(TcBatch) + 256));
+    GS_CUDA(bV.reserve((size_t)ncol * (5 + 2 * MCOR) * nvp * 8));          // nfit vectors of KC * nvp
+    GS_CUDA(bS.reserve((size_t)nfit * sizeof(LbScalars)));
+    GS_CUDA(bMeta.reserve((size_t)nfit * (4 + 8 + 16) + (size_t)nfit * std::max(2, KC) * 4 + (size_t)(nchunk + 4) * sizeof(TcBatch) + 256));
     float *dXa = bXa.as<float>(), *dXat = dXa + (size_t)n * nvp;
     // hi parts of [Xa | Xa^T] contiguous, then the lo parts: one split launch covers both matrices
     float *dXah = bXs.as<float>(), *dXath = dXah + (size_t)n * nvp, *dXal = dXath + (size_t)nvp * npad, *dXatl = dXal + (size_t)n * nvp;
@@ -482,34 +581,38 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
     double *dV = bV.as<double>();
     LbScalars *dS = bS.as<LbScalars>();
     unsigned char *mp = bMeta.as<unsigned char>();
-    double *dInv = reinterpret_cast<double *>(mp); mp += (size_t)ncol * 8;
-    float *dCwBuf = reinterpret_cast<float *>(mp); mp += (size_t)ncol * 8;
-    int *dFoldOf = reinterpret_cast<int *>(mp); mp += (size_t)ncol * 4;
-    int *dCounts = reinterpret_cast<int *>(mp); mp += (size_t)ncol * 16;
+    const int CWS = std::max(2, KC);                           // class weights of a fit
+    double *dInv = reinterpret_cast<double *>(mp); mp += (size_t)nfit * 8;
+    float *dCwBuf = reinterpret_cast<float *>(mp); mp += (size_t)nfit * CWS * 4;
+    int *dFoldOf = reinterpret_cast<int *>(mp); mp += (size_t)nfit * 4;
+    int *dCounts = reinterpret_cast<int *>(mp); mp += (size_t)nfit * 16;
     int *dOpen = reinterpret_cast<int *>(mp); mp += 16;
     TcBatch *dBatch = reinterpret_cast<TcBatch *>(((uintptr_t)mp + 15) & ~(uintptr_t)15);
 
     // per-column constants
-    std::vector<int> ntrain(std::max(ns, 1), 0), ntrain1(std::max(ns, 1), 0);   // training rows of every split, and those of class 1
+    std::vector<int> ntrain(std::max(ns, 1), 0), ntrain_c((size_t)std::max(ns, 1) * nc, 0);   // training rows of every split, and per class
     for (int k = 0; k < ns; k++)
         for (int i = 0; i < n; i++)
-            if (refit || h->is_train(i, k)) { ntrain[k]++; ntrain1[k] += h->yc[i] == 1; }
+            if (refit || h->is_train(i, k)) { ntrain[k]++; ntrain_c[(size_t)k * nc + h->yc[i]]++; }
     const bool weighted = h->class_w_sets > 0;
     if (weighted && h->class_w_sets != 1 && h->class_w_sets != ns) {
         gs_set_error(h, "gs_logreg: gs_set_class_weight was given a weight set per split, but not for this number of splits"); return GS_ERR_ARG;
     }
-    std::vector<float> cwcol((size_t)ncol * 2, 1.f);
-    std::vector<LbScalars> hs(ncol);
-    std::vector<double> inv(ncol);
-    std::vector<int> foldof(ncol);
+    std::vector<float> cwcol((size_t)nfit * CWS, 1.f);
+    std::vector<LbScalars> hs(nfit);
+    std::vector<double> inv(nfit);
+    std::vector<int> foldof(nfit);
     for (int c = 0; c < n_cand; c++)
         for (int k = 0; k < ns; k++) {
             const int col = c * ns + k;
             double sw_sum = (double)ntrain[k];                     // sum of the sample weights of the training rows
             if (weighted) {
-                const double *cw = &h->class_w[(size_t)(h->class_w_sets == 1 ? 0 : k) * 2];
-                cwcol[(size_t)col * 2] = (float)cw[0]; cwcol[(size_t)col * 2 + 1] = (float)cw[1];
-                sw_sum = (double)((float)cw[0]) * (ntrain[k] - ntrain1[k]) + (double)((float)cw[1]) * ntrain1[k];
+                const double *cw = &h->class_w[(size_t)(h->class_w_sets == 1 ? 0 : k) * nc];
+                sw_sum = 0;
+                for (int q = 0; q < nc; q++) {
+                    cwcol[(size_t)col * CWS + q] = (float)cw[q];
+                    sw_sum += (double)((float)cw[q]) * ntrain_c[(size_t)k * nc + q];
+                }
             }
             memset(&hs[col], 0, sizeof(LbScalars));
             hs[col].task = T_FG_START; hs[col].theta = 1.0; hs[col].fresh = 1;
@@ -517,14 +620,14 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
             inv[col] = 1.0 / sw_sum;
             foldof[col] = refit ? -100 : k;
         }
-    GS_CUDA(cudaMemcpyAsync(dS, hs.data(), (size_t)ncol * sizeof(LbScalars), cudaMemcpyHostToDevice, st));
-    GS_CUDA(cudaMemcpyAsync(dInv, inv.data(), (size_t)ncol * 8, cudaMemcpyHostToDevice, st));
+    GS_CUDA(cudaMemcpyAsync(dS, hs.data(), (size_t)nfit * sizeof(LbScalars), cudaMemcpyHostToDevice, st));
+    GS_CUDA(cudaMemcpyAsync(dInv, inv.data(), (size_t)nfit * 8, cudaMemcpyHostToDevice, st));
     const float *dCw = nullptr;
     if (weighted) {
-        GS_CUDA(cudaMemcpyAsync(dCwBuf, cwcol.data(), (size_t)ncol * 8, cudaMemcpyHostToDevice, st));
+        GS_CUDA(cudaMemcpyAsync(dCwBuf, cwcol.data(), cwcol.size() * 4, cudaMemcpyHostToDevice, st));
         dCw = dCwBuf;
     }
-    GS_CUDA(cudaMemcpyAsync(dFoldOf, foldof.data(), (size_t)ncol * 4, cudaMemcpyHostToDevice, st));
+    GS_CUDA(cudaMemcpyAsync(dFoldOf, foldof.data(), (size_t)nfit * 4, cudaMemcpyHostToDevice, st));
     GS_CUDA(cudaMemsetAsync(dV, 0, (size_t)ncol * (5 + 2 * MCOR) * nvp * 8, st));        // x0 = 0
     GS_CUDA(cudaMemsetAsync(dWh, 0, (size_t)ncol * nvp * 4 * 2, st));                      // trial point = x0
     GS_CUDA(cudaMemsetAsync(dRh, 0, (size_t)ncol * npad * 4 * 2, st));
@@ -558,16 +661,17 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
         h->tt.begin(h->evp, st);
         GS_CUDA(launch_gemm_nt_tf32x3(mWh, mWl, mXh, mXl, dBatch, 1, ncol, n, 1.0f, false, st));
         h->tt.end(h->evp, st, 3.0 * 2.0 * (double)ncol * n * nvp);
-        dim3 grid(64, ncol);
-        logistic_residual_kernel<<<grid, 256, 0, st>>>(dZ, npad, n, h->dY.as<int>(), h->masks(), dFoldOf, dInv, dCw, dS, dRh, dRl);
+        dim3 grid(64, nfit);
+        if (multi) multinomial_residual_kernel<<<grid, 256, 0, st>>>(dZ, npad, n, KC, h->dY.as<int>(), h->masks(), dFoldOf, dInv, dCw, dS, dRh, dRl);
+        else logistic_residual_kernel<<<grid, 256, 0, st>>>(dZ, npad, n, h->dY.as<int>(), h->masks(), dFoldOf, dInv, dCw, dS, dRh, dRl);
         GS_CUDA(cudaGetLastError());
         h->tt.begin(h->evp, st);
         GS_CUDA(launch_gemm_nt_tf32x3(mRh, mRl, mXth, mXtl, dBatch + 1, nchunk, ncol, nv, 1.0f, false, st));
         h->tt.end(h->evp, st, 3.0 * 2.0 * (double)ncol * nv * (double)npad);
         GS_CUDA(launch_sum_partials(dGp, nchunk, (int64_t)ncol * nvp, dG, st));
         GS_CUDA(cudaMemsetAsync(dOpen, 0, 4, st));
-        lbfgs_advance_kernel<<<(ncol + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
-            dS, dV, dG, nvp, ncol, nv, nvp, d, tol, factr_eps, max_iter, maxfun, 50, dWh, dWl, nvp, dOpen);
+        lbfgs_advance_kernel<<<(nfit + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
+            dS, dV, dG, (int64_t)nvp * KC, nfit, nv, nvp, KC, d, tol, factr_eps, max_iter, maxfun, 50, dWh, dWl, (int64_t)nvp * KC, dOpen);
         GS_CUDA(cudaGetLastError());
         GS_CUDA(cudaMemcpyAsync(&open, dOpen, 4, cudaMemcpyDeviceToHost, st));
         GS_CUDA(cudaStreamSynchronize(st));
@@ -576,50 +680,70 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
     }
     cudaEventRecord(ev[1], st);
 
-    std::vector<LbScalars> fin(ncol);
-    GS_CUDA(cudaMemcpyAsync(fin.data(), dS, (size_t)ncol * sizeof(LbScalars), cudaMemcpyDeviceToHost, st));
+    std::vector<LbScalars> fin(nfit);
+    GS_CUDA(cudaMemcpyAsync(fin.data(), dS, (size_t)nfit * sizeof(LbScalars), cudaMemcpyDeviceToHost, st));
     if (!refit) {
         // ---- scoring: z at the final iterate for every row, accuracy split by fold ----
-        lbfgs_export_kernel<<<ncol, 128, 0, st>>>(dV, ncol, nv, nvp, dWh, dWl, nvp);
+        lbfgs_export_kernel<<<nfit, 128, 0, st>>>(dV, nfit, nv, nvp, KC, dWh, dWl, (int64_t)nvp * KC);
         GS_CUDA(cudaGetLastError());
         h->tt.begin(h->evp, st);
         GS_CUDA(launch_gemm_nt_tf32x3(mWh, mWl, mXh, mXl, dBatch, 1, ncol, n, 1.0f, false, st));
         h->tt.end(h->evp, st, 3.0 * 2.0 * (double)ncol * n * nvp);
-        GS_CUDA(cudaMemsetAsync(dCounts, 0, (size_t)ncol * 16, st));
-        dim3 grid(64, ncol);
-        logistic_count_kernel<<<grid, 256, 0, st>>>(dZ, npad, n, h->dY.as<int>(), h->masks(), dFoldOf, dCounts);
-        GS_CUDA(cudaGetLastError());
-        launches += 3;
-        std::vector<int> counts((size_t)ncol * 4);
-        GS_CUDA(cudaMemcpyAsync(counts.data(), dCounts, counts.size() * 4, cudaMemcpyDeviceToHost, st));
-        // non-default scorers (gs_set_scoring): class counts or ROC-AUC pair counts from the z values already in HBM
+        GS_CUDA(cudaMemsetAsync(dCounts, 0, (size_t)nfit * 16, st));
+        dim3 grid(64, nfit);
         const int kind = h->score_kind;
+        if (kind == GS_SCORE_NEG_MSE || kind == GS_SCORE_NEG_RMSE) { gs_set_error(h, "gs_logreg: regression scorer on a classifier"); return GS_ERR_ARG; }
+        if (multi && (kind == GS_SCORE_ROC_AUC || kind == GS_SCORE_F1 || kind == GS_SCORE_PRECISION || kind == GS_SCORE_RECALL)) {
+            gs_set_error(h, "gs_logreg: this scorer is defined for binary problems only"); return GS_ERR_UNSUPPORTED;
+        }
+        // non-default scorers (gs_set_scoring): class counts or ROC-AUC pair counts from the z values already in HBM
         std::vector<int> ccounts;
         std::vector<unsigned long long> araw;
+        const int per_fit = 6 * nc;                                          // [2 splits][nc][support, tp, predicted]
+        if (multi) {
+            int *d_cc = nullptr;
+            if (kind != GS_SCORE_DEFAULT) {
+                GS_CUDA(h->dScore.reserve((size_t)nfit * per_fit * 4));
+                GS_CUDA(cudaMemsetAsync(h->dScore.p, 0, (size_t)nfit * per_fit * 4, st));
+                d_cc = h->dScore.as<int>();
+            }
+            multinomial_count_kernel<<<grid, 256, (size_t)per_fit * 4, st>>>(dZ, npad, n, KC, h->dY.as<int>(), h->masks(), dFoldOf, dCounts, d_cc);
+            GS_CUDA(cudaGetLastError());
+            if (d_cc) {
+                ccounts.resize((size_t)nfit * per_fit);
+                GS_CUDA(cudaMemcpyAsync(ccounts.data(), d_cc, ccounts.size() * 4, cudaMemcpyDeviceToHost, st));
+            }
+        } else {
+            logistic_count_kernel<<<grid, 256, 0, st>>>(dZ, npad, n, h->dY.as<int>(), h->masks(), dFoldOf, dCounts);
+            GS_CUDA(cudaGetLastError());
+        }
+        launches += 3;
+        std::vector<int> counts((size_t)nfit * 4);
+        GS_CUDA(cudaMemcpyAsync(counts.data(), dCounts, counts.size() * 4, cudaMemcpyDeviceToHost, st));
         if (kind == GS_SCORE_ROC_AUC) {
-            std::vector<int> meta((size_t)ncol * 2);
-            for (int col = 0; col < ncol; col++) { meta[col] = col; meta[ncol + col] = refit ? -100 : col % ns; }
-            GS_CUDA(h->dScore.reserve((size_t)ncol * 40));
+            std::vector<int> meta((size_t)nfit * 2);
+            for (int col = 0; col < nfit; col++) { meta[col] = col; meta[nfit + col] = refit ? -100 : col % ns; }
+            GS_CUDA(h->dScore.reserve((size_t)nfit * 40));
             unsigned long long *d_auc = h->dScore.as<unsigned long long>();
-            int *d_meta = (int *)(d_auc + (size_t)ncol * 4);
+            int *d_meta = (int *)(d_auc + (size_t)nfit * 4);
             GS_CUDA(cudaMemcpyAsync(d_meta, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice, st));
-            GS_CUDA(cudaMemsetAsync(d_auc, 0, (size_t)ncol * 32, st));
-            GS_CUDA(launch_auc_pairs_f32(dZ, npad, n, h->class_start[1], h->masks(), d_meta, d_meta + ncol, ncol, +1, d_auc, st));
-            araw.resize((size_t)ncol * 4);
-            GS_CUDA(cudaMemcpyAsync(araw.data(), d_auc, (size_t)ncol * 32, cudaMemcpyDeviceToHost, st));
+            GS_CUDA(cudaMemsetAsync(d_auc, 0, (size_t)nfit * 32, st));
+            GS_CUDA(launch_auc_pairs_f32(dZ, npad, n, h->class_start[1], h->masks(), d_meta, d_meta + nfit, nfit, +1, d_auc, st));
+            araw.resize((size_t)nfit * 4);
+            GS_CUDA(cudaMemcpyAsync(araw.data(), d_auc, (size_t)nfit * 32, cudaMemcpyDeviceToHost, st));
             launches++;
-        } else if (kind != GS_SCORE_DEFAULT) {
-            GS_CUDA(h->dScore.reserve((size_t)ncol * 48));
-            GS_CUDA(cudaMemsetAsync(h->dScore.p, 0, (size_t)ncol * 48, st));
+        } else if (kind != GS_SCORE_DEFAULT && !multi) {
+            GS_CUDA(h->dScore.reserve((size_t)nfit * 48));
+            GS_CUDA(cudaMemsetAsync(h->dScore.p, 0, (size_t)nfit * 48, st));
             logistic_classes_kernel<<<grid, 256, 0, st>>>(dZ, npad, n, h->dY.as<int>(), h->masks(), dFoldOf, h->dScore.as<int>());
             GS_CUDA(cudaGetLastError());
-            ccounts.resize((size_t)ncol * 12);
+            ccounts.resize((size_t)nfit * 12);
             GS_CUDA(cudaMemcpyAsync(ccounts.data(), h->dScore.p, ccounts.size() * 4, cudaMemcpyDeviceToHost, st));
             launches++;
         }
         cudaEventRecord(ev[2], st);
         GS_CUDA(cudaStreamSynchronize(st));
-        for (int col = 0; col < ncol; col++) {
+        for (int col = 0; col < nfit; col++) {
             const int *cn = &counts[(size_t)col * 4];
             if (kind == GS_SCORE_DEFAULT) {
                 test_scores[col] = cn[1] > 0 ? (double)cn[0] / cn[1] : NAN;
@@ -636,21 +760,23 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
                 test_scores[col] = na_te * nb_te > 0 ? ((double)a[0] + 0.5 * (double)a[1]) / (na_te * nb_te) : NAN;
                 if (train_scores) train_scores[col] = na_tr * nb_tr > 0 ? ((double)a[2] + 0.5 * (double)a[3]) / (na_tr * nb_tr) : NAN;
             } else {
-                test_scores[col] = gs_score_from_counts(kind, h->score_pos, 2, &ccounts[(size_t)col * 12]);
-                if (train_scores) train_scores[col] = gs_score_from_counts(kind, h->score_pos, 2, &ccounts[(size_t)col * 12 + 6]);
+                test_scores[col] = gs_score_from_counts(kind, h->score_pos, nc, &ccounts[(size_t)col * per_fit]);
+                if (train_scores) train_scores[col] = gs_score_from_counts(kind, h->score_pos, nc, &ccounts[(size_t)col * per_fit + 3 * nc]);
             }
             if (n_iter) n_iter[col] = fin[col].iter;
         }
     } else {
-        std::vector<double> x(nvp);
-        GS_CUDA(cudaMemcpyAsync(x.data(), dV, (size_t)nvp * 8, cudaMemcpyDeviceToHost, st));
+        std::vector<double> x((size_t)nvp * KC);
+        GS_CUDA(cudaMemcpyAsync(x.data(), dV, x.size() * 8, cudaMemcpyDeviceToHost, st));
         cudaEventRecord(ev[2], st);
         GS_CUDA(cudaStreamSynchronize(st));
-        for (int j = 0; j < d; j++) coef_out[j] = x[j];
-        coef_out[d] = fit_intercept ? x[d] : 0.0;
+        for (int q = 0; q < KC; q++) {                                       // [KC][d + 1]: weights, then the intercept
+            for (int j = 0; j < d; j++) coef_out[(size_t)q * (d + 1) + j] = x[(size_t)q * nvp + j];
+            coef_out[(size_t)q * (d + 1) + d] = fit_intercept ? x[(size_t)q * nvp + d] : 0.0;
+        }
         if (n_iter) n_iter[0] = fin[0].iter;
     }
-    for (int col = 0; col < ncol; col++)
+    for (int col = 0; col < nfit; col++)
         if (fin[col].task != T_DONE) { gs_set_error(h, "gs_logreg: optimiser did not terminate"); return GS_ERR_NUMERIC; }
     cudaEventElapsedTime(ms_solve, ev[0], ev[1]);
     cudaEventElapsedTime(ms_score, ev[1], ev[2]);
@@ -662,7 +788,7 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
     pf.launches = launches;
     pf.smo_iterations = rounds;                                 // function-evaluation rounds
     pf.gram_flops = (double)rounds * 2.0 * 2.0 * (double)n * nv * ncol;
-    pf.d2h_bytes = (int64_t)ncol * (16 + sizeof(LbScalars));
+    pf.d2h_bytes = (int64_t)nfit * (16 + sizeof(LbScalars));
     pf.ms_tensor = h->tt.collect(); pf.tensor_flops = h->tt.flops;
     return GS_OK;
 }

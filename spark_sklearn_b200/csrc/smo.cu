@@ -56,6 +56,7 @@ smo_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order, 
     constexpr int LCAP = NT * KPT;                                          // compile-time layout: no address math
 
     const SmoProblem *__restrict__ Pp = probs + order[blockIdx.x];
+    if (Pp->guard != nullptr && (*Pp->guard != 0) == FAST) return;       // the other instance solves this launch (common.cuh)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int l = Pp->l;
     // ---- resident state ----

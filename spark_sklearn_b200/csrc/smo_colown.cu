@@ -99,6 +99,7 @@ smo_colown_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ 
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned rank = cluster.block_rank();
     const SmoProblem *__restrict__ Pp = probs + order[blockIdx.x / CL];
+    if (Pp->guard != nullptr && (*Pp->guard != 0) == FAST) return;       // the other instance solves this launch (common.cuh)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int l = Pp->l;
     const int lhalf = (l + 1) / 2;

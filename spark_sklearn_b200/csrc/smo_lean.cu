@@ -166,6 +166,7 @@ smo_lean_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ or
     constexpr int LCAP = NT * KPT;
 
     const SmoProblem *__restrict__ Pp = probs + order[blockIdx.x];
+    if (Pp->guard != nullptr && (*Pp->guard != 0) == FAST) return;       // the other instance solves this launch (common.cuh)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int l = Pp->l;
     const int nslots = Pp->nslots;

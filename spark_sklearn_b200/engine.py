@@ -152,6 +152,7 @@ class Engine:
         yt = None if y_target is None else np.ascontiguousarray(y_target, np.float32)
         self.n, self.d = X.shape
         self.n_splits = int(n_splits)
+        self.n_classes = 0 if yc is None else int(yc.max()) + 1
         self._check(self._L.gs_set_data(self._h, _ptr(X), 0 if X.dtype == np.float32 else 1, X.shape[0], X.shape[1], _ptr(yc), _ptr(yt),
                                         _ptr(fold_id), int(n_splits)))
 
@@ -235,11 +236,15 @@ class Engine:
         return out
 
     def logreg_refit(self, C, tol=1e-4, max_iter=100, fit_intercept=True):
-        coef = np.zeros(self.d + 1)
+        """-> (coef, intercept, n_iter): binary [d], float; three or more classes (multinomial) [n_classes][d], [n_classes]"""
+        rows = self.n_classes if self.n_classes > 2 else 1
+        coef = np.zeros((rows, self.d + 1))
         it = np.zeros(1, np.int32)
         self._check(self._L.gs_logreg_refit(self._h, float(C), float(tol), int(max_iter), int(bool(fit_intercept)),
                                             _ptr(coef), _ptr(it)))
-        return coef[:-1].copy(), float(coef[-1]), int(it[0])
+        if rows == 1:
+            return coef[0, :-1].copy(), float(coef[0, -1]), int(it[0])
+        return coef[:, :-1].copy(), coef[:, -1].copy(), int(it[0])
 
     # -- test hooks --
     def debug_gram(self):

@@ -620,8 +620,10 @@ class LogRegPlan(_Plan):
     def __init__(self, estimator, cands, X, y, fold_id, n_splits, device=None):
         super().__init__(estimator, cands, X, y, fold_id, n_splits, device)
         self.classes, self.y_class = np.unique(np.asarray(y), return_inverse=True)
-        if len(self.classes) != 2:
-            raise NotImplementedError("LogisticRegression CUDA path is binary only (got %d classes)" % len(self.classes))
+        if len(self.classes) < 2:
+            raise ValueError("LogisticRegression needs samples of at least 2 classes; got %d" % len(self.classes))
+        if len(self.classes) > 64:
+            raise NotImplementedError("LogisticRegression CUDA path handles up to 64 classes (got %d)" % len(self.classes))
         if self.X.dtype != np.float32:
             warnings.warn("spark_sklearn_b200 LogisticRegression computes in float32: float64 X is rounded to float32 "
                           "before the search", UserWarning)
@@ -673,8 +675,12 @@ class LogRegPlan(_Plan):
         self.engine.set_class_weight(None)
         est = clone(self.estimator).set_params(**best_params)
         est.classes_ = self.classes
-        est.coef_ = w.reshape(1, -1)
-        est.intercept_ = np.array([b if p["fit_intercept"] else 0.0])
+        if len(self.classes) > 2:                        # multinomial: one weight row per class (_logistic.py:1355 fit)
+            est.coef_ = np.asarray(w)
+            est.intercept_ = np.asarray(b) if p["fit_intercept"] else np.zeros(len(self.classes))
+        else:
+            est.coef_ = w.reshape(1, -1)
+            est.intercept_ = np.array([b if p["fit_intercept"] else 0.0])
         est.n_iter_ = np.array([it], np.int32)
         est.n_features_in_ = self.X.shape[1]
         return est

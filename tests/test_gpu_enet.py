@@ -119,7 +119,8 @@ def test_elasticnet_general_splitter_and_mse_scoring(engine):
     for k in range(3):
         for part in ("test", "train"):
             key = "split%d_%s_score" % (k, part)
-            np.testing.assert_allclose(a.cv_results_[key], b.cv_results_[key], rtol=3e-3, err_msg=key)
+            # the R^2 bar (5e-5) expressed in MSE units: both solvers stop on a duality gap of 1e-4 * ||y||^2
+            np.testing.assert_allclose(a.cv_results_[key], b.cv_results_[key], rtol=0, atol=5e-5 * np.var(y), err_msg=key)
     assert a.best_params_ == b.best_params_
 
 

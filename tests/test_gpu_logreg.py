@@ -79,3 +79,66 @@ def test_logreg_class_weight_vs_sklearn(engine):
     ca, cb = a.best_estimator_.coef_, b.best_estimator_.coef_
     assert np.abs(ca - cb).max() <= 2e-4 * np.abs(cb).max()
     assert np.mean(a.predict(X) != b.predict(X)) <= 1e-3
+
+
+def _multiclass_data(n=3000, d=24, k=4, seed=0):
+    from sklearn.datasets import make_classification
+    X, y = make_classification(n_samples=n, n_features=d, n_informative=12, n_classes=k, n_clusters_per_class=1,
+                               class_sep=0.8, flip_y=0.02, random_state=seed)
+    return X.astype(np.float32), y
+
+
+def test_multinomial_logreg_vs_oracle_and_sklearn(engine):
+    """Three and more classes (scikit-learn: multinomial loss, one weight row per class): the same batched L-BFGS-B with
+    n_classes weight rows per fit.  Checker: scikit-learn itself and the float32-faithful restatement.  Iteration counts
+    within one or two of scipy's (float32 rounding moves the early stop), scores within a few flips."""
+    import warnings
+    from oracle import oracle as O
+    from sklearn.linear_model import LogisticRegression
+    X, y = _multiclass_data()
+    fold_id, ns = O.folds_from_cv(4, X, y, True)
+    engine.set_data(X, fold_id, ns, y_class=y.astype(np.int32))
+    Cs = [1e-3, 0.05, 1.0, 30.0]
+    r = engine.logreg(Cs)
+    te, tr, it = O.cv_scores_logreg(X, y, fold_id, ns, [{"C": c} for c in Cs], return_n_iter=True)
+    n_te, n_tr = len(y) // ns, len(y) - len(y) // ns
+    assert np.abs(r["test"] - te).max() <= 3.0 / n_te + 1e-12, (r["test"], te)
+    assert np.abs(r["train"] - tr).max() <= 6.0 / n_tr + 1e-12, (r["train"], tr)
+    assert np.abs(r["test"].mean(1) - te.mean(1)).max() <= 1e-3
+    assert np.abs(r["n_iter"] - it).max() <= 3 and np.mean(np.abs(r["n_iter"] - it) <= 1) >= 0.75, (r["n_iter"], it)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for ci, c in enumerate(Cs[1:3], 1):
+            for k in range(ns):
+                m = LogisticRegression(C=c).fit(X[fold_id != k], y[fold_id != k])
+                assert abs(m.score(X[fold_id == k], y[fold_id == k]) - r["test"][ci, k]) <= 3.0 / n_te + 1e-12
+                assert abs(int(m.n_iter_[0]) - int(r["n_iter"][ci, k])) <= 3
+
+
+def test_multinomial_logreg_python_api_iris_and_scorers(engine):
+    from sklearn.datasets import load_iris
+    from sklearn.linear_model import LogisticRegression
+    from sklearn.model_selection import GridSearchCV as SkGrid
+    from spark_sklearn_b200 import GridSearchCV
+    import warnings
+    Xi, yi = load_iris(return_X_y=True)
+    grid = {"C": [0.1, 1.0, 10.0]}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = GridSearchCV(None, LogisticRegression(max_iter=200), grid, cv=5).fit(Xi, yi)
+        b = SkGrid(LogisticRegression(max_iter=200), grid, cv=5, return_train_score=True).fit(Xi, yi)
+    assert np.abs(a.cv_results_["mean_test_score"] - b.cv_results_["mean_test_score"]).max() <= 1.0 / 30 / 5 * 2 + 1e-12   # <= 2 flips over the 5 folds
+    ea, eb = a.best_estimator_, b.best_estimator_
+    assert ea.coef_.shape == eb.coef_.shape == (3, 4) and ea.intercept_.shape == (3,)
+    assert (a.predict(Xi) == eb.predict(Xi)).mean() >= 0.98
+    np.testing.assert_allclose(ea.predict_proba(Xi), eb.predict_proba(Xi), atol=0.05)
+    X, y = _multiclass_data(n=2000, seed=1)
+    for scoring in ("f1_macro", "balanced_accuracy", "f1_weighted"):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            a = GridSearchCV(None, LogisticRegression(class_weight="balanced"), {"C": [0.01, 1.0]}, cv=4, scoring=scoring).fit(X, y)
+            b = SkGrid(LogisticRegression(class_weight="balanced"), {"C": [0.01, 1.0]}, cv=4, scoring=scoring, return_train_score=True).fit(X, y)
+        assert np.abs(a.cv_results_["mean_test_score"] - b.cv_results_["mean_test_score"]).max() <= 4e-3, scoring
+        assert np.abs(a.cv_results_["mean_train_score"] - b.cv_results_["mean_train_score"]).max() <= 4e-3, scoring
+    with pytest.raises(NotImplementedError):
+        GridSearchCV(None, LogisticRegression(), {"C": [1.0]}, cv=3, scoring="roc_auc").fit(X, y)

@@ -134,3 +134,33 @@ def test_enet_oracle_vs_golden(key):
     np.testing.assert_allclose(test, g["test_scores"][::3], atol=2e-6)
     np.testing.assert_allclose(train, g["train_scores"][::3], atol=2e-6)
     np.testing.assert_array_equal(iters, g["diag"][::3, :, 0].astype(int))
+
+
+def test_multinomial_logreg_oracle_vs_sklearn():
+    """Three and more classes: the restatement follows scikit-learn's float32 arithmetic closely enough for the same
+    scores; L-BFGS-B stops after a few dozen iterations, where float32 rounding can move the stop by one iteration."""
+    import warnings
+    from sklearn.datasets import load_iris, make_classification
+    from sklearn.linear_model import LogisticRegression
+    same = total = 0
+    for seed in range(2):
+        X, y = make_classification(n_samples=1500, n_features=20, n_informative=10, n_classes=4, n_clusters_per_class=1, random_state=seed)
+        X = X.astype(np.float32)
+        tr, te = np.arange(1000), np.arange(1000, 1500)
+        for C in (0.01, 1.0, 100.0):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                m = LogisticRegression(C=C).fit(X[tr], y[tr])
+            t, r, it = O.logreg_fit_score(X, y, tr, te, C)
+            assert abs(it - m.n_iter_[0]) <= 1
+            same += it == m.n_iter_[0]; total += 1
+            assert abs(m.score(X[te], y[te]) - t) <= 2.1 / len(te) and abs(m.score(X[tr], y[tr]) - r) <= 2.1 / len(tr)
+    assert same >= total - 2
+    Xi, yi = load_iris(return_X_y=True)                     # float64: identical iterates
+    idx = np.random.RandomState(0).permutation(150)
+    tr, te = idx[:100], idx[100:]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = LogisticRegression(C=0.1).fit(Xi[tr], yi[tr])
+    t, r, it = O.logreg_fit_score(Xi, yi, tr, te, 0.1)
+    assert it == m.n_iter_[0] and t == m.score(Xi[te], yi[te]) and r == m.score(Xi[tr], yi[tr])

@@ -19,7 +19,7 @@ def main(key, reps=2):
     X, y = w["X"], w["y"]
     cands = W.candidates(w)
     eng = get_engine(0)
-    cv = check_cv(w["cv"], y, classifier=w["estimator"] != "Ridge")
+    cv = check_cv(w["cv"], y, classifier=w["estimator"] in ("SVC", "LogisticRegression"))
     splits = list(cv.split(X, y))
     fold_id = fold_ids_from_splits(splits, len(y))
     out = None
@@ -36,6 +36,10 @@ def main(key, reps=2):
             eng.set_data(X, fold_id, len(splits), y_target=y)
             t1 = time.time()
             out = eng.ridge([float(c["alpha"]) for c in cands])
+        elif w["estimator"] in ("Lasso", "ElasticNet"):
+            eng.set_data(X, fold_id, len(splits), y_target=y)
+            t1 = time.time()
+            out = eng.enet([float(c["alpha"]) for c in cands], [float(c.get("l1_ratio", 1.0)) for c in cands])
         else:
             eng.set_data(X, fold_id, len(splits), y_class=y.astype(np.int32))
             t1 = time.time()
