@@ -72,6 +72,14 @@ int gs_set_splits(gs_handle *h, const uint64_t *test_mask, const uint64_t *train
  * weights for every split); w == NULL resets to all ones. */
 int gs_set_class_weight(gs_handle *h, const double *w, int32_t n_sets);
 
+/* Sample weights of the following gs_ridge / gs_enet / gs_logreg calls and their refits.  Replaces: fit_params={'sample_weight': w}
+ * handed to every task's estimator.fit (reference base_search.py:69,83-87; scikit-learn's _fit_and_score slices it by the
+ * training rows and weights the FIT only -- the scores stay unweighted).  w: [n] in the caller's row order, >= 0; NULL resets.
+ * gs_ridge / gs_enet contract a second, sqrt(w)-scaled copy of the row blocks for the weighted training statistics;
+ * gs_logreg multiplies the pointwise loss and gradient.  gs_svc rejects them (its kernels take a C per class, not per row).
+ * gs_set_data resets the weights. */
+int gs_set_sample_weight(gs_handle *h, const double *w);
+
 /* Scorer of the following gs_svc / gs_logreg / gs_ridge calls.  Replaces: check_scoring(estimator, scoring) and the scorer
  * call inside _fit_and_score (reference base_search.py:43,83-87; grid_search.py:212-214 `scoring=`).  The score is
  * computed on the device from the decision values / Gram statistics already in HBM.  pos_class: class id (index into the
@@ -84,7 +92,7 @@ enum {
     GS_SCORE_F1_MACRO = 6, GS_SCORE_F1_MICRO = 7, GS_SCORE_F1_WEIGHTED = 8,
     GS_SCORE_NEG_MSE = 16, GS_SCORE_NEG_RMSE = 17                          /* Ridge                         */
 };
-int gs_set_scoring(gs_handle *h, int32_t kind, int32_t pos_class);   /* gs_set_data resets scoring and class weights to their defaults */
+int gs_set_scoring(gs_handle *h, int32_t kind, int32_t pos_class);   /* gs_set_data resets scoring, class and sample weights to their defaults */
 
 /* Number of sm_100 GPUs this process can drive (0: none).  Replaces: the executor count Spark reports to the driver
  * (reference base_search.py:62 sc.parallelize(..., len(tasks)) leaves placement to Spark); the in-process scheduler of

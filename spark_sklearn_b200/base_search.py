@@ -57,8 +57,6 @@ class B200BaseSearchCV(BaseSearchCV):
         if hasattr(cv, 'random_state'):                       # reference base_search.py:39-41
             if not cv.random_state:
                 cv.random_state = randint(1000, 9999)
-        if self.fit_params:
-            raise NotImplementedError("fit_params are not supported by the CUDA path (no CPU fallback)")
         self.scorer_ = check_scoring(self.estimator, scoring=self.scoring)
         self.multimetric_ = False
 
@@ -99,6 +97,8 @@ class B200BaseSearchCV(BaseSearchCV):
                 for p in plans:
                     if self.scoring is not None or hasattr(p, "set_scoring"):
                         p.set_scoring(self.scoring)           # raises for scorers without a fused CUDA path
+                    if self.fit_params or hasattr(p, "set_fit_params"):
+                        p.set_fit_params(self.fit_params)     # sample_weight; raises for anything without a CUDA path
                 parts = _dist.assign_for_plan(plans[0], n_param_candidates, len(devices))
                 locs = list(pool.map(lambda i: plans[i].evaluate(parts[i], return_train=self.return_train_score,
                                                                  error_score=self.error_score) if parts[i] else None,
@@ -113,6 +113,8 @@ class B200BaseSearchCV(BaseSearchCV):
             plan = adapter.plan(clone(estimator), candidate_params, X_arr, y_arr, fold_id, n_splits)
             if self.scoring is not None or hasattr(plan, "set_scoring"):
                 plan.set_scoring(self.scoring)                # raises for scorers without a fused CUDA path
+            if self.fit_params or hasattr(plan, "set_fit_params"):
+                plan.set_fit_params(self.fit_params)          # sample_weight; raises for anything without a CUDA path
             # candidates dealt to the GPUs by predicted cost (the reference leaves the placement of its tasks to Spark)
             parts = _dist.assign_for_plan(plan, n_param_candidates, world)
             my = parts[rank]

@@ -115,6 +115,25 @@ int gs_set_class_weight(gs_handle *h, const double *w, int32_t n_sets)
     return GS_OK;
 }
 
+int gs_set_sample_weight(gs_handle *h, const double *w)
+{
+    if (!h) return GS_ERR_ARG;
+    if (!w) { h->sample_w.clear(); return GS_OK; }
+    if (h->n == 0) { gs_set_error(h, "gs_set_sample_weight: no dataset (call gs_set_data first)"); return GS_ERR_NO_DATA; }
+    std::vector<float> sw((size_t)h->n);
+    for (int64_t i = 0; i < h->n; i++) {
+        const double v = w[h->perm[i]];
+        if (!(v >= 0) || !std::isfinite(v)) { gs_set_error(h, "gs_set_sample_weight: weights must be finite and >= 0"); return GS_ERR_ARG; }
+        sw[i] = (float)v;                                     // scikit-learn: _check_sample_weight(..., dtype=X.dtype)
+    }
+    GS_CUDA(cudaSetDevice(h->device));
+    GS_CUDA(h->dSw.reserve((size_t)h->n * 4));
+    GS_CUDA(cudaMemcpyAsync(h->dSw.p, sw.data(), (size_t)h->n * 4, cudaMemcpyHostToDevice, h->stream));
+    GS_CUDA(cudaStreamSynchronize(h->stream));
+    h->sample_w.swap(sw);
+    return GS_OK;
+}
+
 int gs_set_scoring(gs_handle *h, int32_t kind, int32_t pos_class)
 {
     if (!h) return GS_ERR_ARG;
@@ -182,7 +201,7 @@ void gs_destroy(gs_handle *h)
     cudaSetDevice(h->device);
     h->dX.release(); h->dY.release(); h->dFold.release(); h->dYt.release(); h->dTe.release(); h->dTr.release();
     h->dS.release(); h->dXsq.release(); h->dK.release(); h->dX64.release();
-    h->evp.release(); h->dScore.release();
+    h->evp.release(); h->dScore.release(); h->dSw.release();
     for (auto &w : h->dWork) w.release();
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream_hi) cudaStreamDestroy(h->stream_hi);
@@ -205,6 +224,7 @@ int gs_set_data(gs_handle *h, const void *X, int32_t x_dtype, int64_t n, int64_t
     h->classification = y_class != nullptr;
     h->score_kind = GS_SCORE_DEFAULT; h->score_pos = 1;      // a new dataset starts from the estimator's own score and unit class weights
     h->class_w.clear(); h->class_w_sets = 0;
+    h->sample_w.clear();
     h->perm.resize(n);
     std::iota(h->perm.begin(), h->perm.end(), 0);
     h->n_classes = 0;
@@ -382,6 +402,10 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
     if (!h->classification) { gs_set_error(h, "gs_svc: dataset has no class labels"); return GS_ERR_ARG; }
     if (h->n_classes < 2 || h->n_classes > 32) { gs_set_error(h, "gs_svc: need 2..32 classes"); return GS_ERR_UNSUPPORTED; }
     if (n_cand <= 0 || !kernel || !Cv || !gamma) { gs_set_error(h, "gs_svc: bad arguments"); return GS_ERR_ARG; }
+    if (!h->sample_w.empty()) {
+        gs_set_error(h, "gs_svc: sample weights (a C per row) are not supported by the SMO kernels; class weights are (gs_set_class_weight)");
+        return GS_ERR_UNSUPPORTED;
+    }
     if (h->class_w_sets > 1 && h->class_w_sets != (refit ? 1 : h->n_splits)) {
         gs_set_error(h, "gs_svc: gs_set_class_weight was given a weight set per split, but not for this number of splits"); return GS_ERR_ARG;
     }

@@ -116,6 +116,8 @@ struct gs_handle {
     int score_kind = 0, score_pos = 1;   // gs_set_scoring
     std::vector<double> class_w;         // gs_set_class_weight: [sets][n_classes]; empty = all ones
     int class_w_sets = 0;
+    std::vector<float> sample_w;         // gs_set_sample_weight: [n] internal order; empty = all ones
+    DevBuf dSw;                          // its device copy
     gs_profile prof;
     EventPool evp;                    // timing events of the current call
     TensorTimer tt;

@@ -45,11 +45,14 @@ __global__ void column_means_kernel(const float *__restrict__ X, const float *__
     }
 }
 
+// (sample weights: the chunk list is doubled; chunks >= first_weighted build sqrt(w)-scaled rows, whose Grams are the weighted
+// training statistics sum w z z^T, while the unweighted copy keeps serving the scores -- _fit_and_score weights the fit only)
 // Zt[j][poff[b] + r] = X[row][j] - shift[j] (j<d) | y[row] - shift[d] (j==d) | 1 (j==d+1); rows of block b are row0[b] .. row0[b]+cnt[b],
 // or rowidx[row0[b] .. row0[b]+cnt[b]) when the blocks are row lists (general splits: the training / test rows of a split)
 __global__ void build_zt_kernel(const float *__restrict__ X, const float *__restrict__ y, const float *__restrict__ shift, int d, int n_blocks,
                                 const int *__restrict__ row0, const int *__restrict__ cnt, const int *__restrict__ poff,
-                                const int *__restrict__ rowidx, float *__restrict__ Zt, int64_t ldz)
+                                const int *__restrict__ rowidx, const float *__restrict__ sw, int first_weighted,
+                                float *__restrict__ Zt, int64_t ldz)
 {
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
@@ -64,6 +67,7 @@ __global__ void build_zt_kernel(const float *__restrict__ X, const float *__rest
             if (j < d) v = X[(size_t)row * d + j] - shift[j];
             else if (j == d) v = y[row] - shift[d];
             else if (j == d + 1) v = 1.f;
+            if (sw && b >= first_weighted) v *= sqrtf(sw[row]);      // chunks of the weighted copy: rows scaled by sqrt(sample_weight)
         }
         tile[threadIdx.y][threadIdx.x] = v;
     }
@@ -76,18 +80,19 @@ __global__ void build_zt_kernel(const float *__restrict__ X, const float *__rest
 
 // The Gram of a row block is contracted in chunks of <= TC_KCHUNK rows (the TMEM accumulator truncates); the chunk
 // partials Gq are added here in float64: G_b = sum of the chunks of block b (chunks qs[b] .. qs[b+1]), T = sum_b G_b.
-__global__ void sum_grams_kernel(const float *__restrict__ Gq, const int *__restrict__ qs, int n_blocks, int64_t per,
-                                 float *__restrict__ G, double *__restrict__ T)
+__global__ void sum_grams_kernel(const float *__restrict__ Gq, const int *__restrict__ qs, int n_blocks, int n_plain, int64_t per,
+                                 float *__restrict__ G, double *__restrict__ T, double *__restrict__ Tw)
 {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x) {
-        double tot = 0;
+        double tot = 0, totw = 0;                                   // blocks [0, n_plain): unweighted; [n_plain, n_blocks): weighted copy
         for (int b = 0; b < n_blocks; b++) {
             double s = 0;
             for (int q = qs[b]; q < qs[b + 1]; q++) s += (double)Gq[(size_t)q * per + i];
             G[(size_t)b * per + i] = (float)s;
-            tot += s;
+            if (b < n_plain) tot += s; else totw += s;
         }
         T[i] = tot;
+        if (Tw) Tw[i] = totw;
     }
 }
 
@@ -95,14 +100,14 @@ __global__ void sum_grams_kernel(const float *__restrict__ Gq, const int *__rest
 // partition the rows) or S = G_train (general splits: the split's own training block), centred normal matrix
 // A (float32, [dp][dp], zero padded) and rhs (float32 [dp]); means kept in float64 for the intercept.
 __global__ void build_systems_kernel(const double *__restrict__ T, const float *__restrict__ G, const int *__restrict__ test_block,
-                                     const int *__restrict__ train_block,
+                                     const int *__restrict__ train_block, int wofs /* block offset of the weighted copy */,
                                      int d, int Dp, int dp, int fit_intercept, float *__restrict__ A, float *__restrict__ rhs,
                                      double *__restrict__ means /* [groups][dp + 3]: xbar[0..d), ybar, n_train, centred y^T y */)
 {
     const int g = blockIdx.z;
     const int tb = test_block[g], trb = train_block[g];
-    const float *Gt = tb >= 0 ? G + (size_t)tb * Dp * Dp : nullptr;
-    const float *Gtr = trb >= 0 ? G + (size_t)trb * Dp * Dp : nullptr;
+    const float *Gt = tb >= 0 ? G + (size_t)(tb + wofs) * Dp * Dp : nullptr;
+    const float *Gtr = trb >= 0 ? G + (size_t)(trb + wofs) * Dp * Dp : nullptr;
     auto S = [&](int a, int b) -> double {
         if (Gtr) return (double)Gtr[(size_t)a * Dp + b];
         return T[(size_t)a * Dp + b] - (Gt ? (double)Gt[(size_t)a * Dp + b] : 0.0);
@@ -571,6 +576,12 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
         }
         if (r < n) { row0.push_back(r); cnt.push_back(n - r); }
     }
+    // sample weights (gs_set_sample_weight): every block once more, its rows scaled by sqrt(w) -- the second copy gives the
+    // weighted training statistics, the first one the (unweighted) scores
+    const bool weighted = !h->sample_w.empty();
+    const int nb_plain = (int)row0.size();
+    if (weighted)
+        for (int b = 0; b < nb_plain; b++) { row0.push_back(row0[b]); cnt.push_back(cnt[b]); }
     const int nb = (int)row0.size();
     // contraction chunks: <= TC_KCHUNK rows each, zero-padded to a multiple of 32 columns of Z^T
     std::vector<int> crow0, ccnt, qs(nb + 1, 0);
@@ -579,6 +590,7 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
         qs[b + 1] = (int)crow0.size();
     }
     const int nq = (int)crow0.size();
+    const int first_weighted = weighted ? qs[nb_plain] : nq;
     std::vector<int> poff(nq + 1, 0);
     for (int q = 0; q < nq; q++) poff[q + 1] = poff[q] + ((ccnt[q] + 31) & ~31);
     const int64_t ldz = poff[nq];
@@ -595,14 +607,14 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
            &bA = h->dWork[5], &bV = h->dWork[6], &bMeta = h->dWork[7];
     GS_CUDA(bZ.reserve((size_t)Dp * ldz * 4)); GS_CUDA(bZh.reserve((size_t)Dp * ldz * 4)); GS_CUDA(bZl.reserve((size_t)Dp * ldz * 4));
     GS_CUDA(bG.reserve((size_t)(nb + nq) * Dp * Dp * 4));                   // per-block Grams, then the chunk partials
-    const size_t tBytes = (size_t)Dp * Dp * 8, meansBytes = (size_t)groups * (dp + 3) * 8;
+    const size_t tBytes = (size_t)Dp * Dp * 8 * 2, meansBytes = (size_t)groups * (dp + 3) * 8;
     GS_CUDA(bMisc.reserve(tBytes + meansBytes + (size_t)nsys * (8 + 8 + 16) + (size_t)n_cand * 8 + (size_t)(d + 1) * 4 + 256));
     GS_CUDA(bA.reserve((size_t)groups * dp * dp * 4 * 3 + (size_t)groups * dp * 4));
     GS_CUDA(bV.reserve((size_t)nsys * dp * 4 * (6 + (size_t)((dp + TC_KCHUNK - 1) / TC_KCHUNK))));
     const int nkc = (dp + TC_KCHUNK - 1) / TC_KCHUNK;                          // K-chunks of the CG product
     GS_CUDA(bMeta.reserve((size_t)(nq * 3 + nb + 1 + 2 * groups) * 4 + (size_t)(nq + groups * nkc) * sizeof(TcBatch) + (size_t)nsys * 4 + rowidx.size() * 4 + 128));
-    double *dT = bMisc.as<double>();
-    double *dMeans = dT + (size_t)Dp * Dp;
+    double *dT = bMisc.as<double>(), *dTw = dT + (size_t)Dp * Dp;          // totals of the unweighted / weighted block Grams
+    double *dMeans = dTw + (size_t)Dp * Dp;
     double *dRR = dMeans + (size_t)groups * (dp + 3), *dBB = dRR + nsys, *dOut = dBB + nsys, *dAlpha = dOut + 2 * (size_t)nsys;
     float *dShift = reinterpret_cast<float *>(dAlpha + n_cand);               // [d + 1] column shifts of [X | y]
     float *dA = bA.as<float>(), *dAh = dA + (size_t)groups * dp * dp, *dAl = dAh + (size_t)groups * dp * dp,
@@ -648,7 +660,8 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
         if (fit_intercept) column_means_kernel<<<(d + 1 + 31) / 32, dim3(32, 32), 0, st>>>(h->dX.as<float>(), h->dYt.as<float>(), n, d, dShift);
         else GS_CUDA(cudaMemsetAsync(dShift, 0, (size_t)(d + 1) * 4, st));
         GS_CUDA(cudaGetLastError());
-        build_zt_kernel<<<grid, block, 0, st>>>(h->dX.as<float>(), h->dYt.as<float>(), dShift, d, nq, dRow0, dCnt, dPoff, dRowIdx, bZ.as<float>(), ldz);
+        build_zt_kernel<<<grid, block, 0, st>>>(h->dX.as<float>(), h->dYt.as<float>(), dShift, d, nq, dRow0, dCnt, dPoff, dRowIdx,
+                                                weighted ? h->dSw.as<float>() : nullptr, first_weighted, bZ.as<float>(), ldz);
         GS_CUDA(cudaGetLastError());
     }
     GS_CUDA(launch_split_tf32(bZ.as<float>(), bZh.as<float>(), bZl.as<float>(), (size_t)Dp * ldz, st));
@@ -658,7 +671,7 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     h->tt.begin(h->evp, st);
     GS_CUDA(launch_gemm_nt_tf32x3(mzh, mzl, mzh, mzl, dBatchG, nq, D, D, 1.0f, false, st, true));   // Gram: upper tiles + mirror
     h->tt.end(h->evp, st, 3.0 * 2.0 * (double)D * D * (double)ldz * (((D + 127) / 128 + 1) / (2.0 * ((D + 127) / 128))));   // tiles on/above the diagonal
-    sum_grams_kernel<<<592, 256, 0, st>>>(dGq, dQs, nb, (int64_t)Dp * Dp, bG.as<float>(), dT);
+    sum_grams_kernel<<<592, 256, 0, st>>>(dGq, dQs, nb, nb_plain, (int64_t)Dp * Dp, bG.as<float>(), dT, weighted ? dTw : nullptr);
     GS_CUDA(cudaGetLastError());
     launches += 5;
     cudaEventRecord(ev[1], st);
@@ -666,7 +679,8 @@ int ridge_run(gs_handle *h, int n_cand, const double *alpha, int fit_intercept, 
     // ---- 2. per-group centred systems ----
     {
         dim3 block(32, 8), grid((dp + 31) / 32, (dp + 7) / 8, groups);
-        build_systems_kernel<<<grid, block, 0, st>>>(dT, bG.as<float>(), dTestBlock, dTrainBlock, d, Dp, dp, fit_intercept, dA, dRhs, dMeans);
+        build_systems_kernel<<<grid, block, 0, st>>>(weighted ? dTw : dT, bG.as<float>(), dTestBlock, dTrainBlock, weighted ? nb_plain : 0, d, Dp, dp,
+                                                     fit_intercept, dA, dRhs, dMeans);
         GS_CUDA(cudaGetLastError());
     }
     int it = 0;

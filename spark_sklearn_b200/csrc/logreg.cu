@@ -333,6 +333,7 @@ __global__ void lbfgs_export_kernel(const double *__restrict__ Vall, int ncol, i
 __global__ void logistic_residual_kernel(const float *__restrict__ Zt, int64_t ldz, int n, const int *__restrict__ y,
                                          SplitMasks sm, const int *__restrict__ fold_of_col,
                                          const double *__restrict__ inv_ntrain, const float *__restrict__ cw /* [ncol][2] class weights or null */,
+                                         const float *__restrict__ sw /* [n] sample weights or null */,
                                          LbScalars *__restrict__ Sc, float *__restrict__ Rh, float *__restrict__ Rl)
 {
     const int c = blockIdx.y;
@@ -349,8 +350,8 @@ __global__ void logistic_residual_kernel(const float *__restrict__ Zt, int64_t l
             // half binomial loss log(1+e^z) - y z, evaluated the numerically stable way
             const float lz = z > 0.f ? z + log1pf(expf(-z)) : log1pf(expf(z));
             const float p = 1.f / (1.f + expf(-z));
-            if (cw) {                                    // sample_weight = class_weight_[y] multiplies the pointwise loss and gradient
-                const float wi = cw[c * 2 + y[i]];       // (_logistic.py: sample_weight *= class_weight_[y]; _loss: loss_out *= sample_weight)
+            if (cw || sw) {                              // sample_weight (x class_weight_[y]) multiplies the pointwise loss and gradient
+                const float wi = (sw ? sw[i] : 1.f) * (cw ? cw[c * 2 + y[i]] : 1.f);   // (_logistic.py: sample_weight *= class_weight_[y]; _loss: loss_out *= sample_weight)
                 acc += (double)(wi * (lz - yi * z));
                 rres = (wi * (p - yi)) * invn;
             } else {
@@ -431,6 +432,7 @@ __global__ void logistic_classes_kernel(const float *__restrict__ Zt, int64_t ld
 __global__ void multinomial_residual_kernel(const float *__restrict__ Zt, int64_t ldz, int n, int K, const int *__restrict__ y,
                                             SplitMasks sm, const int *__restrict__ fold_of_col,
                                             const double *__restrict__ inv_ntrain, const float *__restrict__ cw /* [nfit][K] or null */,
+                                            const float *__restrict__ sw /* [n] sample weights or null */,
                                             LbScalars *__restrict__ Sc, float *__restrict__ Rh, float *__restrict__ Rl)
 {
     const int f = blockIdx.y;
@@ -446,7 +448,7 @@ __global__ void multinomial_residual_kernel(const float *__restrict__ Zt, int64_
             float se = 0.f;
             for (int k = 0; k < K; k++) se += expf(Zt[base + (size_t)k * ldz] - mx);
             const int yi = y[i];
-            const float wi = cw ? cw[(size_t)f * K + yi] : 1.f;
+            const float wi = (sw ? sw[i] : 1.f) * (cw ? cw[(size_t)f * K + yi] : 1.f);
             acc += (double)(wi * (logf(se) + mx - Zt[base + (size_t)yi * ldz]));
             const float inv_se = 1.f / se;
             for (int k = 0; k < K; k++) {
@@ -590,10 +592,16 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
     TcBatch *dBatch = reinterpret_cast<TcBatch *>(((uintptr_t)mp + 15) & ~(uintptr_t)15);
 
     // per-column constants
-    std::vector<int> ntrain(std::max(ns, 1), 0), ntrain_c((size_t)std::max(ns, 1) * nc, 0);   // training rows of every split, and per class
+    // sum of the sample weights (1 without gs_set_sample_weight) of the training rows of every split, and per class
+    const bool has_sw = !h->sample_w.empty();
+    std::vector<double> ntrain(std::max(ns, 1), 0.0), ntrain_c((size_t)std::max(ns, 1) * nc, 0.0);
     for (int k = 0; k < ns; k++)
         for (int i = 0; i < n; i++)
-            if (refit || h->is_train(i, k)) { ntrain[k]++; ntrain_c[(size_t)k * nc + h->yc[i]]++; }
+            if (refit || h->is_train(i, k)) {
+                const double wi = has_sw ? (double)h->sample_w[i] : 1.0;
+                ntrain[k] += wi; ntrain_c[(size_t)k * nc + h->yc[i]] += wi;
+            }
+    const float *dSw = has_sw ? h->dSw.as<float>() : nullptr;
     const bool weighted = h->class_w_sets > 0;
     if (weighted && h->class_w_sets != 1 && h->class_w_sets != ns) {
         gs_set_error(h, "gs_logreg: gs_set_class_weight was given a weight set per split, but not for this number of splits"); return GS_ERR_ARG;
@@ -662,8 +670,8 @@ int logreg_run(gs_handle *h, int n_cand, const double *Cv, double tol, int max_i
         GS_CUDA(launch_gemm_nt_tf32x3(mWh, mWl, mXh, mXl, dBatch, 1, ncol, n, 1.0f, false, st));
         h->tt.end(h->evp, st, 3.0 * 2.0 * (double)ncol * n * nvp);
         dim3 grid(64, nfit);
-        if (multi) multinomial_residual_kernel<<<grid, 256, 0, st>>>(dZ, npad, n, KC, h->dY.as<int>(), h->masks(), dFoldOf, dInv, dCw, dS, dRh, dRl);
-        else logistic_residual_kernel<<<grid, 256, 0, st>>>(dZ, npad, n, h->dY.as<int>(), h->masks(), dFoldOf, dInv, dCw, dS, dRh, dRl);
+        if (multi) multinomial_residual_kernel<<<grid, 256, 0, st>>>(dZ, npad, n, KC, h->dY.as<int>(), h->masks(), dFoldOf, dInv, dCw, dSw, dS, dRh, dRl);
+        else logistic_residual_kernel<<<grid, 256, 0, st>>>(dZ, npad, n, h->dY.as<int>(), h->masks(), dFoldOf, dInv, dCw, dSw, dS, dRh, dRl);
         GS_CUDA(cudaGetLastError());
         h->tt.begin(h->evp, st);
         GS_CUDA(launch_gemm_nt_tf32x3(mRh, mRl, mXth, mXtl, dBatch + 1, nchunk, ncol, nv, 1.0f, false, st));

@@ -50,6 +50,8 @@ def load_library():
     L.gs_set_splits.restype = c.c_int
     L.gs_set_class_weight.argtypes = [vp, vp, i32]
     L.gs_set_class_weight.restype = c.c_int
+    L.gs_set_sample_weight.argtypes = [vp, vp]
+    L.gs_set_sample_weight.restype = c.c_int
     L.gs_set_scoring.argtypes = [vp, i32, i32]
     L.gs_set_scoring.restype = c.c_int
     L.gs_create.argtypes = [c.c_int, c.POINTER(vp)]
@@ -139,6 +141,16 @@ class Engine:
             return
         w = np.ascontiguousarray(np.atleast_2d(w), np.float64)
         self._check(self._L.gs_set_class_weight(self._h, _ptr(w), w.shape[0]))
+
+    def set_sample_weight(self, w=None):
+        """fit_params={'sample_weight': w} of the following ridge / enet / logreg calls (None: unweighted)"""
+        if w is None:
+            self._check(self._L.gs_set_sample_weight(self._h, None))
+            return
+        w = np.ascontiguousarray(w, np.float64)
+        if w.shape != (self.n,):
+            raise ValueError("sample_weight has shape %r; expected (%d,)" % (w.shape, self.n))
+        self._check(self._L.gs_set_sample_weight(self._h, _ptr(w)))
 
     def set_scoring(self, kind=0, pos_class=1):
         """Scorer of the following search calls (include/b200gs.h GS_SCORE_*): reference base_search.py:43 check_scoring."""

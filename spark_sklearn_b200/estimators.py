@@ -163,13 +163,31 @@ class _Plan:
             self.engine.set_data(X, self.fold_id, self.n_splits, **kw)
 
     general_splits = True
+    supports_sample_weight = False
+
+    def set_fit_params(self, fit_params):
+        """reference base_search.py:69,83-87: fit_params go to every task's estimator.fit.  The CUDA paths take
+        sample_weight (Ridge, Lasso, ElasticNet, LogisticRegression); anything else has no device counterpart."""
+        fit_params = dict(fit_params or {})
+        sw = fit_params.pop("sample_weight", None)
+        if fit_params:
+            raise NotImplementedError("fit_params %s have no CUDA path (sample_weight does)" % sorted(fit_params))
+        if sw is not None and not self.supports_sample_weight:
+            raise NotImplementedError("sample_weight has no CUDA path for %s (class_weight does)" % type(self.estimator).__name__)
+        self.sample_weight = None if sw is None else np.asarray(sw, np.float64)
+        if self.sample_weight is not None and self.sample_weight.shape != (len(self.X),):
+            raise ValueError("sample_weight has shape %r; expected (%d,)" % (self.sample_weight.shape, len(self.X)))
+        self.engine.set_sample_weight(self.sample_weight)
+
     def _class_weights(self, cw, k):
         """scikit-learn's class_weight_ of one fit (svm/_base.py, linear_model/_logistic.py: compute_class_weight(class_weight, classes, y_train)):
         None -> ones; dict -> by label (missing labels 1.0); 'balanced' -> n / (n_classes * bincount) on the TRAINING rows of
         split k (k < 0: all rows)."""
         from sklearn.utils.class_weight import compute_class_weight
         rows = self._train_rows(k)
-        return compute_class_weight(cw, classes=self.classes, y=np.asarray(self.y)[rows])
+        sw = getattr(self, "sample_weight", None)        # 'balanced' counts the classes by weight (_logistic.py:431-433)
+        return compute_class_weight(cw, classes=self.classes, y=np.asarray(self.y)[rows],
+                                    sample_weight=None if sw is None else sw[rows])
 
     def _set_class_weight(self, cw, refit=False):
         if cw is None:
@@ -429,6 +447,7 @@ class RidgeAdapter:
 
 class RidgePlan(_Plan):
     scorers = REGRESSION_SCORERS
+    supports_sample_weight = True
     general_splits = True          # partitions: T - G_fold; other splitters: one Gram per training / test row list
 
     def __init__(self, estimator, cands, X, y, fold_id, n_splits, device=None):
@@ -596,6 +615,9 @@ class _PipelinePlan:
     def __getattr__(self, name):                      # evaluate, set_scoring, costs, profile, engine, close ...
         return getattr(self._inner, name)
 
+    def set_fit_params(self, fit_params):
+        self._inner.set_fit_params(self._adapter._strip(fit_params or {}))
+
     def refit(self, best_params):
         from sklearn.pipeline import Pipeline
         fitted = self._inner.refit(self._adapter._strip(best_params))
@@ -616,6 +638,7 @@ class LogRegAdapter:
 
 class LogRegPlan(_Plan):
     scorers = CLASSIFICATION_SCORERS
+    supports_sample_weight = True
 
     def __init__(self, estimator, cands, X, y, fold_id, n_splits, device=None):
         super().__init__(estimator, cands, X, y, fold_id, n_splits, device)

@@ -138,3 +138,34 @@ def test_lasso_1024_features_vs_golden(engine):
     assert np.abs(r["test"].mean(1) - g["test_scores"].mean(1)).max() <= 2e-5
     n_iter = g["diag"][:, :, 0].astype(int)
     assert np.abs(r["n_iter"] - n_iter).max() <= 2
+
+
+def test_sample_weight_fit_params_linear_models(engine):
+    """fit_params={'sample_weight': w} (reference base_search.py:69,83-87): the fit is weighted, the scores are not.
+    Checker: scikit-learn's GridSearchCV.fit(X, y, sample_weight=w)."""
+    from sklearn.linear_model import ElasticNet, Lasso, Ridge
+    from sklearn.model_selection import GridSearchCV as SkGrid, ShuffleSplit
+    from spark_sklearn_b200 import GridSearchCV
+    w = W.make_workload("lasso_small")
+    X, y = w["X"], w["y"]
+    rng = np.random.RandomState(5)
+    sw = rng.gamma(1.0, 1.0, len(y))
+    sw[rng.rand(len(y)) < 0.1] = 0.0                                  # some rows switched off
+    for est, grid, cv in ((Ridge(), {"alpha": [1e-2, 10.0, 1e3]}, 4),
+                          (Lasso(), {"alpha": [0.05, 2.0, 40.0]}, 4),
+                          (ElasticNet(), {"alpha": [0.1, 3.0], "l1_ratio": [0.3, 0.8]}, ShuffleSplit(3, test_size=0.25, random_state=1))):
+        a = GridSearchCV(None, est, grid, cv=cv, iid=False, fit_params={"sample_weight": sw}).fit(X, y)
+        b = SkGrid(est, grid, cv=cv, return_train_score=True).fit(X, y, sample_weight=sw)
+        u = SkGrid(est, grid, cv=cv, return_train_score=True).fit(X, y)
+        for key in ("mean_test_score", "mean_train_score"):
+            np.testing.assert_allclose(a.cv_results_[key], b.cv_results_[key], atol=5e-5, err_msg="%s %s" % (type(est).__name__, key))
+        assert np.abs(b.cv_results_["mean_train_score"] - u.cv_results_["mean_train_score"]).max() > 1e-4      # the weights matter
+        assert a.best_params_ == b.best_params_
+        np.testing.assert_allclose(a.best_estimator_.coef_, b.best_estimator_.coef_, atol=3e-4 * np.abs(b.best_estimator_.coef_).max())
+        np.testing.assert_allclose(a.best_estimator_.intercept_, b.best_estimator_.intercept_, atol=2e-3)
+    from sklearn.svm import SVC
+    wc = W.make_workload("c2_small")
+    with pytest.raises(NotImplementedError):
+        GridSearchCV(None, SVC(), {"C": [1.0]}, cv=3, fit_params={"sample_weight": np.ones(len(wc["y"]))}).fit(wc["X"], wc["y"])
+    with pytest.raises(NotImplementedError):
+        GridSearchCV(None, Ridge(), {"alpha": [1.0]}, cv=3, fit_params={"check_input": False}).fit(X, y)

@@ -142,3 +142,27 @@ def test_multinomial_logreg_python_api_iris_and_scorers(engine):
         assert np.abs(a.cv_results_["mean_train_score"] - b.cv_results_["mean_train_score"]).max() <= 4e-3, scoring
     with pytest.raises(NotImplementedError):
         GridSearchCV(None, LogisticRegression(), {"C": [1.0]}, cv=3, scoring="roc_auc").fit(X, y)
+
+
+def test_logreg_sample_weight_fit_params(engine):
+    """fit_params={'sample_weight': w}: weighted loss and gradient, weight-sum scaling of the penalty, unweighted scores;
+    with class_weight='balanced' the class frequencies are counted by weight.  Binary and multinomial."""
+    import warnings
+    from sklearn.linear_model import LogisticRegression
+    from sklearn.model_selection import GridSearchCV as SkGrid
+    from spark_sklearn_b200 import GridSearchCV
+    w3 = W.make_workload("c3_small")
+    Xm, ym = _multiclass_data(n=2400, seed=2)
+    for X, y, est in ((w3["X"], w3["y"], LogisticRegression()), (Xm, ym, LogisticRegression()),
+                      (w3["X"], w3["y"], LogisticRegression(class_weight="balanced"))):
+        rng = np.random.RandomState(7)
+        sw = rng.gamma(1.0, 1.0, len(y)) + 0.05
+        grid = {"C": [1e-2, 1.0]}
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            a = GridSearchCV(None, est, grid, cv=4, iid=False, fit_params={"sample_weight": sw}).fit(X, y)
+            b = SkGrid(est, grid, cv=4, return_train_score=True).fit(X, y, sample_weight=sw)
+        n_te = len(y) // 4
+        assert np.abs(a.cv_results_["mean_test_score"] - b.cv_results_["mean_test_score"]).max() <= 2.0 / n_te
+        assert np.abs(a.cv_results_["mean_train_score"] - b.cv_results_["mean_train_score"]).max() <= 2.0 / n_te
+        np.testing.assert_allclose(a.best_estimator_.coef_, b.best_estimator_.coef_, atol=0.02 * np.abs(b.best_estimator_.coef_).max() + 1e-3)
