@@ -140,11 +140,28 @@ def test_lasso_1024_features_vs_golden(engine):
     assert np.abs(r["n_iter"] - n_iter).max() <= 2
 
 
+def _reference_tasks(est, grid, cv, X, y, sw, classifier=False):
+    """The reference's own task (base_search.py:74-88 with scikit-learn <0.20's _fit_and_score): fit_params are sliced by the
+    training rows and given to fit(); the scorer gets no weights.  (scikit-learn >= 1.4's GridSearchCV.fit(sample_weight=)
+    also weights the scorer, so it is not the checker here.)  -> mean test / train score per candidate, fitted best"""
+    from sklearn.base import clone
+    from sklearn.model_selection import ParameterGrid, check_cv
+    splits = list(check_cv(cv, y, classifier=classifier).split(X, y))
+    cands = list(ParameterGrid(grid))
+    te = np.zeros((len(cands), len(splits)))
+    tr = np.zeros_like(te)
+    for ci, p in enumerate(cands):
+        for k, (a, b) in enumerate(splits):
+            m = clone(est).set_params(**p).fit(X[a], y[a], sample_weight=sw[a])
+            te[ci, k], tr[ci, k] = m.score(X[b], y[b]), m.score(X[a], y[a])
+    best = int(np.argmax(te.mean(1)))
+    return te.mean(1), tr.mean(1), cands[best], clone(est).set_params(**cands[best]).fit(X, y, sample_weight=sw)
+
+
 def test_sample_weight_fit_params_linear_models(engine):
-    """fit_params={'sample_weight': w} (reference base_search.py:69,83-87): the fit is weighted, the scores are not.
-    Checker: scikit-learn's GridSearchCV.fit(X, y, sample_weight=w)."""
+    """fit_params={'sample_weight': w} (reference base_search.py:69,83-87): the fit is weighted, the scores are not."""
     from sklearn.linear_model import ElasticNet, Lasso, Ridge
-    from sklearn.model_selection import GridSearchCV as SkGrid, ShuffleSplit
+    from sklearn.model_selection import ShuffleSplit
     from spark_sklearn_b200 import GridSearchCV
     w = W.make_workload("lasso_small")
     X, y = w["X"], w["y"]
@@ -155,14 +172,15 @@ def test_sample_weight_fit_params_linear_models(engine):
                           (Lasso(), {"alpha": [0.05, 2.0, 40.0]}, 4),
                           (ElasticNet(), {"alpha": [0.1, 3.0], "l1_ratio": [0.3, 0.8]}, ShuffleSplit(3, test_size=0.25, random_state=1))):
         a = GridSearchCV(None, est, grid, cv=cv, iid=False, fit_params={"sample_weight": sw}).fit(X, y)
-        b = SkGrid(est, grid, cv=cv, return_train_score=True).fit(X, y, sample_weight=sw)
-        u = SkGrid(est, grid, cv=cv, return_train_score=True).fit(X, y)
-        for key in ("mean_test_score", "mean_train_score"):
-            np.testing.assert_allclose(a.cv_results_[key], b.cv_results_[key], atol=5e-5, err_msg="%s %s" % (type(est).__name__, key))
-        assert np.abs(b.cv_results_["mean_train_score"] - u.cv_results_["mean_train_score"]).max() > 1e-4      # the weights matter
-        assert a.best_params_ == b.best_params_
-        np.testing.assert_allclose(a.best_estimator_.coef_, b.best_estimator_.coef_, atol=3e-4 * np.abs(b.best_estimator_.coef_).max())
-        np.testing.assert_allclose(a.best_estimator_.intercept_, b.best_estimator_.intercept_, atol=2e-3)
+        te, tr, best, fitted = _reference_tasks(est, grid, cv, X, y, sw)
+        u = GridSearchCV(None, est, grid, cv=cv, iid=False).fit(X, y)
+        name = type(est).__name__
+        np.testing.assert_allclose(a.cv_results_["mean_test_score"], te, atol=5e-5, err_msg=name)
+        np.testing.assert_allclose(a.cv_results_["mean_train_score"], tr, atol=5e-5, err_msg=name)
+        assert np.abs(a.cv_results_["mean_train_score"] - u.cv_results_["mean_train_score"]).max() > 1e-5, name   # the weights matter
+        assert a.best_params_ == best
+        np.testing.assert_allclose(a.best_estimator_.coef_, fitted.coef_, atol=3e-4 * np.abs(fitted.coef_).max())
+        np.testing.assert_allclose(a.best_estimator_.intercept_, fitted.intercept_, atol=2e-3)
     from sklearn.svm import SVC
     wc = W.make_workload("c2_small")
     with pytest.raises(NotImplementedError):
