@@ -304,8 +304,12 @@ class Runner:
         if self.dist is not None:
             self.dist.all_reduce(tm, op=self.dist.ReduceOp.MAX)
             self.dist.all_reduce(ts, op=self.dist.ReduceOp.SUM)
+        tavg = torch.tensor([acc.get(k, 0.0) for k in keys_max], dtype=torch.float64, device="cuda")
+        if self.dist is not None:
+            self.dist.all_reduce(tavg, op=self.dist.ReduceOp.SUM)
         r = dict(zip(keys_max + ["wall", "e2e_wall"], [float(x) for x in tm.cpu()]))
         r.update(zip(keys_sum, [float(x) for x in ts.cpu()]))
+        r["phase_mean"] = dict(zip(keys_max, [float(x) / max(self.world, 1) for x in tavg.cpu()]))
         r.update(test=out["test"], e2e_prof=e2e_prof, clocks=clocks, steps=steps)
         return r
 
@@ -467,6 +471,9 @@ def main():
                 "h2d_bytes_per_step": int(m["e2e_prof"].get("h2d_bytes", 0)), "d2h_bytes_per_step": int(m["e2e_prof"].get("d2h_bytes", 0)),
                 "api": "spark_sklearn_b200.GridSearchCV(sc=None, ..., refit=False).fit(X, y) with host numpy arrays"},
         "gpu_launches": int(m["launches"]), "smo_iterations_per_step": m["smo_iterations"] / K,
+        # device ms per step of the phases of a search (CUDA events on the engine stream): slowest rank / mean over the ranks
+        "phases_ms": {k[3:]: {"max": m[k] / K, "mean": m["phase_mean"][k] / K}
+                      for k in ("ms_total", "ms_gram", "ms_kernel_matrix", "ms_solve", "ms_score")},
         "roofline": roofline, "gram_roofline": gram_roofline, "clocks": m["clocks"],
         "best_mean_test_score": float(np.max(np.mean(test_scores, 1))),
         "parity": parity_block(w, test_scores),

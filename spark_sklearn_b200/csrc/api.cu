@@ -774,16 +774,20 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
         tm.mark(2);
         // -- score (skipped for refit) --
         if (!refit) {
-            int max_cols = 0;
-            for (int g = g0; g < g1; g++) max_cols = std::max(max_cols, group_first[g - g0 + 1] - group_first[g - g0]);
-            const int jch = decision_chunks(n);
-            if (jch > 1) GS_CUDA(h->dWork[8].reserve((size_t)jch * max_cols * n * 8));      // partial sums of the j-chunks
+            size_t part_doubles = 0;                                              // partial sums of the j-slabs
+            std::vector<int> jch(g1 - g0, 1);
             for (int g = g0; g < g1; g++) {
-                const int c0 = group_first[g - g0], c1 = group_first[g - g0 + 1];
+                const int cols = group_first[g - g0 + 1] - group_first[g - g0];
+                jch[g - g0] = decision_chunks(n, cols, h->sm_count);
+                if (jch[g - g0] > 1) part_doubles = std::max(part_doubles, (size_t)jch[g - g0] * cols * n);
+            }
+            if (part_doubles) GS_CUDA(h->dWork[8].reserve(part_doubles * 8));
+            for (int g = g0; g < g1; g++) {
+                const int c0 = group_first[g - g0], c1 = group_first[g - g0 + 1], jc = jch[g - g0];
                 GS_CUDA(launch_decision(h->dS.as<double>(), h->dXsq.as<double>(), n, groups[g].first, groups[g].second,
                                         h->dWork[3].as<double>() + (size_t)c0 * n, c1 - c0,
-                                        h->dWork[4].as<double>() + (size_t)c0 * n, jch > 1 ? h->dWork[8].as<double>() : nullptr, st));
-                pf.launches += jch > 1 ? 2 : 1;
+                                        h->dWork[4].as<double>() + (size_t)c0 * n, jc > 1 ? h->dWork[8].as<double>() : nullptr, jc, st));
+                pf.launches += jc > 1 ? 2 : 1;
             }
             const int kind = h->score_kind, nvt = (int)vtasks.size();
             if (kind == GS_SCORE_DEFAULT) {

@@ -176,9 +176,11 @@ cudaError_t launch_smo_colown(const SmoProblem *d_probs, const int *d_order, int
 // ---- score.cu ----
 // dec[c][r] = sum_j k64(r, j) * coef[c][j]  (float64 kernel values recomputed from S, not the
 // float32-rounded K: svm.cpp:2821 svm_predict_values uses k_function in double).
-int decision_chunks(int n);
+// decision_chunks: into how many slabs the support-row range of one launch is split so that its CTAs fill the GPU in whole
+// rounds (157 row blocks on 592 resident CTAs: 4 slabs = 628 CTAs = two rounds for 1.06 rounds of work; 15 slabs = 3.98).
+int decision_chunks(int n, int ncols, int sms);
 cudaError_t launch_decision(const double *S, const double *xsq, int n, int kernel, double gamma,
-                            const double *coef, int ncols, double *dec, double *part, cudaStream_t st);
+                            const double *coef, int ncols, double *dec, double *part, int jchunks, cudaStream_t st);
 struct VoteTask {          // one (candidate, fold) task
     int first_col;         // first decision column of this task inside its group (n_pairs consecutive)
     int fold;              // test fold id

@@ -281,15 +281,49 @@ cudaError_t launch_auc_pairs_f32(const float *score, int64_t ld, int n, int n_a,
     return cudaGetLastError();
 }
 
-// part: workspace of at least jchunks * ncols * n doubles when jchunks > 1 (see decision_chunks)
-int decision_chunks(int n) { return n >= 4096 ? 4 : 1; }
+// resident CTAs per SM of the instance that serves `tc` columns (queried once per instance)
+static int decision_ctas_per_sm(int tc)
+{
+    static int cache[13] = {0};
+    const int slot = tc / 8;
+    if (cache[slot] == 0) {
+        int nb = 0;
+#define GS_OCC(T) case T: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decision_kernel<T>, 256, 0); break;
+        switch (tc) {
+            GS_OCC(8) GS_OCC(16) GS_OCC(24) GS_OCC(32) GS_OCC(40) GS_OCC(48) GS_OCC(56) GS_OCC(64) GS_OCC(72) GS_OCC(80) GS_OCC(88)
+            default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decision_kernel<96>, 256, 0); break;
+        }
+#undef GS_OCC
+        cache[slot] = nb > 0 ? nb : 1;
+    }
+    return cache[slot];
+}
+
+// part: workspace of at least jchunks * ncols * n doubles when jchunks > 1.
+// The CTAs of a launch take the same time, so a launch costs ceil(CTAs / resident CTAs) rounds; the slab count with the
+// fewest rounds per unit of work wins (config 2: 40 columns, 4 CTAs/SM -> 15 slabs instead of 4: 3.98 rounds of 1/15 against
+// 2 rounds of 1/4).  Short ranges are not split (each slab keeps >= 8 tiles of TJ support rows).
+int decision_chunks(int n, int ncols, int sms)
+{
+    if (n < 4096 || ncols <= 0) return 1;
+    const int tc = std::min(96, (ncols + 7) / 8 * 8);
+    const long long slots = (long long)sms * decision_ctas_per_sm(tc);
+    const long long base = (long long)((n + TR - 1) / TR) * ((ncols + tc - 1) / tc);
+    int best = 1;
+    double best_cost = 1e30;
+    for (int jc = 1; jc <= 16 && n / jc >= 8 * TJ; jc++) {
+        const double cost = (double)((base * jc + slots - 1) / slots) / jc;
+        if (cost < best_cost - 1e-12) { best_cost = cost; best = jc; }
+    }
+    return best;
+}
 
 cudaError_t launch_decision(const double *S, const double *xsq, int n, int kernel, double gamma,
-                            const double *coef, int ncols, double *dec, double *part, cudaStream_t st)
+                            const double *coef, int ncols, double *dec, double *part, int jchunks, cudaStream_t st)
 {
     if (ncols <= 0) return cudaSuccess;
     const int tc = std::min(96, (ncols + 7) / 8 * 8);
-    const int jchunks = part ? decision_chunks(n) : 1;
+    if (!part || jchunks < 1) jchunks = 1;
     const int jlen = ((n + jchunks - 1) / jchunks + TJ - 1) / TJ * TJ;
     dim3 grid((n + TR - 1) / TR, (ncols + tc - 1) / tc, jchunks);
     double *out = jchunks > 1 ? part : dec;
