@@ -362,10 +362,10 @@ extern "C" int32_t gs_svc_cluster_count(const double *cost_desc, int32_t n, int3
 
 // Three-tier schedule of the slot-layout solver (smo_lean.cu): how many of the predicted-longest problems go on 4-CTA
 // clusters (n_cluster) and how many of the next-longest get an SM to themselves (n_exclusive); the rest run two per SM.
-// Measured per-iteration times of an 8000-row sub-problem (profiles/r02_smo_*): 3.55 us on a 4-CTA cluster, 5.8 us alone on
-// an SM, 10.5 us when two share an SM (= 5.25 us of SM time per iteration; a cluster costs 14.2).  Only the RATIOS enter:
+// Measured per-iteration times of an 8000-row sub-problem (profiles/r02_smo_*): 3.55 us on a 4-CTA cluster, 5.4-5.5 us alone on
+// an SM (1024 threads x 8 slots), 10.5 us when two share an SM (= 5.25 us of SM time per iteration; a cluster costs 14.2).  Only the RATIOS enter:
 //   T(n_cl, n_ex) = max( 0.34 c[0]                                       longest clustered problem
-//                        0.55 c[n_cl]                                    longest exclusive problem
+//                        0.52 c[n_cl]                                    longest exclusive problem
 //                        0.50 sum(rest) / SMs left, 0.78 c[n_cl + n_ex]  shared SMs: throughput, and the longest shared
 //                                                                        problem (paired for most of its life, alone at the end) )
 // in units of (cost x shared-SM iteration time).  More specialised SMs only for a clear (3 %) predicted gain.
@@ -384,7 +384,7 @@ extern "C" void gs_svc_schedule(const double *cost_desc, int32_t n, int32_t sm_c
             const int left = sm_count - 4 * nc - ne;
             double t = std::max(0.50 * suffix[nc + ne] / left, 0.78 * cost_desc[nc + ne]);
             if (nc > 0) t = std::max(t, 0.34 * cost_desc[0]);
-            if (ne > 0) t = std::max(t, 0.55 * cost_desc[nc]);
+            if (ne > 0) t = std::max(t, 0.52 * cost_desc[nc]);
             if (best < 0 || t < 0.97 * best || (t < best && nc + ne <= bc + be)) { best = t; bc = nc; be = ne; }
         }
     }
@@ -844,6 +844,30 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
             // a task whose solve went non-finite scores NaN; the caller applies error_score to THAT task only
             // (reference base_search.py:69,87: _fit_and_score(..., error_score) fills per task)
             if (!std::isfinite(rho[q])) { if (refit) { gs_set_error(h, "gs_svc_refit: non-finite intercept"); return GS_ERR_NUMERIC; } task_bad[t] = 1; }
+        }
+        if (getenv("B200GS_SMO_TIMELINE") && atoi(getenv("B200GS_SMO_TIMELINE"))) {
+            // development aid: when each tier starts and ends (globaltimer of the sub-problems, ms after the first start)
+            unsigned long long t0 = ~0ull;
+            for (int q = 0; q < np; q++) if (ns[(size_t)q * 12]) t0 = std::min(t0, ns[(size_t)q * 12]);
+            auto span = [&](int a, int b, const char *name) {
+                if (b <= a) return;
+                double s0 = 1e30, s1 = 0, e0 = 1e30, e1 = 0; long long it_max = 0;
+                for (int i = a; i < b; i++) {
+                    const int q = order[i];
+                    const double st_ = (double)(ns[(size_t)q * 12] - t0) * 1e-6, en = (double)(ns[(size_t)q * 12 + 1] - t0) * 1e-6;
+                    s0 = std::min(s0, st_); s1 = std::max(s1, st_); e0 = std::min(e0, en); e1 = std::max(e1, en);
+                    it_max = std::max<long long>(it_max, info[(size_t)q * 4]);
+                }
+                fprintf(stderr, "[timeline] %-9s %4d problems: starts %.2f..%.2f ms, ends %.2f..%.2f ms, longest %lld iterations\n",
+                        name, b - a, s0, s1, e0, e1, it_max);
+            };
+            span(0, n_cl, "cluster"); span(n_cl, n_cl + n_ex, "exclusive"); span(n_cl + n_ex, np, "shared");
+            for (int i = 0; i < std::min(np, 16); i++) {
+                const int q = order[i];
+                fprintf(stderr, "[timeline]   #%d: %d iterations, %.2f -> %.2f ms (%.3f us/iteration)\n", i, info[(size_t)q * 4],
+                        (double)(ns[(size_t)q * 12] - t0) * 1e-6, (double)(ns[(size_t)q * 12 + 1] - t0) * 1e-6,
+                        (double)(ns[(size_t)q * 12 + 1] - ns[(size_t)q * 12]) * 1e-3 / std::max(1, info[(size_t)q * 4]));
+            }
         }
         if (getenv("B200GS_SMO_PROF") && atoi(getenv("B200GS_SMO_PROF"))) {
             int qmax = 0;

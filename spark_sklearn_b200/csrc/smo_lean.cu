@@ -156,7 +156,7 @@ struct LeanRed {                                      // static shared scratch; 
 // update (no third barrier: latency).  Otherwise two sub-problems share the SM and issue slots are the scarce resource: warp 0
 // evaluates it once and the others wait at a third barrier, which the co-resident CTA fills.
 template <int NT, int G, bool FAST, bool PROF, bool SOLO>
-__global__ void __launch_bounds__(NT, (NT * G >= 4096 ? 1 : 2048 / (NT * G / 2) > 8 ? 8 : 2048 / (NT * G / 2)))
+__global__ void __launch_bounds__(NT, (NT * G >= 4096 || NT >= 1024 ? 1 : 2048 / (NT * G / 2) > 8 ? 8 : 2048 / (NT * G / 2)))
 smo_lean_kernel(const SmoProblem *__restrict__ probs, const int *__restrict__ order)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -974,8 +974,16 @@ cudaError_t launch_smo_lean(const SmoProblem *d_probs, const int *d_order, int n
     if (env_int("B200GS_SMO_NOFAST", 0)) fast = false;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    bool solo = exclusive || n_prob <= sms;                                  // nobody shares this problem's SM
+    // Two instances of the two-variable update: warp 0 evaluates it behind a third barrier, or every warp evaluates it
+    // redundantly (SOLO).  Same-box A/B on config 2 (tools/exp_solo2.sh): the barrier instance is faster in BOTH tiers
+    // (exclusive SM: 5.62 vs 5.83-5.92 us per iteration; shared SMs finish at 233 vs 248 ms), so it is the default.
+    bool solo = false;
     if (const char *e = getenv("B200GS_LEAN_SOLO")) solo = atoi(e) != 0;      // development switch
+    (void)sms;
+    // A problem alone on its SM spreads over 1024 threads x 8 slots instead of 512 x 16: 5.38-5.49 against 5.65-5.72 us per
+    // iteration on config 2's 8000-row problems (tools/exp_wide.sh; bit-identical trajectories).  B200GS_LEAN_EXCL_WIDE=0: off.
+    if (exclusive && max_slots > 4096 && max_slots <= 8192 && env_int("B200GS_LEAN_EXCL_WIDE", 1))
+        return launch_lean_cfg<1024, 2>(d_probs, d_order, n_prob, fast, prof, exclusive, solo, st);
     if (max_slots <= 2048) return launch_lean_cfg<128, 4>(d_probs, d_order, n_prob, fast, prof, exclusive, solo, st);
     if (max_slots <= 4096) return launch_lean_cfg<256, 4>(d_probs, d_order, n_prob, fast, prof, exclusive, solo, st);
     if (max_slots <= 8192) return launch_lean_cfg<512, 4>(d_probs, d_order, n_prob, fast, prof, exclusive, solo, st);
