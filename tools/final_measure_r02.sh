@@ -10,5 +10,5 @@ python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_o
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r02.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-secondary > gpurun_out/bench_under_ncu.log 2>&1
 python tools/summarize_launches.py gpurun_out/launches_r02.csv | head -30
-bash tools/exp_ncu_new.sh
+[ "${NCU_NEW:-0}" = "1" ] && bash tools/exp_ncu_new.sh
 echo done
