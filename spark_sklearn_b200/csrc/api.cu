@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <mutex>
+#include <queue>
 #include <numeric>
 
 static std::string g_create_error;
@@ -362,31 +364,125 @@ extern "C" int32_t gs_svc_cluster_count(const double *cost_desc, int32_t n, int3
 
 // Three-tier schedule of the slot-layout solver (smo_lean.cu): how many of the predicted-longest problems go on 4-CTA
 // clusters (n_cluster) and how many of the next-longest get an SM to themselves (n_exclusive); the rest run two per SM.
-// Measured per-iteration times of an 8000-row sub-problem (profiles/r02_smo_*): 3.55 us on a 4-CTA cluster, 5.4-5.5 us alone on
-// an SM (1024 threads x 8 slots), 10.5 us when two share an SM (= 5.25 us of SM time per iteration; a cluster costs 14.2).  Only the RATIOS enter:
-//   T(n_cl, n_ex) = max( 0.34 c[0]                                       longest clustered problem
-//                        0.52 c[n_cl]                                    longest exclusive problem
-//                        0.50 sum(rest) / SMs left, 0.78 c[n_cl + n_ex]  shared SMs: throughput, and the longest shared
-//                                                                        problem (paired for most of its life, alone at the end) )
-// in units of (cost x shared-SM iteration time).  More specialised SMs only for a clear (3 %) predicted gain.
+//
+// The makespan of a candidate split is SIMULATED, not bounded by a formula: the block scheduler hands every SM that a
+// finished cluster or exclusive problem gives back to the pending CTAs of the shared launch, so "SMs left for the shared
+// tier" is not a constant (the closed form used before under-used clusters whenever a second class of long problems
+// existed: 292 instead of ~255 ms of solve on the ranks of the 8-GPU weak-scaling grid).  Inputs are the measured
+// per-iteration times of an 8000-row sub-problem (profiles/r02_smo_*; only their RATIOS matter): 3.55 us on a 4-CTA
+// cluster, 5.45 us alone on an SM, 9.4 us each when two share an SM.  Checked against tier timelines measured on config 2
+// (B200GS_SMO_TIMELINE) and against forced splits of config 4 (0 / 20 / 40 / 70 exclusive problems: the order is right,
+// the values 3 % high).
+namespace {
+constexpr double RATE_CLUSTER = 3.55, RATE_SOLO = 5.45, RATE_PAIR = 9.4;
+
+// Event simulation of one launch: cost_desc[0..nc) on clusters (4 SMs each), [nc, nc+ne) alone on an SM, the others in
+// launch order on the two slots of every SM as it becomes free.  Returns the makespan in cost x rate units.
+double simulate_tiers(const double *c, int n, int sms, int nc, int ne)
+{
+    if (nc < 0 || ne < 0 || nc + ne > n || 4 * nc + ne > sms) return 1e300;
+    struct Ev { double t; int sm, slot, ver; bool operator<(const Ev &o) const { return t > o.t; } };
+    struct Sm { double rem[2] = {0, 0}; bool busy[2] = {false, false}; int ver[2] = {0, 0}; double last = 0; };
+    std::vector<Sm> sm(sms);
+    std::priority_queue<Ev> ev;
+    double end = 0;
+    int s = 0;
+    for (int i = 0; i < nc; i++) { const double t = c[i] * RATE_CLUSTER; end = std::max(end, t); for (int k = 0; k < 4; k++) ev.push(Ev{t, s++, -1, 0}); }
+    for (int i = 0; i < ne; i++) { const double t = c[nc + i] * RATE_SOLO; end = std::max(end, t); ev.push(Ev{t, s++, -1, 0}); }
+    for (; s < sms; s++) ev.push(Ev{0.0, s, -1, 0});
+    int next = nc + ne;
+    auto resched = [&](int q, double t) {
+        Sm &m = sm[q];
+        const double per = (m.busy[0] && m.busy[1]) ? RATE_PAIR : RATE_SOLO;
+        for (int k = 0; k < 2; k++)
+            if (m.busy[k]) ev.push(Ev{t + m.rem[k] * per, q, k, ++m.ver[k]});
+    };
+    while (!ev.empty()) {
+        const Ev e = ev.top(); ev.pop();
+        Sm &m = sm[e.sm];
+        if (e.slot < 0) {                                           // the SM joins the shared tier
+            m.last = e.t;
+            for (int k = 0; k < 2 && next < n; k++) { m.rem[k] = c[next++]; m.busy[k] = true; }
+            resched(e.sm, e.t);
+            continue;
+        }
+        if (!m.busy[e.slot] || e.ver != m.ver[e.slot]) continue;     // superseded by a rate change
+        const double rate = 1.0 / ((m.busy[0] && m.busy[1]) ? RATE_PAIR : RATE_SOLO), dt = e.t - m.last;
+        for (int k = 0; k < 2; k++)
+            if (m.busy[k]) m.rem[k] = std::max(0.0, m.rem[k] - dt * rate);
+        m.last = e.t;
+        m.busy[e.slot] = false;
+        end = std::max(end, e.t);
+        if (next < n) { m.rem[e.slot] = c[next++]; m.busy[e.slot] = true; }
+        resched(e.sm, e.t);
+    }
+    return end;
+}
+}  // namespace
+
+extern "C" double gs_svc_simulate(const double *cost_desc, int32_t n, int32_t sm_count, int32_t n_cluster, int32_t n_exclusive)
+{
+    if (!cost_desc || n < 1 || sm_count < 1) return 0.0;
+    return simulate_tiers(cost_desc, n, sm_count, n_cluster, n_exclusive);
+}
+
 extern "C" void gs_svc_schedule(const double *cost_desc, int32_t n, int32_t sm_count, int32_t *n_cluster, int32_t *n_exclusive)
 {
     if (n_cluster) *n_cluster = 0;
     if (n_exclusive) *n_exclusive = 0;
     if (!cost_desc || n < 2 || sm_count < 8) return;
+    // a repeated search of the same shape re-uses the last answer
+    static std::mutex mu;
+    static std::vector<double> last_cost;
+    static int last_sms = 0, last_c = 0, last_e = 0;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (last_sms == sm_count && (int)last_cost.size() == n && std::equal(last_cost.begin(), last_cost.end(), cost_desc)) {
+            if (n_cluster) *n_cluster = last_c;
+            if (n_exclusive) *n_exclusive = last_e;
+            return;
+        }
+    }
+    const double *c = cost_desc;
     std::vector<double> suffix(n + 1, 0.0);
-    for (int q = n - 1; q >= 0; q--) suffix[q] = suffix[q + 1] + cost_desc[q];
-    double best = -1;
+    for (int q = n - 1; q >= 0; q--) suffix[q] = suffix[q + 1] + c[q];
+    // candidates: tier boundaries at changes of the predicted cost (the folds of one candidate stay in one tier)
+    std::vector<int> cut;
+    for (int q = 0; q <= n - 1; q++)
+        if (q == 0 || c[q - 1] > c[q] * (1.0 + 1e-9)) cut.push_back(q);
+    double best = simulate_tiers(c, n, sm_count, 0, 0);
     int bc = 0, be = 0;
     const int max_cl = std::min(n - 1, sm_count / 4);
-    for (int nc = 0; nc <= max_cl; nc++) {
-        for (int ne = 0; nc + ne < n && 4 * nc + ne <= sm_count - 8; ne++) {
-            const int left = sm_count - 4 * nc - ne;
-            double t = std::max(0.50 * suffix[nc + ne] / left, 0.78 * cost_desc[nc + ne]);
-            if (nc > 0) t = std::max(t, 0.34 * cost_desc[0]);
-            if (ne > 0) t = std::max(t, 0.52 * cost_desc[nc]);
-            if (best < 0 || t < 0.97 * best || (t < best && nc + ne <= bc + be)) { best = t; bc = nc; be = ne; }
+    // at most ~12 x 24 candidate splits (costs that are all distinct, e.g. one-vs-one pairs of different sizes, would
+    // otherwise give one boundary per problem): every k-th boundary among those a tier can reach
+    std::vector<int> cut_c, cut_e;
+    for (int q : cut) { if (q <= max_cl) cut_c.push_back(q); if (q <= sm_count - 8) cut_e.push_back(q); }
+    auto thin = [](std::vector<int> &v, size_t keep) {
+        if (v.size() <= keep) return;
+        std::vector<int> w;
+        for (size_t i = 0; i < keep; i++) w.push_back(v[i * (v.size() - 1) / (keep - 1)]);
+        w.erase(std::unique(w.begin(), w.end()), w.end());
+        v.swap(w);
+    };
+    thin(cut_c, 12); thin(cut_e, 24);
+    for (int nc : cut_c) {
+        for (int pos : cut_e) {
+            const int ne = pos - nc;
+            if (ne < 0 || (nc == 0 && ne == 0)) continue;
+            if (4 * nc + ne > sm_count - 8 || nc + ne >= n) break;
+            // lower bounds: the longest problem of every tier, and the SM time of the whole split
+            double lb = std::max(nc ? c[0] * RATE_CLUSTER : 0.0, std::max(ne ? c[nc] * RATE_SOLO : 0.0, c[nc + ne] * RATE_SOLO));
+            lb = std::max(lb, (4.0 * RATE_CLUSTER * (suffix[0] - suffix[nc]) + RATE_SOLO * (suffix[nc] - suffix[nc + ne]) +
+                               0.5 * RATE_PAIR * suffix[nc + ne]) / sm_count);
+            if (lb >= 0.985 * best) continue;
+            const double t = simulate_tiers(c, n, sm_count, nc, ne);
+            // specialised SMs only for a clear (1.5 %) predicted gain; near-ties go to the split that uses fewer of them
+            if (t < 0.985 * best || (t < best && 4 * nc + ne <= 4 * bc + be)) { best = t; bc = nc; be = ne; }
         }
+    }
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        last_cost.assign(cost_desc, cost_desc + n); last_sms = sm_count; last_c = bc; last_e = be;
     }
     if (n_cluster) *n_cluster = bc;
     if (n_exclusive) *n_exclusive = be;
