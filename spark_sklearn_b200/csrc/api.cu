@@ -364,11 +364,42 @@ extern "C" int32_t gs_svc_cluster_count(const double *cost_desc, int32_t n, int3
 
 // Three-tier schedule of the slot-layout solver (smo_lean.cu): how many of the predicted-longest problems go on 4-CTA
 // clusters (n_cluster) and how many of the next-longest get an SM to themselves (n_exclusive); the rest run two per SM.
-//
-// The makespan of a candidate split is SIMULATED, not bounded by a formula: the block scheduler hands every SM that a
-// finished cluster or exclusive problem gives back to the pending CTAs of the shared launch, so "SMs left for the shared
-// tier" is not a constant (the closed form used before under-used clusters whenever a second class of long problems
-// existed: 292 instead of ~255 ms of solve on the ranks of the 8-GPU weak-scaling grid).  Inputs are the measured
+// Measured per-iteration times of an 8000-row sub-problem (profiles/r02_smo_*): 3.55 us on a 4-CTA cluster, 5.4-5.5 us alone on
+// an SM (1024 threads x 8 slots), 10.5 us when two share an SM (= 5.25 us of SM time per iteration; a cluster costs 14.2).  Only the RATIOS enter:
+//   T(n_cl, n_ex) = max( 0.34 c[0]                                       longest clustered problem
+//                        0.52 c[n_cl]                                    longest exclusive problem
+//                        0.50 sum(rest) / SMs left, 0.78 c[n_cl + n_ex]  shared SMs: throughput, and the longest shared
+//                                                                        problem (paired for most of its life, alone at the end) )
+// in units of (cost x shared-SM iteration time).  More specialised SMs only for a clear (3 %) predicted gain.
+static void schedule_closed_form(const double *cost_desc, int32_t n, int32_t sm_count, int32_t *n_cluster, int32_t *n_exclusive)
+{
+    if (n_cluster) *n_cluster = 0;
+    if (n_exclusive) *n_exclusive = 0;
+    if (!cost_desc || n < 2 || sm_count < 8) return;
+    std::vector<double> suffix(n + 1, 0.0);
+    for (int q = n - 1; q >= 0; q--) suffix[q] = suffix[q + 1] + cost_desc[q];
+    double best = -1;
+    int bc = 0, be = 0;
+    const int max_cl = std::min(n - 1, sm_count / 4);
+    for (int nc = 0; nc <= max_cl; nc++) {
+        for (int ne = 0; nc + ne < n && 4 * nc + ne <= sm_count - 8; ne++) {
+            const int left = sm_count - 4 * nc - ne;
+            double t = std::max(0.50 * suffix[nc + ne] / left, 0.78 * cost_desc[nc + ne]);
+            if (nc > 0) t = std::max(t, 0.34 * cost_desc[0]);
+            if (ne > 0) t = std::max(t, 0.52 * cost_desc[nc]);
+            if (best < 0 || t < 0.97 * best || (t < best && nc + ne <= bc + be)) { best = t; bc = nc; be = ne; }
+        }
+    }
+    if (n_cluster) *n_cluster = bc;
+    if (n_exclusive) *n_exclusive = be;
+}
+
+// Alternative (B200GS_SCHEDULE=simulate; also the test hook gs_svc_simulate): the makespan of a candidate split is SIMULATED,
+// not bounded by a formula: the block scheduler hands every SM that a finished cluster or exclusive problem gives back to
+// the pending CTAs of the shared launch, so "SMs left for the shared tier" is not a constant.  Measured (1 x B200 and
+// 8 x B200, tools/exp_sched2.sh, tools/exp_scale8.sh): config 2 255.0 vs 254.7 ms of solve, config 4 identical, the 8-GPU
+// weak-scaling step 321.9 vs 315.7 ms (its choice of 15 clusters for the ranks that hold a second class of long problems
+// did not shorten their solve phase) -- no gain, so the closed form above stays the default.  Inputs are the measured
 // per-iteration times of an 8000-row sub-problem (profiles/r02_smo_*; only their RATIOS matter): 3.55 us on a 4-CTA
 // cluster, 5.45 us alone on an SM, 9.4 us each when two share an SM.  Checked against tier timelines measured on config 2
 // (B200GS_SMO_TIMELINE) and against forced splits of config 4 (0 / 20 / 40 / 70 exclusive problems: the order is right,
@@ -426,7 +457,7 @@ extern "C" double gs_svc_simulate(const double *cost_desc, int32_t n, int32_t sm
     return simulate_tiers(cost_desc, n, sm_count, n_cluster, n_exclusive);
 }
 
-extern "C" void gs_svc_schedule(const double *cost_desc, int32_t n, int32_t sm_count, int32_t *n_cluster, int32_t *n_exclusive)
+static void schedule_simulated(const double *cost_desc, int32_t n, int32_t sm_count, int32_t *n_cluster, int32_t *n_exclusive)
 {
     if (n_cluster) *n_cluster = 0;
     if (n_exclusive) *n_exclusive = 0;
@@ -486,6 +517,13 @@ extern "C" void gs_svc_schedule(const double *cost_desc, int32_t n, int32_t sm_c
     }
     if (n_cluster) *n_cluster = bc;
     if (n_exclusive) *n_exclusive = be;
+}
+
+extern "C" void gs_svc_schedule(const double *cost_desc, int32_t n, int32_t sm_count, int32_t *n_cluster, int32_t *n_exclusive)
+{
+    const char *mode = getenv("B200GS_SCHEDULE");
+    if (mode && !strcmp(mode, "simulate")) schedule_simulated(cost_desc, n, sm_count, n_cluster, n_exclusive);
+    else schedule_closed_form(cost_desc, n, sm_count, n_cluster, n_exclusive);
 }
 
 static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double *Cv, const double *gamma,
