@@ -454,11 +454,12 @@ class RidgePlan(_Plan):
         super().__init__(estimator, cands, X, y, fold_id, n_splits, device)
         y = np.asarray(y)
         if y.ndim != 1:
-            raise NotImplementedError("multi-output Ridge is not supported by the CUDA path")
+            raise NotImplementedError("multi-output %s is not supported by the CUDA path" % type(estimator).__name__)
         if self.X.dtype != np.float32:
             # scikit-learn solves float64 input in float64; the tensor-core Grams are fp32-faithful (3xTF32 split)
-            warnings.warn("spark_sklearn_b200 Ridge computes in float32: float64 X is rounded to float32 before the "
-                          "search (scores agree with scikit-learn's float64 fit to about 1e-6 relative)", UserWarning)
+            warnings.warn("spark_sklearn_b200 %s computes in float32: float64 X is rounded to float32 before the "
+                          "search (scores agree with scikit-learn's float64 fit to about 1e-6 relative)"
+                          % type(estimator).__name__, UserWarning)
         self._set_data(self.X.astype(np.float32, copy=False), y_target=y.astype(np.float32))
 
     def _check(self, p):

@@ -579,3 +579,47 @@ def test_simulated_schedule_opt_in(monkeypatch):
     spiky = np.r_[np.full(5, 100.0), np.ones(400)]                             # five dominant problems
     nc, ne, _ = sched(spiky)
     assert nc == 5 and ne == 0
+
+
+def test_one_step_pipeline_adapter_translates_names_and_wraps_the_refit(monkeypatch):
+    """reference tests/test_search_2.py:69-93 search Pipeline([('lasso', Lasso())]) through 'lasso__alpha': the step's own
+    plan runs with the prefix stripped (candidates, fit_params, best_params_), the refit estimator comes back inside a
+    Pipeline, foreign parameter names raise.  CPU: the step's adapter is a stub over the oracle."""
+    from sklearn.pipeline import Pipeline
+    from sklearn.svm import SVC
+    from spark_sklearn_b200 import GridSearchCV, base_search, estimators as E
+    seen = {}
+
+    class StubPlan(OraclePlan):
+        def set_fit_params(self, fp):
+            seen["fit_params"] = dict(fp or {})
+
+        def evaluate(self, my, **kw):
+            seen["cands"] = [self.cands[i] for i in my]
+            return super().evaluate(my, **kw)
+
+    class StubAdapter:
+        multi_device = False
+        scorers = {None: 0}
+        plan = staticmethod(lambda est, cands, X, y, f, n, device=None: StubPlan(est, cands, X, y, f, n))
+
+    real = E.adapter_for
+    monkeypatch.setattr(E, "adapter_for", lambda est: StubAdapter if isinstance(est, SVC) else real(est))
+    X, y = _iris()
+    pipe = Pipeline([("svc", SVC(gamma="auto"))])
+    grid = {"svc__C": [1, 10], "svc__kernel": ["linear", "rbf"]}
+    s = GridSearchCV(None, pipe, grid, cv=5, fit_params={"svc__sample_weight": None}).fit(X, y)
+    assert all(set(c) == {"C", "kernel"} for c in seen["cands"]) and seen["fit_params"] == {"sample_weight": None}
+    assert set(s.best_params_) == {"svc__C", "svc__kernel"}
+    assert isinstance(s.best_estimator_, Pipeline) and s.best_estimator_.steps[0][0] == "svc"
+    ref = SVC(gamma="auto", C=s.best_params_["svc__C"], kernel=s.best_params_["svc__kernel"]).fit(X, y)
+    np.testing.assert_array_equal(s.predict(X), ref.predict(X))
+    plain = GridSearchCV(None, SVC(gamma="auto"), {"C": [1, 10], "kernel": ["linear", "rbf"]}, cv=5)
+    monkeypatch.setattr(base_search._est, "adapter_for", lambda est: StubAdapter if isinstance(est, SVC) else real(est))
+    plain.fit(X, y)
+    np.testing.assert_array_equal(s.cv_results_["mean_test_score"], plain.cv_results_["mean_test_score"])
+    with pytest.raises(NotImplementedError):
+        GridSearchCV(None, pipe, {"memory": [None]}, cv=3).fit(X, y)
+    with pytest.raises(NotImplementedError):                                 # two steps: transformers are fitted per fold on the host
+        from sklearn.preprocessing import StandardScaler
+        E.adapter_for(Pipeline([("sc", StandardScaler()), ("svc", SVC())]))
