@@ -1,4 +1,4 @@
-// linear.cu -- Ridge search (gs_ridge / gs_ridge_refit).
+// linear.cu -- linear regressors on fold Grams: Ridge (gs_ridge / gs_ridge_refit) and Lasso / ElasticNet (gs_enet / gs_enet_refit).
 //
 // Ridge path (replaces sklearn Ridge.fit/score reached from reference base_search.py:83-87:
 // linear_model/_ridge.py:919 fit, :964 _preprocess_data centring, :215-227 _solve_cholesky, base.py:716 r2):
@@ -11,8 +11,12 @@
 //   3. (A_k + alpha I) w = rhs for ALL alphas of a fold at once by conjugate gradients whose matrix product is the
 //      same tensor-core contraction (P[alphas x d] times the symmetric A_k); the per-system vector updates and dot
 //      products are one small kernel per iteration.  Converged systems freeze; non-convergence fails loudly.
-//   4. R^2 on the held-out fold and on the training rows from the Gram statistics in float64 (quadratic forms),
-//      no pass over X.
+//   4. R^2 (or -MSE / -RMSE) on the held-out fold and on the training rows from the Gram statistics in float64, no pass over
+//      X: the quadratic forms w^T G w of all systems are one float64 tile product with a fused row-dot (ridge_quad_kernel).
+// Splits whose test sets are no partition (gs_set_splits): one Gram per training / test ROW LIST of a split instead of
+// T - G_k.  Sample weights (gs_set_sample_weight): a second, sqrt(w)-scaled copy of the row blocks gives the weighted training
+// statistics; the scores stay unweighted.  Lasso / ElasticNet: steps 1, 2 and 4 as above, step 3 is scikit-learn's cyclic
+// coordinate descent restated on (A_k, rhs) -- enet_cd_kernel below.
 // With fit_intercept the Grams are formed from SHIFTED data, Z = [X - c | y - c_y | 1] with c the column means over all
 // rows (float64 sums, rounded to float32): the raw-moment subtractions X^T X - n xbar xbar^T and yy - ys^2/n then cancel
 // nothing even when a feature's mean dwarfs its spread (scikit-learn centres before forming products, _ridge.py:964).
