@@ -720,6 +720,7 @@ static int svc_run(gs_handle *h, int n_cand, const int32_t *kernel, const double
         // device flag the kernel-matrix kernels raise: both instances are enqueued and the wrong one returns at once
         // (SmoProblem::guard), so the host never waits in the middle of a search and everything it prepares below overlaps
         // the Gram and kernel-matrix kernels already in flight.
+        if (getenv("B200GS_SMO_NOFAST") && atoi(getenv("B200GS_SMO_NOFAST"))) fast = false;   // development switch: general instance only, unguarded
         const int *d_guard = fast ? h->dWork[7].as<int>() : nullptr;
         tm.mark(1);
         // -- problems: ordered by (group, task, pair); column index == problem index --
